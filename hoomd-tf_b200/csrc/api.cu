@@ -1,0 +1,374 @@
+// extern "C" boundary of libhtf_b200.so (see include/htf_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Orchestration only: argument checks,
+// scratch ownership, kernel sequencing on the caller's stream.  No device synchronisation.
+#include "common.cuh"
+#include "../../include/htf_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+void set_err(htf_ctx *ctx, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+#define HTF_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_ == cudaErrorMemoryAllocation ? HTF_ENOMEM : HTF_ECUDA;                 \
+        }                                                                                    \
+    } while (0)
+
+template <typename T>
+int dev_realloc(htf_ctx *ctx, T **ptr, size_t count)
+{
+    if (*ptr) { cudaFree(*ptr); *ptr = nullptr; }
+    if (count == 0) count = 1;
+    HTF_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(ptr), sizeof(T) * count));
+    return HTF_OK;
+}
+
+int ensure_particles(htf_ctx *ctx, int64_t n)
+{
+    if (n <= ctx->n_cap) return HTF_OK;
+    int rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_cell_of, (size_t)n))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_sorted_idx, (size_t)n))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_spos, (size_t)n))) return rc;
+    ctx->n_cap = n;
+    return HTF_OK;
+}
+
+int ensure_cells(htf_ctx *ctx, int ncell)
+{
+    if (ncell <= ctx->ncell_cap) return HTF_OK;
+    int rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_cell_cnt, (size_t)ncell))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_cell_start, (size_t)ncell + 1))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_block_sums, (size_t)ncell / 1024 + 2))) return rc;
+    ctx->ncell_cap = ncell;
+    return HTF_OK;
+}
+
+// Cell grid for the current box and cutoff.  Any cell edge >= r_cut is correct; the edge
+// is kept 1e-4 above r_cut (see CellGrid) and the cell count is capped so that a huge,
+// nearly empty box (e.g. compute_pairwise's 1e10 box) cannot exhaust memory.
+int make_grid(htf_ctx *ctx)
+{
+    CellGrid &g = ctx->grid;
+    double budget = 2.0 * (double)(ctx->n_max > 2048 ? ctx->n_max : 2048);
+    double want[3];
+    for (int a = 0; a < 3; a++) {
+        double L = (double)g.L[a];
+        double n = std::floor(L / ((double)ctx->r_cut * (1.0 + 1e-4)));
+        if (!(n >= 1.0)) n = 1.0;
+        if (n > 1024.0) n = 1024.0;
+        want[a] = n;
+    }
+    while (want[0] * want[1] * want[2] > budget) {
+        int big = 0;
+        for (int a = 1; a < 3; a++) if (want[a] > want[big]) big = a;
+        if (want[big] <= 1.0) break;
+        want[big] = std::floor(want[big] * 0.8);
+        if (want[big] < 1.0) want[big] = 1.0;
+    }
+    g.ncell = 1;
+    for (int a = 0; a < 3; a++) {
+        g.n[a] = (int)want[a];
+        g.inv_w[a] = (float)((double)g.n[a] / (double)g.L[a]);
+        g.ncell *= g.n[a];
+    }
+    ctx->binned = false;
+    return ensure_cells(ctx, g.ncell);
+}
+
+int check_ctx(htf_ctx *ctx)
+{
+    if (!ctx) { set_err(nullptr, "null context"); return HTF_EINVAL; }
+    return HTF_OK;
+}
+
+int upload_rdf_table(htf_ctx *ctx, float r_lo, float r_hi, int nbins, cudaStream_t st)
+{
+    if (nbins < 1 || !(r_hi > r_lo)) { set_err(ctx, "rdf: need nbins >= 1 and r_hi > r_lo"); return HTF_EINVAL; }
+    if (ctx->d_rdf_thr && ctx->rdf_lo == r_lo && ctx->rdf_hi == r_hi && ctx->rdf_nbins == nbins) return HTF_OK;
+    const int nb = nbins + 2;
+    std::vector<float> thr((size_t)nb + 1);
+    htf_rdf_thresholds(r_lo, r_hi, nbins, thr.data());
+    if (ctx->rdf_nbins != nbins || !ctx->d_rdf_thr) {
+        int rc = dev_realloc(ctx, &ctx->d_rdf_thr, (size_t)nb + 1);
+        if (rc) return rc;
+    }
+    // pageable source: the runtime stages it before returning, so `thr` may go out of scope
+    HTF_CUDA(ctx, cudaMemcpyAsync(ctx->d_rdf_thr, thr.data(), sizeof(float) * ((size_t)nb + 1),
+                                  cudaMemcpyHostToDevice, st));
+    ctx->rdf_lo = r_lo; ctx->rdf_hi = r_hi; ctx->rdf_nbins = nbins;
+    return HTF_OK;
+}
+
+}  // namespace
+
+// bin(q) of the reference for a squared distance q: r = fp32 sqrt, TF CPU
+// histogram_fixed_width rule (double step, truncation).  Monotone in q, so the kernel only
+// needs the nb-1 switch points; they are found by bisection over fp32 bit patterns.
+static int rdf_bin_of_q(float q, float r_lo, double step, int nb)
+{
+    float r = sqrtf(q);
+    float v = r > r_lo ? r : r_lo;
+    double t = (double)(float)(v - r_lo) / step;
+    double last = (double)(nb - 1);
+    if (t > last) t = last;
+    return (int)t;
+}
+
+void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr)
+{
+    const int nb = nbins + 2;
+    const double step = (double)(float)(r_hi - r_lo) / (double)nb;
+    thr[0] = 0.0f;
+    thr[nb] = INFINITY;
+    for (int b = 1; b < nb; b++) {
+        // smallest non-negative float q with bin(q) >= b; bit patterns of non-negative floats are ordered
+        uint32_t lo = 0u, hi = 0x7f800000u;     // [+0, +inf]
+        float fhi;
+        memcpy(&fhi, &hi, 4);
+        if (rdf_bin_of_q(fhi, r_lo, step, nb) < b) { thr[b] = INFINITY; continue; }
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            float fm;
+            memcpy(&fm, &mid, 4);
+            if (rdf_bin_of_q(fm, r_lo, step, nb) >= b) hi = mid; else lo = mid + 1;
+        }
+        memcpy(&thr[b], &lo, 4);
+    }
+}
+
+extern "C" {
+
+int htf_abi_version(void) { return HTF_ABI_VERSION; }
+
+int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int flags)
+{
+    if (!out) { set_err(nullptr, "htf_create: out is NULL"); return HTF_EINVAL; }
+    *out = nullptr;
+    if (n_max < 0 || n_max > 2000000000LL) { set_err(nullptr, "htf_create: n_max out of range"); return HTF_EINVAL; }
+    if (k < 1) { set_err(nullptr, "htf_create: nneighbor_cutoff must be >= 1"); return HTF_EINVAL; }
+    if (!(r_cut > 0.0f)) { set_err(nullptr, "htf_create: r_cut must be > 0"); return HTF_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        set_err(nullptr, "htf_create: no CUDA device %d (%s)", device, cudaGetErrorString(e));
+        return HTF_ECUDA;
+    }
+    int major = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (major != 10 && !(flags & HTF_FLAG_ANY_ARCH)) {
+        set_err(nullptr, "htf_create: device %d is sm_%d0, this library carries sm_100a code only", device, major);
+        return HTF_EARCH;
+    }
+    htf_ctx *ctx = new (std::nothrow) htf_ctx();
+    if (!ctx) { set_err(nullptr, "htf_create: host allocation failed"); return HTF_ENOMEM; }
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device; ctx->sm_count = sms; ctx->flags = flags; ctx->n_max = n_max; ctx->K = k;
+    ctx->r_cut = r_cut; ctx->map_type_start = -1;
+    DeviceGuard guard(device);
+    int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
+    if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
+    *out = ctx;
+    return HTF_OK;
+}
+
+void htf_destroy(htf_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->d_cell_cnt); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_block_sums);
+    cudaFree(ctx->d_cell_of); cudaFree(ctx->d_sorted_idx); cudaFree(ctx->d_spos);
+    cudaFree(ctx->d_nlist_scratch); cudaFree(ctx->d_rdf_thr);
+    delete ctx;
+}
+
+const char *htf_last_error(const htf_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int htf_set_box(htf_ctx *ctx, const float h_lo[3], const float h_hi[3], const float h_tilt[3])
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!h_lo || !h_hi) { set_err(ctx, "htf_set_box: null box"); return HTF_EINVAL; }
+    if (h_tilt) {
+        // the reference asserts sum(box[2]) < 1e-4 (htf/simmodel.py:195); use |.| so negative tilt is caught too
+        float s = fabsf(h_tilt[0]) + fabsf(h_tilt[1]) + fabsf(h_tilt[2]);
+        if (!(s < 1e-4f)) { set_err(ctx, "box is skewed"); return HTF_ESKEW; }
+    }
+    for (int a = 0; a < 3; a++) {
+        if (!(h_hi[a] > h_lo[a])) { set_err(ctx, "htf_set_box: hi <= lo on axis %d", a); return HTF_EINVAL; }
+        ctx->grid.lo[a] = h_lo[a]; ctx->grid.hi[a] = h_hi[a]; ctx->grid.L[a] = h_hi[a] - h_lo[a];
+    }
+    ctx->box_set = true;
+    DeviceGuard guard(ctx->device);
+    return make_grid(ctx);
+}
+
+int htf_set_mapped_nlist(htf_ctx *ctx, int map_type_start)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    ctx->map_type_start = map_type_start < 0 ? -1 : map_type_start;
+    return HTF_OK;
+}
+
+int htf_set_cutoff(htf_ctx *ctx, float r_cut, int k)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (k < 1 || !(r_cut > 0.0f)) { set_err(ctx, "htf_set_cutoff: need r_cut > 0 and k >= 1"); return HTF_EINVAL; }
+    ctx->r_cut = r_cut; ctx->K = k;
+    if (!ctx->box_set) return HTF_OK;
+    DeviceGuard guard(ctx->device);
+    return make_grid(ctx);
+}
+
+int htf_get_cell_grid(const htf_ctx *ctx, int h_ncell[3])
+{
+    if (!ctx || !h_ncell) return HTF_EINVAL;
+    for (int a = 0; a < 3; a++) h_ncell[a] = ctx->grid.n[a];
+    return ctx->box_set ? HTF_OK : HTF_ESTATE;
+}
+
+int64_t htf_launch_count(const htf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int htf_bin_particles(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->box_set) { set_err(ctx, "htf_bin_particles: box not set"); return HTF_ESTATE; }
+    if (n_all < 0 || n_all > 2000000000LL || (n_all > 0 && !d_pos_all)) {
+        set_err(ctx, "htf_bin_particles: bad positions"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    if ((rc = ensure_particles(ctx, n_all))) return rc;
+    if (n_all > ctx->n_max) {                 // the cell budget follows the particle count
+        ctx->n_max = n_all;
+        if ((rc = make_grid(ctx))) return rc;
+    }
+    HTF_CUDA(ctx, htf_launch_binning(ctx, reinterpret_cast<const float4 *>(d_pos_all), n_all, (cudaStream_t)stream));
+    ctx->binned = true;
+    ctx->n_binned = n_all;
+    return HTF_OK;
+}
+
+int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                    float *d_nlist_out, int32_t *d_idx_out, int32_t *d_count_out, int32_t *d_overflow,
+                    void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    (void)d_pos_all;
+    if (!ctx->binned || ctx->n_binned != n_all) {
+        set_err(ctx, "htf_build_nlist: call htf_bin_particles on these %lld particles first", (long long)n_all);
+        return HTF_ESTATE;
+    }
+    if (row_lo < 0 || row_hi > n_all || row_lo > row_hi) { set_err(ctx, "htf_build_nlist: bad row range"); return HTF_EINVAL; }
+    if (row_hi > row_lo && !d_nlist_out) { set_err(ctx, "htf_build_nlist: null output"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(d_nlist_out), d_idx_out,
+                                   d_count_out, d_overflow, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, float *d_force_energy, float *d_virial,
+                  int virial_components, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (rows < 0 || (rows > 0 && (!d_nlist || !d_force_energy))) { set_err(ctx, "htf_lj_forces: bad arguments"); return HTF_EINVAL; }
+    if (d_virial && virial_components != 6 && virial_components != 9) {
+        set_err(ctx, "htf_lj_forces: virial_components must be 6 or 9"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, ctx->K,
+                                reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components,
+                                nullptr, 0, nullptr, -1, -1, nullptr, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, const float *d_row_pos, float r_lo, float r_hi,
+                 int nbins, int type_i, int type_j, int64_t *d_bins, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (rows < 0 || (rows > 0 && !d_nlist) || !d_bins) { set_err(ctx, "htf_rdf_hist: bad arguments"); return HTF_EINVAL; }
+    if (type_i >= 0 && !d_row_pos) { set_err(ctx, "htf_rdf_hist: type_i needs the row positions"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, (cudaStream_t)stream))) return rc;
+    HTF_CUDA(ctx, htf_launch_rdf(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, ctx->K,
+                                 reinterpret_cast<const float4 *>(d_row_pos), ctx->d_rdf_thr, nbins + 2,
+                                 type_i, type_j, reinterpret_cast<unsigned long long *>(d_bins),
+                                 (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
+                int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (row_lo < 0 || row_hi > n_all || row_lo > row_hi) { set_err(ctx, "htf_lj_step: bad row range"); return HTF_EINVAL; }
+    const int64_t rows = row_hi - row_lo;
+    if (rows > 0 && !d_force_energy) { set_err(ctx, "htf_lj_step: null force output"); return HTF_EINVAL; }
+    if (d_virial && virial_components != 6 && virial_components != 9) {
+        set_err(ctx, "htf_lj_step: virial_components must be 6 or 9"); return HTF_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(ctx->device);
+    if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    float *nl = d_nlist_out;
+    if (!nl) {
+        const int64_t need = rows * ctx->K * 4;
+        if (need > ctx->nlist_scratch_elems) {
+            if ((rc = dev_realloc(ctx, &ctx->d_nlist_scratch, (size_t)need))) return rc;
+            ctx->nlist_scratch_elems = need;
+        }
+        nl = ctx->d_nlist_scratch;
+    }
+    HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(nl), nullptr, nullptr,
+                                   d_overflow, st));
+    const float *thr = nullptr;
+    int nb = 0;
+    if (d_bins) {
+        if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, st))) return rc;
+        thr = ctx->d_rdf_thr; nb = nbins + 2;
+    }
+    HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(nl), rows, ctx->K,
+                                reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components,
+                                thr, nb, nullptr, -1, -1, reinterpret_cast<unsigned long long *>(d_bins), st));
+    return HTF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// Cell binning for the neighbor build: replaces the candidate search of HOOMD's
+// NeighborList::compute (called at /root/reference htf/TensorflowCompute.cc:163).
+//
+// Pipeline (all HBM-bound, ~56 B/particle):
+//   count   : cell id per particle, atomic count per cell
+//   scan    : exclusive prefix sum of the counts (3 small kernels)
+//   scatter : particle index -> slot of its cell (count-down atomics, no second zeroing)
+//   order   : (deterministic mode) sort the indices inside each cell
+//   gather  : cell-sorted copy of the positions, the only array the build kernel reads
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int cell_coord(float p, float lo, float inv_w, int n)
+{
+    float u = __fmul_rn(__fsub_rn(p, lo), inv_w);
+    int c = (int)floorf(u);
+    return max(0, min(n - 1, c));      // particles on/over the box faces go to the edge cells
+}
+
+__global__ void __launch_bounds__(256) cell_count_kernel(const float4 *__restrict__ pos, int n, CellGrid g,
+                                                         int *__restrict__ cell_of, int *__restrict__ cell_cnt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = __ldg(pos + i);
+    int cx = cell_coord(p.x, g.lo[0], g.inv_w[0], g.n[0]);
+    int cy = cell_coord(p.y, g.lo[1], g.inv_w[1], g.n[1]);
+    int cz = cell_coord(p.z, g.lo[2], g.inv_w[2], g.n[2]);
+    int c = (cz * g.n[1] + cy) * g.n[0] + cx;
+    cell_of[i] = c;
+    atomicAdd(cell_cnt + c, 1);
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(HTF_FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one tile held as SCAN_ITEMS per thread; returns the tile total
+__device__ __forceinline__ int block_excl_scan(int (&v)[SCAN_ITEMS], int *warp_tot /* smem[8] */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+    int incl = warp_incl_scan(s, lane);
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_THREADS / 32; q++) {
+        int t = warp_tot[q];
+        if (q < w) base += t;
+        total += t;
+    }
+    int run = base + incl - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { int t = v[k]; v[k] = run; run += t; }
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const int *__restrict__ in, int n,
+                                                                      int *__restrict__ tile_sums)
+{
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+    int total = block_excl_scan(v, warp_tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the tile sums in place, total -> *grand_total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(int *__restrict__ tile_sums, int ntiles,
+                                                                int *__restrict__ grand_total)
+{
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    int carry = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += SCAN_TILE) {
+        const int base = t0 + threadIdx.x * SCAN_ITEMS;
+        int v[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < ntiles) ? tile_sums[base + k] : 0;
+        int total = block_excl_scan(v, warp_tot);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++)
+            if (base + k < ntiles) tile_sums[base + k] = v[k] + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int *__restrict__ in, int n,
+                                                                  const int *__restrict__ tile_offs,
+                                                                  int *__restrict__ out)
+{
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+    block_excl_scan(v, warp_tot);
+    const int off = tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) out[base + k] = v[k] + off;
+}
+
+// count-down scatter: cell_cnt[c] still holds the population from the count pass
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict__ cell_of, int n,
+                                                           const int *__restrict__ cell_start,
+                                                           int *__restrict__ cell_cnt, int *__restrict__ sorted_idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of[i];
+    int k = atomicSub(cell_cnt + c, 1) - 1;
+    sorted_idx[cell_start[c] + k] = i;
+}
+
+// one thread per cell: insertion sort of the (few) particle indices of the cell
+__global__ void __launch_bounds__(128) cell_order_kernel(const int *__restrict__ cell_start, int ncell,
+                                                         int *__restrict__ sorted_idx)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int b = cell_start[c], e = cell_start[c + 1];
+    for (int a = b + 1; a < e; a++) {
+        int key = sorted_idx[a];
+        int q = a - 1;
+        while (q >= b) {
+            int t = sorted_idx[q];
+            if (t <= key) break;
+            sorted_idx[q + 1] = t;
+            q--;
+        }
+        sorted_idx[q + 1] = key;
+    }
+}
+
+__global__ void __launch_bounds__(256) cell_gather_kernel(const float4 *__restrict__ pos,
+                                                          const int *__restrict__ sorted_idx, int n,
+                                                          float4 *__restrict__ spos)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    spos[s] = __ldg(pos + sorted_idx[s]);
+}
+
+}  // namespace
+
+cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cudaStream_t st)
+{
+    const int n = (int)n64;
+    const CellGrid &g = ctx->grid;
+    const int ncell = g.ncell;
+    cudaError_t e = cudaMemsetAsync(ctx->d_cell_cnt, 0, sizeof(int) * (size_t)ncell, st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) {
+        e = cudaMemsetAsync(ctx->d_cell_start, 0, sizeof(int) * ((size_t)ncell + 1), st);
+        return e;
+    }
+    const int pb = (n + 255) / 256;
+    cell_count_kernel<<<pb, 256, 0, st>>>(pos, n, g, ctx->d_cell_of, ctx->d_cell_cnt);
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
+    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
+    cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_sorted_idx);
+    ctx->launches += 5;
+    if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */) {
+        cell_order_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ctx->d_cell_start, ncell, ctx->d_sorted_idx);
+        ctx->launches += 1;
+    }
+    cell_gather_kernel<<<pb, 256, 0, st>>>(pos, ctx->d_sorted_idx, n, ctx->d_spos);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}

@@ -1,0 +1,65 @@
+// Internal declarations shared by the kernels of libhtf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HTF_WARP 32
+#define HTF_FULL 0xffffffffu
+
+// Cell grid of the periodic orthorhombic box.  Cell edge >= r_cut*(1+1e-4) in every
+// dimension, so all neighbors of a particle live in the 3x3x3 stencil of its cell even
+// when the fp32 cell index of a particle on a cell face rounds to either side.
+struct CellGrid {
+    float lo[3], hi[3], L[3];
+    float inv_w[3];      // n / L
+    int n[3];
+    int ncell;
+};
+
+struct htf_ctx {
+    int device;
+    int sm_count;
+    int flags;
+    int64_t n_max;
+    int K;
+    float r_cut;
+    int map_type_start;
+    bool box_set;
+    bool binned;
+    int64_t n_binned;
+    CellGrid grid;
+    // device scratch owned by the context
+    int *d_cell_cnt;      // [ncell_cap]
+    int *d_cell_start;    // [ncell_cap + 1]
+    int *d_block_sums;    // [scan blocks]
+    int ncell_cap;
+    int *d_cell_of;       // [n_cap]
+    int *d_sorted_idx;    // [n_cap] cell-sorted slot -> particle index
+    float4 *d_spos;       // [n_cap] cell-sorted positions
+    int64_t n_cap;
+    float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
+    int64_t nlist_scratch_elems;
+    // RDF threshold table (device) and the key it was built for
+    float *d_rdf_thr;
+    float rdf_lo, rdf_hi;
+    int rdf_nbins;
+    int64_t launches;
+    char err[512];
+};
+
+// ---- launchers (each returns a cudaError_t from the launch) ----
+cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n, cudaStream_t st);
+
+cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *out, int32_t *idx_out,
+                             int32_t *count_out, int32_t *overflow, cudaStream_t st);
+
+cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
+                          int vcomp, const float *rdf_thr, int nb, const float4 *row_pos, int type_i, int type_j,
+                          unsigned long long *bins, cudaStream_t st);
+
+cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float4 *row_pos,
+                           const float *thr, int nb, int type_i, int type_j, unsigned long long *bins,
+                           cudaStream_t st);
+
+// host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
+void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

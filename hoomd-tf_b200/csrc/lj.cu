@@ -1,0 +1,234 @@
+// One streaming pass over the neighbor tensor: LJModel forces + per-particle energy +
+// virial, and (optionally, fused into the same read) the compute_rdf histogram.
+//
+// Replaces, for the built-in LJ model, the TensorFlow graph
+//   nlist_rinv (/root/reference htf/simmodel.py:618-635) -> pair energy
+//   (htf/test-py/build_examples.py:67-77) -> tf.gradients + *2 + reduce_sum
+//   (htf/simmodel.py:542-550) -> _add_energy (:558-578) -> _compute_virial (:509-523),
+// the TfToHoomd copies (htf/tf2hoomd_op/tf2hoomd.cc:48-59) and the 3x3 -> 6 virial scatter
+// (htf/TensorflowCompute.cu:41-71); and for the RDF masked_nlist + tf.norm +
+// tf.histogram_fixed_width (htf/simmodel.py:638-693).
+//
+// HBM-bound: 16*K bytes read per row, 16 (+24) written.  LPR lanes share a row, each lane
+// streams float4 slots LPR apart (a warp request covers 32/LPR rows x 128 B = whole cache
+// lines), partial sums are combined with xor shuffles inside the LPR-lane group.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LJ_THREADS = 256;
+constexpr int LJ_UNROLL = 4;          // independent 16-byte loads in flight per lane
+constexpr int RDF_MAX_BINS = 1024;    // nbins + 2 <= RDF_MAX_BINS (shared-memory histogram)
+
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+struct PairParams {
+    const float4 *nlist;
+    long long rows;
+    int K;
+    float4 *fe;
+    float *virial;
+    int vcomp;                 // 0, 6 or 9
+    // rdf
+    const float *thr;          // [nb + 1]: thr[b], b = 1..nb-1, ascending thresholds in rsq space
+    int nb;                    // nbins + 2
+    float r_lo, inv_step;      // first guess only; the thresholds decide
+    const float4 *row_pos;
+    int type_i, type_j;
+    unsigned long long *bins;
+};
+
+template <int LPR, bool FORCES, bool VIRIAL, bool RDF>
+__global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams p)
+{
+    extern __shared__ int s_hist[];             // RDF: [warps][nb] private histograms + thr copy
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPR;
+    constexpr int RPW = 32 / LPR;               // rows per warp
+    constexpr int WARPS = LJ_THREADS / 32;
+    const int K = p.K;
+
+    int *my_hist = nullptr;
+    float *s_thr = nullptr;
+    unsigned bin0 = 0;                          // lane-private count of bin 0 (padded slots land here)
+    if (RDF) {
+        my_hist = s_hist + warp * p.nb;
+        s_thr = reinterpret_cast<float *>(s_hist + WARPS * p.nb);
+        for (int q = threadIdx.x; q < WARPS * p.nb; q += LJ_THREADS) s_hist[q] = 0;
+        for (int q = threadIdx.x; q <= p.nb; q += LJ_THREADS) s_thr[q] = p.thr[q];
+        __syncthreads();
+    }
+
+    const long long groups = (p.rows + RPW - 1) / RPW;      // one warp-iteration = RPW rows
+    for (long long gi = (long long)blockIdx.x * WARPS + warp; gi < groups; gi += (long long)gridDim.x * WARPS) {
+        const long long row = gi * RPW + lane / LPR;
+        const bool active = row < p.rows;
+        const float4 *rp = p.nlist + (active ? row : 0) * K;
+        float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+        float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
+        bool row_in_rdf = false;
+        if (RDF) {
+            row_in_rdf = active;
+            if (active && p.type_i >= 0) row_in_rdf = (__ldg(&p.row_pos[row].w) == (float)p.type_i);
+        }
+        for (int s0 = sub; s0 < K; s0 += LPR * LJ_UNROLL) {
+            float4 d[LJ_UNROLL];
+#pragma unroll
+            for (int u = 0; u < LJ_UNROLL; u++) {
+                const int s = s0 + u * LPR;
+                d[u] = (active && s < K) ? ld_stream(rp + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < LJ_UNROLL; u++) {
+                const float dx = d[u].x, dy = d[u].y, dz = d[u].z;
+                if (FORCES) {
+                    const float ax = dx + 1e-7f, ay = dy + 1e-7f, az = dz + 1e-7f;
+                    const float rt = sqrtf(ax * ax + ay * ay + az * az);
+                    if (rt > 3e-6f) {
+                        const float si = 1.0f / (rt + 3e-6f);
+                        const float s2 = si * si, s6 = s2 * s2 * s2;
+                        en += 2.0f * (s6 * s6 - s6);
+                        const float coef = (24.0f * s6 * si - 48.0f * s6 * s6 * si) / rt;
+                        const float px = coef * ax, py = coef * ay, pz = coef * az;
+                        fx += px; fy += py; fz += pz;
+                        if (VIRIAL) {
+                            const float rm = sqrtf(dx * dx + dy * dy + dz * dz);
+                            const float fm = sqrtf(px * px + py * py + pz * pz);
+                            const float w = (rm == 0.f) ? 0.f : fm / (2.0f * rm);
+                            const float wx = w * dx, wy = w * dy, wz = w * dz;
+                            vxx += wx * dx; vxy += wx * dy; vxz += wx * dz;
+                            vyy += wy * dy; vyz += wy * dz; vzz += wz * dz;
+                        }
+                    }
+                }
+                if (RDF) {
+                    const int s = s0 + u * LPR;
+                    if (row_in_rdf && s < K) {
+                        float m = 1.0f;
+                        if (p.type_j >= 0) m = (d[u].w == (float)p.type_j) ? 1.0f : 0.0f;
+                        const float x = __fmul_rn(dx, m), y = __fmul_rn(dy, m), z = __fmul_rn(dz, m);
+                        const float q = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+                        // first guess from an approximate r, then the exact threshold table decides
+                        int g = (int)((__fsqrt_rn(q) - p.r_lo) * p.inv_step);
+                        g = max(0, min(p.nb - 1, g));
+                        while (g < p.nb - 1 && q >= s_thr[g + 1]) g++;
+                        while (g > 0 && q < s_thr[g]) g--;
+                        if (g == 0) bin0++;
+                        else atomicAdd(my_hist + g, 1);
+                    }
+                }
+            }
+        }
+        if (FORCES) {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) {
+                fx += __shfl_xor_sync(HTF_FULL, fx, o);
+                fy += __shfl_xor_sync(HTF_FULL, fy, o);
+                fz += __shfl_xor_sync(HTF_FULL, fz, o);
+                en += __shfl_xor_sync(HTF_FULL, en, o);
+                if (VIRIAL) {
+                    vxx += __shfl_xor_sync(HTF_FULL, vxx, o);
+                    vxy += __shfl_xor_sync(HTF_FULL, vxy, o);
+                    vxz += __shfl_xor_sync(HTF_FULL, vxz, o);
+                    vyy += __shfl_xor_sync(HTF_FULL, vyy, o);
+                    vyz += __shfl_xor_sync(HTF_FULL, vyz, o);
+                    vzz += __shfl_xor_sync(HTF_FULL, vzz, o);
+                }
+            }
+            if (active && sub == 0) p.fe[row] = make_float4(fx, fy, fz, en);
+            if (VIRIAL && active) {
+                if (p.vcomp == 6) {
+                    // xx,xy,xz,yy,yz,zz  (htf/TensorflowCompute.cc:294-299)
+                    if (sub < 6) {
+                        const float v = sub == 0 ? vxx : sub == 1 ? vxy : sub == 2 ? vxz : sub == 3 ? vyy : sub == 4 ? vyz : vzz;
+                        p.virial[row * 6 + sub] = -v;
+                    }
+                } else {
+                    for (int c = sub; c < 9; c += LPR) {
+                        const int k = c / 3, l = c % 3;
+                        const int a = min(k, l), b2 = max(k, l);
+                        const float v = a == 0 ? (b2 == 0 ? vxx : b2 == 1 ? vxy : vxz) : a == 1 ? (b2 == 1 ? vyy : vyz) : vzz;
+                        p.virial[row * 9 + c] = -v;
+                    }
+                }
+            }
+        }
+    }
+    if (RDF) {
+        // bin 0 holds every padded slot: reduce it in registers, one shared atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bin0 += __shfl_xor_sync(HTF_FULL, bin0, o);
+        if (lane == 0 && bin0) atomicAdd(my_hist, (int)bin0);
+        __syncthreads();
+        for (int b = threadIdx.x; b < p.nb; b += LJ_THREADS) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) t += (unsigned)s_hist[w * p.nb + b];
+            if (t) atomicAdd(p.bins + b, t);
+        }
+    }
+}
+
+template <bool FORCES, bool VIRIAL, bool RDF>
+cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
+{
+    // lanes per row: 8 keeps every warp request on whole 128-byte lines; small K uses fewer
+    const int K = p.K;
+    const size_t smem = RDF ? sizeof(int) * ((size_t)(LJ_THREADS / 32) * p.nb + p.nb + 1) : 0;
+    const int lpr = (K >= 24) ? 8 : (K >= 12 ? 4 : (K >= 6 ? 2 : 1));
+    const long long rpw = 32 / lpr;
+    const long long groups = (p.rows + rpw - 1) / rpw;
+    const long long blocks_needed = (groups + LJ_THREADS / 32 - 1) / (LJ_THREADS / 32);
+    long long grid = blocks_needed;
+    const long long persistent = (long long)ctx->sm_count * 8;     // 8 x 256 threads = full occupancy
+    if (RDF && grid > persistent) grid = persistent;               // fewer histogram flushes
+    if (grid < 1) grid = 1;
+    switch (lpr) {
+    case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 4: pair_pass_kernel<4, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 2: pair_pass_kernel<2, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    default: pair_pass_kernel<1, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    }
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
+                          int vcomp, const float *rdf_thr, int nb, const float4 *row_pos, int type_i, int type_j,
+                          unsigned long long *bins, cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    PairParams p;
+    p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
+    p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
+    p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
+    p.row_pos = row_pos; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    const bool rdf = bins != nullptr;
+    if (rdf && nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
+    if (virial) return rdf ? launch_pair<true, true, true>(ctx, p, st) : launch_pair<true, true, false>(ctx, p, st);
+    return rdf ? launch_pair<true, false, true>(ctx, p, st) : launch_pair<true, false, false>(ctx, p, st);
+}
+
+cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float4 *row_pos,
+                           const float *thr, int nb, int type_i, int type_j, unsigned long long *bins,
+                           cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    if (nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
+    PairParams p;
+    p.nlist = nlist; p.rows = rows; p.K = K; p.fe = nullptr; p.virial = nullptr; p.vcomp = 0;
+    p.thr = thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
+    p.inv_step = (ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
+    p.row_pos = row_pos; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    return launch_pair<false, false, true>(ctx, p, st);
+}

@@ -1,0 +1,161 @@
+"""Thin torch-tensor front end over the C ABI (one ``HtfContext`` per device).
+
+Plays the role of the reference's ``_htf.TensorflowComputeGPU`` object plus its
+``TFArrayComm`` buffers (/root/reference htf/TensorflowCompute.cc:422-486,
+htf/TFArrayComm.h:86-231): torch only provides device memory and the current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_dev_f32(t, name, last=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("%s must be contiguous float32" % name)
+    if last is not None and t.shape[-1] != last:
+        raise ValueError("%s must have last dimension %d" % (name, last))
+
+
+class HtfContext:
+    def __init__(self, n_max, nneighbor_cutoff, r_cut, device=None, deterministic=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("htf_b200 needs a CUDA device: the hot path has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None
+                                   else torch.device(device).index or 0)
+        self.K = int(nneighbor_cutoff)
+        self.r_cut = float(r_cut)
+        self._h = ctypes.c_void_p()
+        flags = _lib.FLAG_DETERMINISTIC if deterministic else 0
+        rc = self.lib.htf_create(ctypes.byref(self._h), self.device.index, int(n_max), self.K, self.r_cut, flags)
+        if rc != 0:
+            raise _lib.HtfError(rc, self.lib.htf_last_error(None).decode())
+        self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.box = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.htf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers --
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc):
+        return _lib.check(self._h, rc)
+
+    # -- configuration --
+    def set_box(self, lo, hi, tilt=(0.0, 0.0, 0.0)):
+        """updateBox (htf/TensorflowCompute.cc:272-282) + skew check (htf/simmodel.py:195)."""
+        a3 = ctypes.c_float * 3
+        self._ck(self.lib.htf_set_box(self._h, a3(*[float(x) for x in lo]), a3(*[float(x) for x in hi]),
+                                      a3(*[float(x) for x in tilt])))
+        self.box = ([float(x) for x in lo], [float(x) for x in hi], [float(x) for x in tilt])
+
+    def set_cutoff(self, r_cut, nneighbor_cutoff):
+        self._ck(self.lib.htf_set_cutoff(self._h, float(r_cut), int(nneighbor_cutoff)))
+        self.r_cut, self.K = float(r_cut), int(nneighbor_cutoff)
+
+    def set_mapped_nlist(self, map_type_start):
+        self._ck(self.lib.htf_set_mapped_nlist(self._h, -1 if map_type_start is None else int(map_type_start)))
+
+    def cell_grid(self):
+        n = (ctypes.c_int * 3)()
+        self._ck(self.lib.htf_get_cell_grid(self._h, n))
+        return tuple(n)
+
+    @property
+    def launches(self):
+        return int(self.lib.htf_launch_count(self._h))
+
+    # -- the path --
+    def bin_particles(self, pos):
+        _check_dev_f32(pos, "positions", 4)
+        self._ck(self.lib.htf_bin_particles(self._h, _ptr(pos), pos.shape[0], self._stream()))
+
+    def build_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False, rebin=True):
+        """positions [N,4] -> nlist [rows,K,4] (and optionally idx [rows,K], count [rows])."""
+        _check_dev_f32(pos, "positions", 4)
+        n = pos.shape[0]
+        row_hi = n if row_hi is None else int(row_hi)
+        rows = row_hi - int(row_lo)
+        if rebin:
+            self.bin_particles(pos)
+        if out is None:
+            out = torch.empty((rows, self.K, 4), dtype=torch.float32, device=self.device)
+        else:
+            _check_dev_f32(out, "nlist out", 4)
+        idx = torch.empty((rows, self.K), dtype=torch.int32, device=self.device) if want_idx else None
+        cnt = torch.empty((rows,), dtype=torch.int32, device=self.device) if want_count else None
+        self._ck(self.lib.htf_build_nlist(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(out), _ptr(idx),
+                                          _ptr(cnt), _ptr(self._overflow), self._stream()))
+        res = (out,)
+        if want_idx:
+            res += (idx,)
+        if want_count:
+            res += (cnt,)
+        return res if len(res) > 1 else out
+
+    def overflow(self, reset=True):
+        """max neighbor count over rows that reached K since the last reset (0 = no row is full).
+        Synchronises the stream (D2H read of one int)."""
+        v = int(self._overflow.item())
+        if reset and v:
+            self._overflow.zero_()
+        return v
+
+    def lj_forces(self, nlist, virial=False, virial_components=6, out=None, virial_out=None):
+        _check_dev_f32(nlist, "nlist", 4)
+        if nlist.dim() != 3 or nlist.shape[1] != self.K:
+            raise ValueError("nlist must be [rows, %d, 4]" % self.K)
+        rows = nlist.shape[0]
+        fe = out if out is not None else torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        vir = None
+        if virial:
+            vir = virial_out if virial_out is not None else \
+                torch.empty((rows, virial_components), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.htf_lj_forces(self._h, _ptr(nlist), rows, _ptr(fe), _ptr(vir), int(virial_components),
+                                        self._stream()))
+        return (fe, vir) if virial else fe
+
+    def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None):
+        """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given."""
+        _check_dev_f32(nlist, "nlist", 4)
+        rows = nlist.shape[0]
+        if bins is None:
+            bins = torch.zeros((nbins + 2,), dtype=torch.int64, device=self.device)
+        if row_pos is not None:
+            _check_dev_f32(row_pos, "row positions", 4)
+        self._ck(self.lib.htf_rdf_hist(self._h, _ptr(nlist), rows, _ptr(row_pos), float(r_range[0]), float(r_range[1]),
+                                       int(nbins), -1 if type_i is None else int(type_i),
+                                       -1 if type_j is None else int(type_j), _ptr(bins), self._stream()))
+        return bins
+
+    def lj_step(self, pos, row_lo=0, row_hi=None, nlist_out=None, force_out=None, virial_out=None,
+                virial_components=6, bins=None, r_range=(0.0, 1.0), nbins=100):
+        """One computeForces pass of the built-in LJ model (htf/TensorflowCompute.cc:130-216)."""
+        _check_dev_f32(pos, "positions", 4)
+        n = pos.shape[0]
+        row_hi = n if row_hi is None else int(row_hi)
+        rows = row_hi - int(row_lo)
+        if force_out is None:
+            force_out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.htf_lj_step(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(nlist_out), _ptr(force_out),
+                                      _ptr(virial_out), int(virial_components), _ptr(self._overflow), _ptr(bins),
+                                      float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
+        return force_out

@@ -1,0 +1,161 @@
+/*
+ * htf_b200.h -- C ABI of libhtf_b200.so, the sm_100a implementation of hoomd-tf's
+ * nlist -> forces+virial hot path.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * hoomd-tf source tree, v2.4.0).  The reference crosses this boundary three ways:
+ *   - the pybind11 module `_htf` (htf/module.cc:16-28, htf/TensorflowCompute.cc:422-486),
+ *   - the TensorFlow custom ops HoomdToTf / TfToHoomd that memcpy through a CommStruct*
+ *     baked into the graph as an integer attr (htf/hoomd2tf_op/hoomd2tf.cc:15-34,64-89;
+ *     htf/tf2hoomd_op/tf2hoomd.cc:17-24,48-59; htf/CommStruct.h:29-104),
+ *   - the C++ -> Python callback _finish_update (htf/TensorflowCompute.cc:219-226).
+ * Here the whole path is one shared library with plain pointers and sizes; tensors are
+ * owned by the caller (torch / DLPack / cudaMalloc -- the library does not care) and are
+ * borrowed for the duration of the enqueue.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative HTF_E* code; nothing throws
+ *     across the ABI; htf_last_error() returns a human-readable message.
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) and is asynchronous: no implicit device
+ *     synchronisation (the reference ends every batch with cudaDeviceSynchronize,
+ *     htf/TensorflowCompute.cc:208-211).
+ *   - one context per device, not re-entrant per context (the reference is single
+ *     threaded too: htf/tf2hoomd_op/tf2hoomd.cc:11-12).
+ *   - "pos" is always float[n][4] = (x, y, z, type) with the type stored as a float
+ *     VALUE (what the reference produces with its unstuff4 kernel, htf/TFArrayComm.cu:9-15).
+ *   - "nlist" is always float[rows][K][4] = (dx, dy, dz, type_j), zero padded, dx = minimum
+ *     image of pos[j]-pos[i] (htf/TensorflowCompute.cc:353-367).
+ *   - the box is orthorhombic: lo[3], hi[3], tilt[3] must be 0 (htf/simmodel.py:195).
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ */
+#ifndef HTF_B200_H
+#define HTF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTF_OK            0
+#define HTF_EINVAL       -1   /* bad argument */
+#define HTF_ECUDA        -2   /* a CUDA runtime call or kernel launch failed */
+#define HTF_ENOMEM       -3   /* device allocation failed */
+#define HTF_ESTATE       -4   /* call order (e.g. box not set) */
+#define HTF_ESKEW        -5   /* box has non-zero tilt factors */
+#define HTF_EARCH        -6   /* device is not sm_100 */
+
+/* htf_create flags */
+#define HTF_FLAG_DETERMINISTIC  1   /* sort particles inside each cell by index: row-internal order and
+                                       therefore fp32 force sums are bit-reproducible run to run */
+#define HTF_FLAG_ANY_ARCH       2   /* do not refuse devices other than sm_100 (kernels still need sm_100a SASS) */
+
+typedef struct htf_ctx htf_ctx;
+
+/* ABI version of this header; htf_abi_version() of the loaded library must match. */
+#define HTF_ABI_VERSION 3
+int htf_abi_version(void);
+
+/*
+ * Replaces the TensorflowCompute constructor + reallocate()
+ * (htf/TensorflowCompute.cc:31-121, GPU subclass :493-537): sizes the scratch that belongs
+ * to the path (cell list, cell-sorted positions) for up to n_max particles.
+ * k = nneighbor_cutoff (>=1), r_cut > 0.
+ */
+int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int flags);
+void htf_destroy(htf_ctx *ctx);
+
+/* Message of the last failing call on ctx (ctx == NULL: last failing htf_create). */
+const char *htf_last_error(const htf_ctx *ctx);
+
+/*
+ * Replaces updateBox() (htf/TensorflowCompute.cc:272-282) and the skew assertion of
+ * SimModel.compute_inputs (htf/simmodel.py:195).  Host pointers.  Returns HTF_ESKEW when
+ * |tilt| sums to >= 1e-4.
+ */
+int htf_set_box(htf_ctx *ctx, const float h_lo[3], const float h_hi[3], const float h_tilt[3]);
+
+/* Mapped-nlist pair rule (htf/tensorflowcompute.py:284-305, TensorflowCompute::setMappedNlist
+ * htf/TensorflowCompute.cc:472-478): pairs are listed iff both types are < map_type_start or
+ * both are >= map_type_start.  map_type_start < 0 switches the rule off (default). */
+int htf_set_mapped_nlist(htf_ctx *ctx, int map_type_start);
+
+/* Change r_cut / nneighbor_cutoff of an existing context (tfcompute.attach arguments,
+ * htf/tensorflowcompute.py:38-39). */
+int htf_set_cutoff(htf_ctx *ctx, float r_cut, int k);
+
+/*
+ * Replaces HOOMD's NeighborList::compute (called at htf/TensorflowCompute.cc:163) for this
+ * path: bins all n_all particles into a cell list (cell edge >= r_cut) and writes the
+ * cell-sorted copy used by htf_build_nlist.  Must be called again whenever positions change.
+ */
+int htf_bin_particles(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, void *stream);
+
+/*
+ * Replaces prepareNeighbors (CPU htf/TensorflowCompute.cc:304-374; GPU :546-586 ->
+ * htf_gpu_reshape_nlist htf/TensorflowCompute.cu:80-209), the memset before it (.cu:180) and
+ * the HoomdToTf copy of the result (htf/hoomd2tf_op/hoomd2tf.cc:64-89).
+ * Builds rows [row_lo,row_hi) of the padded neighbor tensor from the binned particles
+ * (row batching = the reference's batch_size/offset chunking, htf/TensorflowCompute.cc:143-150).
+ *   d_nlist_out   float[rows][K][4]
+ *   d_idx_out     nullable int32[rows][K]: neighbor particle index per slot, -1 padded
+ *                 (validation only; the reference has no equivalent)
+ *   d_count_out   nullable int32[rows]: number of neighbors found (may exceed K: slots then
+ *                 wrap modulo K exactly like htf/TensorflowCompute.cc:370)
+ *   d_overflow    nullable int32[1]: atomically max'ed with count for every row with
+ *                 count >= K ("Neighbor list is full!", htf/simmodel.py:216-224); the caller
+ *                 zeroes it.
+ */
+int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                    float *d_nlist_out, int32_t *d_idx_out, int32_t *d_count_out, int32_t *d_overflow,
+                    void *stream);
+
+/*
+ * Replaces the LJModel graph (htf/test-py/build_examples.py:67-77 = benchmark.py:12-23):
+ * nlist_rinv (htf/simmodel.py:618-635) -> pair energy -> compute_nlist_forces (:526-555) ->
+ * _add_energy (:558-578) -> _compute_virial (:509-523), and the TfToHoomd copies plus the
+ * 3x3 -> 6 virial scatter (htf/tf2hoomd_op/tf2hoomd.cc:48-59, htf/TensorflowCompute.cc:285-301,
+ * htf/TensorflowCompute.cu:41-71).
+ *   d_force_energy  float[rows][4] = (Fx, Fy, Fz, e_i)
+ *   d_virial        nullable; virial_components = 6: float[rows][6] (xx,xy,xz,yy,yz,zz);
+ *                   = 9: float[rows][9] row-major 3x3 (what get_virial_array returns,
+ *                   htf/tensorflowcompute.py:388-392)
+ */
+int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, float *d_force_energy,
+                  float *d_virial, int virial_components, void *stream);
+
+/*
+ * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,
+ * tf.histogram_fixed_width over nbins+2 bins).  Adds this call's counts to d_bins
+ * (int64[nbins+2], caller zeroes; bins 0 and nbins+1 are the ones the reference drops).
+ *   d_row_type  nullable float[rows][4] positions of the rows (only .w is read) -- needed
+ *               when type_i >= 0;  type_i / type_j < 0 = None.
+ */
+int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, const float *d_row_pos,
+                 float r_lo, float r_hi, int nbins, int type_i, int type_j,
+                 int64_t *d_bins, void *stream);
+
+/*
+ * One pass of TensorflowCompute::computeForces for the built-in LJ model
+ * (htf/TensorflowCompute.cc:130-216): bin, build rows [row_lo,row_hi), forces, virial and --
+ * when d_bins != NULL -- the RDF histogram fused into the force pass.
+ * d_nlist_out may be NULL: the context then keeps the tensor in its own scratch.
+ */
+int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
+                int32_t *d_overflow,
+                int64_t *d_bins, float r_lo, float r_hi, int nbins,
+                void *stream);
+
+/* Number of kernels the library has launched on this context since creation
+ * (bench.py's gpu_launches claim). */
+int64_t htf_launch_count(const htf_ctx *ctx);
+
+/* Cell grid chosen by the last htf_set_box/htf_set_cutoff: h_ncell[3]. */
+int htf_get_cell_grid(const htf_ctx *ctx, int h_ncell[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTF_B200_H */

@@ -1,0 +1,167 @@
+"""CPU oracle for the hoomd-tf nlist -> forces+virial path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package, and only as the checker or the CPU
+baseline.  The product (``hoomd-tf_b200/``) never imports it.
+
+The arithmetic lives in ``htf_oracle.c`` (fp32, no FMA, fixed operation order); this
+module is the numpy/ctypes front end plus the scalar EDS layer restatement
+(/root/reference htf/layers.py:142-195).  See the header of ``htf_oracle.c`` for the
+reference file:line each function follows and for the pinning status
+("parity unpinned" for the RDF bin rule and the EDS/Adam update).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libhtf_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile libhtf_oracle.so with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "htf_oracle.c")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libhtf_oracle.so"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        lp = ctypes.POINTER(ctypes.c_int64)
+        i64, i32, f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_float
+        for name in ("htf_oracle_nlist", "htf_oracle_nlist_cells"):
+            fn = getattr(L, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [fp, i64, fp, fp, f32, i32, i64, i64, i32, fp, ip, ip]
+        L.htf_oracle_lj.restype = ctypes.c_int
+        L.htf_oracle_lj.argtypes = [fp, i64, i32, fp, fp, fp]
+        L.htf_oracle_rdf_hist.restype = ctypes.c_int
+        L.htf_oracle_rdf_hist.argtypes = [fp, i64, i32, fp, f32, f32, i32, i32, i32, lp]
+        L.htf_oracle_num_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct)) if a is not None else None
+
+
+def num_threads():
+    return int(lib().htf_oracle_num_threads())
+
+
+def nlist(pos, box_lo, box_hi, r_cut, K, row_lo=0, row_hi=None, cells=None, map_type_start=-1,
+          want_idx=True):
+    """Neighbor tensor of rows [row_lo,row_hi) (htf/TensorflowCompute.cc:304-374).
+
+    Returns (nlist[rows,K,4] f32, idx[rows,K] i32 (-1 padded), count[rows] i32).
+    ``cells=None`` picks the O(N^2) loop for n <= 4096 and the cell-list candidates above.
+    """
+    pos = _f32(pos)
+    n = pos.shape[0]
+    row_hi = n if row_hi is None else row_hi
+    rows = row_hi - row_lo
+    lo, hi = _f32(box_lo), _f32(box_hi)
+    out = np.empty((rows, K, 4), dtype=np.float32)
+    idx = np.empty((rows, K), dtype=np.int32) if want_idx else None
+    cnt = np.empty((rows,), dtype=np.int32)
+    if cells is None:
+        cells = n > 4096
+    fn = lib().htf_oracle_nlist_cells if cells else lib().htf_oracle_nlist
+    rc = fn(_ptr(pos, ctypes.c_float), n, _ptr(lo, ctypes.c_float), _ptr(hi, ctypes.c_float),
+            float(r_cut), int(K), int(row_lo), int(row_hi), int(map_type_start),
+            _ptr(out, ctypes.c_float), _ptr(idx, ctypes.c_int32), _ptr(cnt, ctypes.c_int32))
+    if rc != 0:
+        raise RuntimeError("oracle nlist failed: %d" % rc)
+    return out, idx, cnt
+
+
+def lj(nl, virial=True):
+    """LJModel forces+energy [rows,4] and virial ([rows,9], [rows,6]) from a neighbor tensor."""
+    nl = _f32(nl)
+    rows, K = nl.shape[0], nl.shape[1]
+    fe = np.empty((rows, 4), dtype=np.float32)
+    v9 = np.empty((rows, 9), dtype=np.float32) if virial else None
+    v6 = np.empty((rows, 6), dtype=np.float32) if virial else None
+    rc = lib().htf_oracle_lj(_ptr(nl, ctypes.c_float), rows, K, _ptr(fe, ctypes.c_float),
+                             _ptr(v9, ctypes.c_float), _ptr(v6, ctypes.c_float))
+    if rc != 0:
+        raise RuntimeError("oracle lj failed: %d" % rc)
+    return fe, v9, v6
+
+
+def rdf_hist(nl, r_range, nbins=100, row_type=None, type_i=None, type_j=None):
+    """compute_rdf's integer histogram over nbins+2 bins (htf/simmodel.py:662)."""
+    nl = _f32(nl)
+    rows, K = nl.shape[0], nl.shape[1]
+    hist = np.zeros((nbins + 2,), dtype=np.int64)
+    rt = _f32(row_type) if row_type is not None else None
+    if type_i is not None and rt is None:
+        raise ValueError("type_i needs row_type")
+    rc = lib().htf_oracle_rdf_hist(_ptr(nl, ctypes.c_float), rows, K, _ptr(rt, ctypes.c_float),
+                                   float(np.float32(r_range[0])), float(np.float32(r_range[1])), int(nbins),
+                                   -1 if type_i is None else int(type_i),
+                                   -1 if type_j is None else int(type_j),
+                                   _ptr(hist, ctypes.c_int64))
+    if rc != 0:
+        raise RuntimeError("oracle rdf failed: %d" % rc)
+    return hist
+
+
+def rdf_from_hist(hist, r_range, nbins=100):
+    """hist[nbins+2] -> (rdf[nbins], bin centres[nbins]) as htf/simmodel.py:663-669 (fp32)."""
+    lo, hi = np.float32(r_range[0]), np.float32(r_range[1])
+    shell = np.linspace(lo, hi, nbins + 1, dtype=np.float32)
+    vis = ((shell[1:] + shell[:-1]) * np.float32(0.5)).astype(np.float32)
+    vols = (shell[1:] ** 3 - shell[:-1] ** 3).astype(np.float32)
+    return (hist[1:-1].astype(np.float32) / vols).astype(np.float32), vis
+
+
+class EDSLayer:
+    """Scalar restatement of htf/layers.py:142-195 (EDSLayer.call) with tf.compat.v1 Adam
+    (beta1 .9, beta2 .999, eps 1e-8, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)); fp32 state.
+    PARITY UNPINNED: the reference only tests a convergence band (test_utils.py:447-461)."""
+
+    def __init__(self, set_point, period, learning_rate=1e-2, cv_scale=1.0):
+        f = np.float32
+        self.set_point, self.period = f(set_point), int(period)
+        self.lr, self.cv_scale = f(learning_rate), f(cv_scale)
+        self.mean = f(0); self.ssd = f(0); self.n = 0; self.alpha = f(0)
+        self.m = f(0); self.v = f(0); self.t = 0
+
+    def __call__(self, cv):
+        f = np.float32
+        cv = f(cv)
+        h = self.period // 2
+        if self.n == 0:                                   # layers.py:161-165
+            self.mean = f(0); self.ssd = f(0)
+        if self.n > h:                                    # :169-178
+            delta = f(cv - self.mean)
+            self.mean = f(self.mean + f(delta / f(self.n - h)))
+            self.ssd = f(self.ssd + f(delta * f(cv - self.mean)))
+        if self.n == self.period - 1:                     # :181-190
+            g = f(f(f(f(f(-2) * f(self.mean - self.set_point)) * self.ssd) / f(self.period)) / f(2))
+            g = f(g / self.cv_scale)
+            self.t += 1
+            self.m = f(f(0.9) * self.m + f(0.1) * g)
+            self.v = f(f(0.999) * self.v + f(0.001) * f(g * g))
+            lr_t = f(self.lr * f(np.sqrt(f(1) - f(0.999) ** self.t)) / f(f(1) - f(0.9) ** self.t))
+            self.alpha = f(self.alpha - f(lr_t * self.m) / f(f(np.sqrt(self.v)) + f(1e-8)))
+        self.n = (self.n + 1) % self.period               # :193
+        return self.alpha

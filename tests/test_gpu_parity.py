@@ -1,0 +1,269 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * per-row neighbor (index, type) sets, compared after sorting by index: bit-exact
+    (the d = (dx,dy,dz) values are bit-exact too, same arithmetic);
+  * RDF bin counts: bit-exact;
+  * forces / energies / virials: 1e-5 relative in fp32.  The row-internal slot order is
+    unspecified (HOOMD-internal in the reference), so sums differ by fp32
+    re-association; "relative" is therefore taken against max(|value|, row scale) where the
+    row scale is the RMS magnitude over rows (rows with a nearly cancelled force cannot
+    meet a pure relative bound in any summation order).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _ctx(n, K, r_cut, lo, hi, **kw):
+    import htf
+    c = htf.HtfContext(n, K, r_cut, **kw)
+    c.set_box(lo, hi)
+    return c
+
+
+def sort_rows(nl, idx):
+    key = np.where(idx < 0, np.iinfo(np.int32).max, idx)
+    order = np.argsort(key, axis=1, kind="stable")
+    return np.take_along_axis(nl, order[:, :, None], axis=1), np.take_along_axis(idx, order, axis=1)
+
+
+def assert_close_rel(got, want, rtol=RTOL, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = np.sqrt(np.mean(want ** 2)) + 1e-30
+    err = np.abs(got - want) / np.maximum(np.abs(want), scale)
+    assert err.max() <= rtol, "%s: max rel err %.3e at %s" % (what, err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def gpu_nlist(ctx, pos, row_lo=0, row_hi=None):
+    dpos = torch.from_numpy(pos).cuda()
+    nl, idx, cnt = ctx.build_nlist(dpos, row_lo, row_hi, want_idx=True, want_count=True)
+    torch.cuda.synchronize()
+    return nl, idx.cpu().numpy(), cnt.cpu().numpy()
+
+
+def check_nlist_case(oracle, pos, lo, hi, r_cut, K, row_lo=0, row_hi=None, cells=None):
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    nl_g, idx_g, cnt_g = gpu_nlist(ctx, pos, row_lo, row_hi)
+    nl_o, idx_o, cnt_o = oracle.nlist(pos, lo, hi, r_cut, K, row_lo, pos.shape[0] if row_hi is None else row_hi,
+                                      cells=cells)
+    assert np.array_equal(cnt_g, cnt_o), "neighbor counts differ"
+    assert cnt_o.max() <= K, "generator must not overflow K in this test"
+    nls, ids = sort_rows(nl_g.cpu().numpy(), idx_g)
+    assert np.array_equal(ids, idx_o), "neighbor index sets differ"
+    assert np.array_equal(nls.view(np.uint32), nl_o.view(np.uint32)), "(dx,dy,dz,type) not bit-exact"
+    assert ctx.overflow() == (cnt_o.max() if cnt_o.max() >= K else 0)
+    return ctx, nl_g, nl_o
+
+
+@pytest.mark.parametrize("n,a,K", [(3, 4.0, 8), (5, 3.0, 32), (16, 2.0, 64)])
+def test_nlist_square_lattices(oracle_mod, n, a, K):
+    """2-D square lattices of the reference tests (one cell in z, tiny cell grids)."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.square_lattice(n, a)
+    pos = synthetic.perturb(pos, lo, hi, 0.05, seed=n)
+    pos[:, 2] = 0.0
+    check_nlist_case(oracle_mod, pos, lo, hi, 5.0 if n < 16 else 3.0, K, cells=False)
+
+
+def test_nlist_bcc(oracle_mod):
+    """bcc 4x4x4 a=4.0, r_cut=5, NN=32 (htf/test-py/test_utils.py:401-430)."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.bcc_lattice(4, 4.0)
+    pos = synthetic.perturb(pos, lo, hi, 0.1, seed=7)
+    check_nlist_case(oracle_mod, pos, lo, hi, 5.0, 32, cells=False)
+
+
+def test_nlist_cfg1_types(oracle_mod):
+    from htf import synthetic
+    pos, lo, hi, r_cut, K = synthetic.config("cfg1", two_types_p=0.3)
+    check_nlist_case(oracle_mod, pos, lo, hi, r_cut, K, cells=False)
+
+
+def test_nlist_fluid_8k_bruteforce(oracle_mod):
+    """dense fluid, many interior cells (no-wrap fast path) + boundary cells, vs the O(N^2) oracle."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((16, 16, 32), 0.7, seed=11)
+    check_nlist_case(oracle_mod, pos, lo, hi, 2.5, 64, cells=False)
+
+
+def test_nlist_cfg2_and_lj_rdf(oracle_mod):
+    """cfg2: 65,536 particles, K=64: nlist sets, LJ forces/virial, RDF counts."""
+    from htf import synthetic
+    pos, lo, hi, r_cut, K = synthetic.config("cfg2")
+    ctx, nl_g, nl_o = check_nlist_case(oracle_mod, pos, lo, hi, r_cut, K, cells=True)
+    fe_o, v9_o, v6_o = oracle_mod.lj(nl_o)
+    fe_g, v6_g = ctx.lj_forces(nl_g, virial=True, virial_components=6)
+    _, v9_g = ctx.lj_forces(nl_g, virial=True, virial_components=9)
+    torch.cuda.synchronize()
+    assert_close_rel(fe_g.cpu().numpy()[:, :3], fe_o[:, :3], what="forces")
+    assert_close_rel(fe_g.cpu().numpy()[:, 3], fe_o[:, 3], what="energy")
+    assert_close_rel(v6_g.cpu().numpy(), v6_o, what="virial6")
+    assert_close_rel(v9_g.cpu().numpy(), v9_o, what="virial9")
+    # same slot order as the oracle -> only per-pair arithmetic differs (FMA contraction)
+    fe_s = ctx.lj_forces(torch.from_numpy(nl_o).cuda())
+    assert_close_rel(fe_s.cpu().numpy(), fe_o, what="forces, oracle slot order")
+    # RDF: 100 bins over [0, r_cut] -> 102-bin histogram, bit-exact
+    h_g = ctx.rdf_hist(nl_g, (0.0, r_cut), 100).cpu().numpy()
+    h_o = oracle_mod.rdf_hist(nl_o, (0.0, r_cut), 100)
+    assert np.array_equal(h_g, h_o)
+    assert h_g.sum() == pos.shape[0] * K
+
+
+def test_lj_step_fused_matches_separate(oracle_mod):
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((16, 16, 16), 0.7, seed=5)
+    K, r_cut = 64, 2.5
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    dpos = torch.from_numpy(pos).cuda()
+    nl = ctx.build_nlist(dpos)
+    fe, vir = ctx.lj_forces(nl, virial=True)
+    h = ctx.rdf_hist(nl, (0.0, r_cut), 100)
+    bins = torch.zeros(102, dtype=torch.int64, device="cuda")
+    vir2 = torch.empty_like(vir)
+    nl2 = torch.empty_like(nl)
+    fe2 = ctx.lj_step(dpos, nlist_out=nl2, virial_out=vir2, bins=bins, r_range=(0.0, r_cut), nbins=100)
+    torch.cuda.synchronize()
+    assert torch.equal(nl, nl2) and torch.equal(fe, fe2) and torch.equal(vir, vir2) and torch.equal(h, bins)
+    # and without a caller-provided tensor (context scratch)
+    fe3 = ctx.lj_step(dpos)
+    torch.cuda.synchronize()
+    assert torch.equal(fe, fe3)
+    nl_o, _, _ = oracle_mod.nlist(pos, lo, hi, r_cut, K)
+    fe_o, _, v6_o = oracle_mod.lj(nl_o)
+    assert_close_rel(fe.cpu().numpy(), fe_o, what="force+energy")
+    assert_close_rel(vir.cpu().numpy(), v6_o, what="virial")
+
+
+def test_row_batches_equal_unbatched(oracle_mod):
+    """batch_size chunking (htf/test-py/test_tensorflow.py:106-129): rows [lo,hi) == slice of the full build."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 16), 0.7, seed=3)
+    K, r_cut = 64, 2.5
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    dpos = torch.from_numpy(pos).cuda()
+    full = ctx.build_nlist(dpos)
+    n = pos.shape[0]
+    for a, b in [(0, 4), (4, 9), (100, 613), (n - 7, n), (5, 5)]:
+        part = ctx.build_nlist(dpos, a, b)
+        assert torch.equal(part, full[a:b])
+
+
+def test_overflow_wraps_and_flags(oracle_mod):
+    """K=4, r_cut=10 on the 8x8 lattice (htf/test-py/test_tensorflow.py:830-848): flagged, counts exact."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.square_lattice(8, 4.0)
+    ctx = _ctx(pos.shape[0], 4, 10.0, lo, hi)
+    nl, idx, cnt = gpu_nlist(ctx, pos)
+    _, idx_o, cnt_o = oracle_mod.nlist(pos, lo, hi, 10.0, 4)
+    assert np.array_equal(cnt, cnt_o) and cnt.min() > 4
+    assert ctx.overflow() == cnt_o.max()
+    # every slot holds a genuine neighbor of the row (which ones survive the wrap is order dependent)
+    nl_all, idx_all, _ = oracle_mod.nlist(pos, lo, hi, 10.0, 64)
+    for r in range(pos.shape[0]):
+        assert set(idx[r]).issubset(set(idx_all[r][idx_all[r] >= 0]))
+        assert len(set(idx[r])) == 4
+
+
+def test_typed_rdf_symmetry_and_parity(oracle_mod):
+    """typed RDF A->B == B->A on the two-type chains (htf/test-py/test_tensorflow.py:450-485) + oracle parity."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.typed_chains()
+    pos = synthetic.perturb(pos, lo, hi, 0.05, seed=1)
+    K, r_cut = 256, 10.0
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    dpos = torch.from_numpy(pos).cuda()
+    nl = ctx.build_nlist(dpos)
+    assert ctx.overflow() == 0
+    nl_o, _, _ = oracle_mod.nlist(pos, lo, hi, r_cut, K)
+    hs = {}
+    for ti, tj in [(0, 1), (1, 0), (None, 1), (0, None), (None, None)]:
+        h_g = ctx.rdf_hist(nl, (0.0, 10.0), 100, row_pos=dpos, type_i=ti, type_j=tj).cpu().numpy()
+        h_o = oracle_mod.rdf_hist(nl_o, (0.0, 10.0), 100, row_type=pos[:, 3], type_i=ti, type_j=tj)
+        assert np.array_equal(h_g, h_o), (ti, tj)
+        hs[(ti, tj)] = h_g
+    assert np.array_equal(hs[(0, 1)][1:-1], hs[(1, 0)][1:-1]) and hs[(0, 1)][1:-1].sum() > 0
+    # a range that does not start at 0 (LJRDF model uses [3, 5], build_examples.py:303-310)
+    h_g = ctx.rdf_hist(nl, (3.0, 5.0), 100).cpu().numpy()
+    h_o = oracle_mod.rdf_hist(nl_o, (3.0, 5.0), 100)
+    assert np.array_equal(h_g, h_o)
+
+
+def test_mapped_nlist_pair_rule(oracle_mod):
+    """AA <-> bead pairs are never listed (htf/tensorflowcompute.py:297-304)."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 8), 0.5, seed=9)
+    pos[-40:, 3] = 2.0 + (np.arange(40) % 2)          # beads: types 2,3 ; AA: type 0
+    K, r_cut = 64, 3.0
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    ctx.set_mapped_nlist(2)
+    nl_g, idx_g, cnt_g = gpu_nlist(ctx, pos)
+    nl_o, idx_o, cnt_o = oracle_mod.nlist(pos, lo, hi, r_cut, K, map_type_start=2)
+    assert np.array_equal(cnt_g, cnt_o)
+    nls, ids = sort_rows(nl_g.cpu().numpy(), idx_g)
+    assert np.array_equal(ids, idx_o) and np.array_equal(nls.view(np.uint32), nl_o.view(np.uint32))
+
+
+def test_empty_and_tiny_inputs(oracle_mod):
+    import htf
+    ctx = htf.HtfContext(16, 8, 2.0)
+    ctx.set_box([-5, -5, -5], [5, 5, 5])
+    one = torch.zeros((1, 4), device="cuda")
+    nl, cnt = ctx.build_nlist(one, want_count=True)
+    torch.cuda.synchronize()
+    assert nl.abs().sum().item() == 0 and cnt.item() == 0
+    empty = torch.zeros((0, 4), device="cuda")
+    nl = ctx.build_nlist(empty)
+    assert nl.shape == (0, 8, 4)
+    two = torch.tensor([[0.0, 0, 0, 0], [4.9, 0, 0, 1]], device="cuda")
+    nl = ctx.build_nlist(two).cpu().numpy()           # neighbor through the periodic boundary? |d|=4.9 > r_cut
+    assert np.all(nl == 0)
+    two = torch.tensor([[-4.5, 0, 0, 0], [4.5, 0, 0, 1]], device="cuda")
+    nl = ctx.build_nlist(two).cpu().numpy()           # d = 9 -> wraps to -1
+    assert np.allclose(nl[0, 0], [-1.0, 0, 0, 1]) and np.allclose(nl[1, 0], [1.0, 0, 0, 0])
+    with pytest.raises(htf._lib.HtfError):
+        ctx.set_box([-5, -5, -5], [5, 5, 5], tilt=[0.5, 0, 0])   # "box is skewed"
+
+
+@pytest.mark.parametrize("name", ["cfg3"])
+def test_full_size_properties(oracle_mod, name):
+    """BASELINE full size (1M particles, K=64): size-independent properties + an oracle-checked row slice."""
+    from htf import synthetic
+    pos, lo, hi, r_cut, K = synthetic.config(name)
+    n = pos.shape[0]
+    ctx = _ctx(n, K, r_cut, lo, hi)
+    dpos = torch.from_numpy(pos).cuda()
+    nl, idx, cnt = ctx.build_nlist(dpos, want_idx=True, want_count=True)
+    assert ctx.overflow() == 0
+    # (1) the list is full (double counted): sum of counts is even, i in nlist(j) <=> j in nlist(i)
+    assert int(cnt.sum().item()) % 2 == 0
+    rows = torch.arange(n, device="cuda", dtype=torch.int64)[:, None].expand(-1, K)
+    valid = idx >= 0
+    a = (rows[valid] * n + idx[valid].long())
+    b = (idx[valid].long() * n + rows[valid])
+    assert torch.equal(torch.sort(a).values, torch.sort(b).values)
+    # (2) every listed d has |d|^2 <= rc^2 and padded slots are all-zero
+    rsq = (nl[..., :3] ** 2).sum(-1)
+    assert bool((rsq[valid] <= r_cut * r_cut * (1 + 1e-6)).all()) and float(nl[~valid].abs().sum()) == 0.0
+    # (3) Newton's third law on the total force, energy finite, histogram total = N*K
+    bins = torch.zeros(102, dtype=torch.int64, device="cuda")
+    vir = torch.empty((n, 6), device="cuda")
+    fe = ctx.lj_step(dpos, virial_out=vir, bins=bins, r_range=(0.0, r_cut), nbins=100)
+    ftot = fe[:, :3].double().sum(0).abs().max().item()
+    fabs = fe[:, :3].double().abs().sum().item()
+    assert ftot <= 1e-5 * fabs
+    assert int(bins.sum().item()) == n * K and int(bins[1:-1].sum().item()) + int(bins[0].item()) + int(bins[-1].item()) == n * K
+    assert int(bins[0].item()) >= int((~valid).sum().item())
+    # (4) an oracle-checked slice of rows in the middle of the system
+    a0, b0 = n // 2, n // 2 + 4096
+    nl_o, idx_o, cnt_o = oracle_mod.nlist(pos, lo, hi, r_cut, K, a0, b0, cells=True)
+    nls, ids = sort_rows(nl[a0:b0].cpu().numpy(), idx[a0:b0].cpu().numpy())
+    assert np.array_equal(ids, idx_o) and np.array_equal(nls.view(np.uint32), nl_o.view(np.uint32))
+    fe_o, _, v6_o = oracle_mod.lj(nl_o)
+    assert_close_rel(fe[a0:b0].cpu().numpy(), fe_o, what="force+energy slice")
+    assert_close_rel(vir[a0:b0].cpu().numpy(), v6_o, what="virial slice")

@@ -1,0 +1,200 @@
+"""Pins the CPU oracle against the reference's own known-answer-by-construction tests.
+
+The reference stores no golden vectors for this path and neither hoomd nor tensorflow is
+importable here, so every test below restates one of the reference's self-checking tests
+without HOOMD: same lattice, same cutoff, same tolerance, an independent float64 O(N^2)
+computation as the truth (what `hoomd.md.pair.lj` / the Python loops provide there).
+"""
+import numpy as np
+import pytest
+
+from htf import synthetic
+
+
+def min_image64(d, L):
+    return d - np.round(d / L) * L
+
+
+def brute_pairs(pos, lo, hi, r_cut):
+    """float64 O(N^2) neighbor vectors: dict row -> list of (j, d)."""
+    xyz = pos[:, :3].astype(np.float64)
+    L = np.asarray(hi, np.float64) - np.asarray(lo, np.float64)
+    out = []
+    for i in range(len(xyz)):
+        d = min_image64(xyz - xyz[i], L)
+        r = np.sqrt((d ** 2).sum(1))
+        js = np.where((r <= r_cut) & (np.arange(len(xyz)) != i))[0]
+        out.append((js, d[js]))
+    return out
+
+
+def lj_analytic(pos, lo, hi, r_cut):
+    """hoomd.md.pair.lj(epsilon=1, sigma=1, r_cut) net force, per-particle energy and virial (xx,xy,...)."""
+    n = pos.shape[0]
+    F = np.zeros((n, 3)); E = np.zeros(n); V = np.zeros((n, 6))
+    for i, (js, d) in enumerate(brute_pairs(pos, lo, hi, r_cut)):
+        r2 = (d ** 2).sum(1)
+        ir6 = 1.0 / r2 ** 3
+        # F on i = -dU/dr_i ; d = r_j - r_i  ->  F_i = -(48 r^-14 - 24 r^-8) d
+        fdivr = (48.0 * ir6 * ir6 - 24.0 * ir6) / r2
+        F[i] = -(fdivr[:, None] * d).sum(0)
+        E[i] = 0.5 * (4.0 * (ir6 * ir6 - ir6)).sum()
+        pick = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+        for c, (k, l) in enumerate(pick):
+            V[i, c] = 0.5 * (fdivr * d[:, k] * d[:, l]).sum()      # HOOMD pair virial
+    return F, E, V
+
+
+@pytest.mark.parametrize("n,a", [(5, 3.0), (3, 4.0)])
+def test_lj_forces_vs_analytic_lj(oracle_mod, n, a):
+    """htf/test-py/test_tensorflow.py:335-382: LJModel(32) vs hoomd.md.pair.lj, r_cut=5, atol 1e-5."""
+    pos, lo, hi = synthetic.square_lattice(n, a)
+    pos = synthetic.perturb(pos, lo, hi, 0.15, seed=1)      # the reference runs 20 NVT steps first
+    pos[:, 2] = 0.0
+    nl, idx, cnt = oracle_mod.nlist(pos, lo, hi, 5.0, 32)
+    fe, v9, v6 = oracle_mod.lj(nl)
+    F, E, V = lj_analytic(pos, lo, hi, 5.0)
+    np.testing.assert_allclose(fe[:, :3], F, atol=1e-5)
+    assert np.all(np.sum(F ** 2, axis=1) > 1e-4 ** 2), "forces are too low to assess"
+    np.testing.assert_allclose(fe[:, 3], E, atol=1e-5)       # :400-431 (w column = per-particle energy)
+
+
+def test_lj_virial_vs_pair_virial(oracle_mod):
+    """htf/test-py/test_tensorflow.py:619-671: virial xx, xy vs lj.forces[j].virial, atol 1e-5 (3x3, a=4)."""
+    pos, lo, hi = synthetic.square_lattice(3, 4.0)
+    pos = synthetic.perturb(pos, lo, hi, 0.1, seed=2)
+    pos[:, 2] = 0.0
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 5.0, 32)
+    fe, v9, v6 = oracle_mod.lj(nl)
+    F, E, V = lj_analytic(pos, lo, hi, 5.0)
+    np.testing.assert_allclose(v6[:, 0:2], V[:, 0:2], atol=1e-5)
+    np.testing.assert_allclose(v6, V, atol=1e-5)             # all pairs are attractive here (r > 2^(1/6))
+    # 3x3 -> 6 layout (htf/TensorflowCompute.cc:294-299)
+    np.testing.assert_array_equal(v6, v9[:, [0, 1, 2, 4, 5, 8]])
+    np.testing.assert_array_equal(v9[:, 1], v9[:, 3])
+
+
+def test_inverse_r_forces_vs_python_loop(oracle_mod):
+    """htf/test-py/test_tensorflow.py:20-35,81-104: SimplePotential (F = -sum d/|d|) vs the O(N^2) loop."""
+    pos, lo, hi = synthetic.square_lattice(3, 4.0)
+    pos = synthetic.perturb(pos, lo, hi, 0.2, seed=3)
+    pos[:, 2] = 0.0
+    N, rcut = 9, 5.0
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, rcut, N - 1)
+    d = nl[:, :, :3].astype(np.float64)
+    r = np.sqrt((d ** 2).sum(-1, keepdims=True))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        fr = np.where(r > 0, -d / r, 0.0)
+    got = fr.sum(1)
+    want = np.zeros((N, 3))
+    xyz = pos[:, :3].astype(np.float64)
+    L = np.asarray(hi, np.float64) - np.asarray(lo, np.float64)
+    for i in range(N):
+        for j in range(i + 1, N):
+            rr = min_image64(xyz[j] - xyz[i], L)
+            rd = np.sqrt((rr ** 2).sum())
+            if rd <= rcut:
+                f = -rr / rd
+                want[i] += f
+                want[j] -= f
+    np.testing.assert_allclose(got, want, atol=1e-5)
+
+
+def test_nlist_is_full_not_half(oracle_mod):
+    """htf/test-py/test_tensorflow.py:559-579: 3x3 lattice a=4, r_cut=5 -> every row has 4 neighbors."""
+    pos, lo, hi = synthetic.square_lattice(3, 4.0)
+    nl, _, cnt = oracle_mod.nlist(pos, lo, hi, 5.0, 32)
+    ncount = np.sum(np.sum(nl ** 2, axis=2) > 0.1, axis=1)
+    assert np.min(ncount) == 4 and np.array_equal(ncount, cnt)
+
+
+def test_nlist_vs_bruteforce_bcc(oracle_mod):
+    """htf/test-py/test_utils.py:401-430: bcc 4x4x4 a=4.0, r_cut=5, NN=32; sorted per-row r to 5 decimals."""
+    pos, lo, hi = synthetic.bcc_lattice(4, 4.0)
+    pos = synthetic.perturb(pos, lo, hi, 0.1, seed=4)
+    nl, idx, cnt = oracle_mod.nlist(pos, lo, hi, 5.0, 32)
+    assert cnt.max() <= 32
+    r = np.sqrt((nl[:, :, :3].astype(np.float64) ** 2).sum(-1))
+    for i, (js, d) in enumerate(brute_pairs(pos, lo, hi, 5.0)):
+        want = np.zeros(32); want[:len(js)] = np.sqrt((d ** 2).sum(1))
+        np.testing.assert_array_almost_equal(np.sort(r[i]), np.sort(want), decimal=5)
+        assert set(idx[i][idx[i] >= 0]) == set(js)
+
+
+def test_cells_equal_bruteforce(oracle_mod):
+    """the oracle's cell-list candidate path is bit-identical to its O(N^2) loop (incl. 2-D and tiny grids)."""
+    cases = [synthetic.lattice_fluid((8, 8, 12), 0.7, seed=6) + (2.5, 64),
+             synthetic.square_lattice(16, 2.0) + (3.0, 64),
+             synthetic.lattice_fluid((4, 8, 8), 0.1, seed=1, two_types_p=0.3) + (3.0, 32)]
+    for pos, lo, hi, rc, K in cases:
+        a = oracle_mod.nlist(pos, lo, hi, rc, K, cells=False)
+        b = oracle_mod.nlist(pos, lo, hi, rc, K, cells=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    pos, lo, hi, rc, K = cases[0]
+    full = oracle_mod.nlist(pos, lo, hi, rc, K, cells=True)
+    part = oracle_mod.nlist(pos, lo, hi, rc, K, 100, 300, cells=True)
+    for x, y in zip(full, part):
+        assert np.array_equal(x[100:300], y)          # batch_size / offset chunking (TensorflowCompute.cc:143-150)
+
+
+def test_types_carried_in_w(oracle_mod):
+    """htf/test-py/test_tensorflow.py:46-70: three types visible in nlist[..., 3] and positions[:, 3]."""
+    pos, lo, hi = synthetic.lattice_fluid((5, 5, 5), 0.3, seed=8)
+    pos[:, 3] = np.arange(pos.shape[0]) % 3
+    nl, idx, cnt = oracle_mod.nlist(pos, lo, hi, 3.0, 32)
+    assert len(np.unique(nl[:, :, 3].astype(int))) == 3
+    v = idx >= 0
+    assert np.array_equal(nl[:, :, 3][v], pos[idx[v], 3])
+
+
+def test_overflow_wraps_modulo_k(oracle_mod):
+    """htf/test-py/test_tensorflow.py:830-848 (K=4, r_cut=10, 8x8 lattice) + the % K rule of TensorflowCompute.cc:370."""
+    pos, lo, hi = synthetic.square_lattice(8, 4.0)
+    nl, idx, cnt = oracle_mod.nlist(pos, lo, hi, 10.0, 4)
+    assert cnt.min() > 4                                   # 'Neighbor list is full!'
+    big, idx_big, _ = oracle_mod.nlist(pos, lo, hi, 10.0, 64)
+    for r in range(pos.shape[0]):
+        c = cnt[r]
+        for s in range(4):                                 # slot s holds the last neighbor q with q % 4 == s
+            q = max(q for q in range(c) if q % 4 == s)
+            assert idx[r, s] == idx_big[r, q]
+
+
+def test_typed_rdf_symmetry(oracle_mod):
+    """htf/test-py/test_tensorflow.py:450-485: rdf(A->B) == rdf(B->A), sum > 0."""
+    pos, lo, hi = synthetic.typed_chains()
+    pos = synthetic.perturb(pos, lo, hi, 0.05, seed=1)
+    nl, _, cnt = oracle_mod.nlist(pos, lo, hi, 10.0, 256)
+    assert cnt.max() <= 256
+    ha = oracle_mod.rdf_hist(nl, (0, 10), 100, row_type=pos[:, 3], type_i=0, type_j=1)
+    hb = oracle_mod.rdf_hist(nl, (0, 10), 100, row_type=pos[:, 3], type_i=1, type_j=0)
+    rdfa, rs = oracle_mod.rdf_from_hist(ha, (0, 10))
+    rdfb, _ = oracle_mod.rdf_from_hist(hb, (0, 10))
+    assert rdfa.sum() > 0 and len(rdfa) == 100
+    np.testing.assert_array_almost_equal(rdfa, rdfb)
+
+
+def test_rdf_histogram_against_float64_binning(oracle_mod):
+    """the recalled TF rule (UNPINNED) must at least agree with a float64 histogram away from bin edges."""
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 8), 0.7, seed=12)
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 2.5, 64)
+    h = oracle_mod.rdf_hist(nl, (0.0, 2.5), 100)
+    assert h.sum() == nl.shape[0] * 64
+    r = np.sqrt((nl[:, :, :3].astype(np.float64) ** 2).sum(-1)).ravel()
+    b64 = np.minimum((r / (2.5 / 102)).astype(np.int64), 101)
+    h64 = np.bincount(b64, minlength=102)
+    assert np.abs(h - h64).sum() <= 4                      # only values within an ulp of an edge may move
+    assert h[0] == (r == 0).sum()                          # padded zeros land in bin 0 ("remove 0s", simmodel.py:667)
+
+
+def test_eds_layer_statistics(oracle_mod):
+    """htf/layers.py:142-195: window = second half of each period, Adam step at n == period-1, alpha sign."""
+    eds = oracle_mod.EDSLayer(set_point=4.0, period=10, learning_rate=0.5)
+    rng = np.random.default_rng(0)
+    alphas = [float(eds(5.0 + 0.1 * rng.standard_normal())) for _ in range(30)]
+    assert all(a == 0.0 for a in alphas[:9])               # no update before the first period ends
+    assert alphas[9] != 0.0 and alphas[9] == alphas[10] == alphas[18]
+    # cv above the set point: gradient = -2 (mean - sp) ssd / period / 2 < 0 -> Adam moves alpha up
+    assert alphas[9] > 0.0 and alphas[19] > alphas[9]
+    assert eds.n == 0 and eds.t == 3
