@@ -301,33 +301,35 @@ int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t
     return HTF_OK;
 }
 
-int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, float *d_force_energy, float *d_virial,
+int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy, float *d_virial,
                   int virial_components, void *stream)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (rows < 0 || (rows > 0 && (!d_nlist || !d_force_energy))) { set_err(ctx, "htf_lj_forces: bad arguments"); return HTF_EINVAL; }
+    if (rows < 0 || k < 1 || (rows > 0 && (!d_nlist || !d_force_energy))) { set_err(ctx, "htf_lj_forces: bad arguments"); return HTF_EINVAL; }
     if (d_virial && virial_components != 6 && virial_components != 9) {
         set_err(ctx, "htf_lj_forces: virial_components must be 6 or 9"); return HTF_EINVAL;
     }
     DeviceGuard guard(ctx->device);
-    HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, ctx->K,
+    HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
                                 reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components,
-                                nullptr, 0, nullptr, -1, -1, nullptr, (cudaStream_t)stream));
+                                nullptr, 0, nullptr, 0, -1, -1, nullptr, (cudaStream_t)stream));
     return HTF_OK;
 }
 
-int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, const float *d_row_pos, float r_lo, float r_hi,
-                 int nbins, int type_i, int type_j, int64_t *d_bins, void *stream)
+int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_row_type,
+                 int64_t row_type_stride, float r_lo, float r_hi, int nbins, int type_i, int type_j,
+                 int64_t *d_bins, void *stream)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (rows < 0 || (rows > 0 && !d_nlist) || !d_bins) { set_err(ctx, "htf_rdf_hist: bad arguments"); return HTF_EINVAL; }
-    if (type_i >= 0 && !d_row_pos) { set_err(ctx, "htf_rdf_hist: type_i needs the row positions"); return HTF_EINVAL; }
+    if (rows < 0 || k < 1 || (rows > 0 && !d_nlist) || !d_bins) { set_err(ctx, "htf_rdf_hist: bad arguments"); return HTF_EINVAL; }
+    if (type_i >= 0 && !d_row_type) { set_err(ctx, "htf_rdf_hist: type_i needs the row types"); return HTF_EINVAL; }
+    if (nbins + 2 > 1024) { set_err(ctx, "htf_rdf_hist: nbins must be <= 1022"); return HTF_EINVAL; }
     DeviceGuard guard(ctx->device);
     if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, (cudaStream_t)stream))) return rc;
-    HTF_CUDA(ctx, htf_launch_rdf(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, ctx->K,
-                                 reinterpret_cast<const float4 *>(d_row_pos), ctx->d_rdf_thr, nbins + 2,
+    HTF_CUDA(ctx, htf_launch_rdf(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
+                                 d_row_type, (long long)row_type_stride, ctx->d_rdf_thr, nbins + 2,
                                  type_i, type_j, reinterpret_cast<unsigned long long *>(d_bins),
                                  (cudaStream_t)stream));
     return HTF_OK;
@@ -367,7 +369,7 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
     }
     HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(nl), rows, ctx->K,
                                 reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components,
-                                thr, nb, nullptr, -1, -1, reinterpret_cast<unsigned long long *>(d_bins), st));
+                                thr, nb, nullptr, 0, -1, -1, reinterpret_cast<unsigned long long *>(d_bins), st));
     return HTF_OK;
 }
 

@@ -54,12 +54,12 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
                              int32_t *count_out, int32_t *overflow, cudaStream_t st);
 
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
-                          int vcomp, const float *rdf_thr, int nb, const float4 *row_pos, int type_i, int type_j,
-                          unsigned long long *bins, cudaStream_t st);
+                          int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
+                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st);
 
-cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float4 *row_pos,
-                           const float *thr, int nb, int type_i, int type_j, unsigned long long *bins,
-                           cudaStream_t st);
+cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *row_type,
+                           long long row_type_stride, const float *thr, int nb, int type_i, int type_j,
+                           unsigned long long *bins, cudaStream_t st);
 
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -40,7 +40,8 @@ struct PairParams {
     const float *thr;          // [nb + 1]: thr[b], b = 1..nb-1, ascending thresholds in rsq space
     int nb;                    // nbins + 2
     float r_lo, inv_step;      // first guess only; the thresholds decide
-    const float4 *row_pos;
+    const float *row_type;     // type of row r at row_type[r * row_type_stride]
+    long long row_type_stride;
     int type_i, type_j;
     unsigned long long *bins;
 };
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
         bool row_in_rdf = false;
         if (RDF) {
             row_in_rdf = active;
-            if (active && p.type_i >= 0) row_in_rdf = (__ldg(&p.row_pos[row].w) == (float)p.type_i);
+            if (active && p.type_i >= 0) row_in_rdf = (__ldg(p.row_type + row * p.row_type_stride) == (float)p.type_i);
         }
         for (int s0 = sub; s0 < K; s0 += LPR * LJ_UNROLL) {
             float4 d[LJ_UNROLL];
@@ -204,24 +205,24 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 }  // namespace
 
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
-                          int vcomp, const float *rdf_thr, int nb, const float4 *row_pos, int type_i, int type_j,
-                          unsigned long long *bins, cudaStream_t st)
+                          int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
+                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st)
 {
     if (rows <= 0) return cudaSuccess;
     PairParams p;
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
-    p.row_pos = row_pos; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    p.row_type = row_type; p.row_type_stride = row_type_stride; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
     const bool rdf = bins != nullptr;
     if (rdf && nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
     if (virial) return rdf ? launch_pair<true, true, true>(ctx, p, st) : launch_pair<true, true, false>(ctx, p, st);
     return rdf ? launch_pair<true, false, true>(ctx, p, st) : launch_pair<true, false, false>(ctx, p, st);
 }
 
-cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float4 *row_pos,
-                           const float *thr, int nb, int type_i, int type_j, unsigned long long *bins,
-                           cudaStream_t st)
+cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *row_type,
+                           long long row_type_stride, const float *thr, int nb, int type_i, int type_j,
+                           unsigned long long *bins, cudaStream_t st)
 {
     if (rows <= 0) return cudaSuccess;
     if (nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
@@ -229,6 +230,6 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = nullptr; p.virial = nullptr; p.vcomp = 0;
     p.thr = thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
-    p.row_pos = row_pos; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    p.row_type = row_type; p.row_type_stride = row_type_stride; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
     return launch_pair<false, false, true>(ctx, p, st);
 }

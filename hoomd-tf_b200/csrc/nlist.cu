@@ -16,11 +16,20 @@
 // Arithmetic is the oracle's, bit for bit: d = p_j - p_i, compare-and-shift minimum image
 // (HOOMD BoxDim::minImage CPU branch), rsq = (dx*dx + dy*dy) + dz*dz with explicit
 // round-to-nearest mul/add (never contracted to FMA), keep iff rsq <= rc^2.
+//
+// The hot loop is kept branch-light: the staged candidate list is padded to a multiple of
+// 32 with +inf sentinels (never a hit), rows missing from the last group of four sit at
+// +inf too, each row buffer has 32 spare slots so a chunk can be appended without a bounds
+// check, and the modulo-K overflow rule of the reference (htf/TensorflowCompute.cc:370)
+// lives in a separate slow path entered only once a row has more than K neighbors.
 #include "common.cuh"
+
+#include <math_constants.h>
 
 namespace {
 
-constexpr int ROWS_PER_PASS = 4;   // rows tested against each staged candidate chunk
+constexpr int RPP = 4;            // rows tested against each staged candidate chunk
+constexpr int SPARE = 32;         // spare slots per row buffer (one chunk of hits)
 
 struct NlistParams {
     CellGrid g;
@@ -46,56 +55,121 @@ __device__ __forceinline__ float wrap_axis(float d, float lo, float hi, float L)
     return __fsub_rn(d, adj);
 }
 
-template <bool WRAP, bool WITH_IDX>
-__device__ __forceinline__ void test_chunks(const NlistParams &p, const float4 *cand, const int *candidx,
-                                            int mstage, int vbase, const float (&pix)[ROWS_PER_PASS],
-                                            const float (&piy)[ROWS_PER_PASS], const float (&piz)[ROWS_PER_PASS],
-                                            const float (&pit)[ROWS_PER_PASS], const int (&vself)[ROWS_PER_PASS],
-                                            const bool (&rvalid)[ROWS_PER_PASS], int (&cnt)[ROWS_PER_PASS],
-                                            float4 *rowbuf, int *rowidx, int lane)
+__device__ __forceinline__ void sts128(unsigned addr, float x, float y, float z, float w)
 {
-    const int K = p.K;
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+struct RowState {
+    float x[RPP], y[RPP], z[RPP], t[RPP];
+    int self_rel[RPP];      // index of the row's own particle inside the staged window (or -1)
+    unsigned wp[RPP];       // shared-space byte address of the row's next free slot
+    unsigned lim[RPP];      // shared-space byte address of the row's slot K (fast path may not pass it)
+};
+
+// pair test shared by the fast and the slow path
+template <bool WRAP, bool MAPPED>
+__device__ __forceinline__ bool pair_hit(const NlistParams &p, const float4 &c, const RowState &rs, int r, int tl,
+                                         float &dx, float &dy, float &dz)
+{
+    dx = __fsub_rn(c.x, rs.x[r]);
+    dy = __fsub_rn(c.y, rs.y[r]);
+    dz = __fsub_rn(c.z, rs.z[r]);
+    if (WRAP) {
+        dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+        dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+        dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+    }
+    const float rsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; the +inf sentinels give inf/NaN -> no hit
+    bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]);
+    if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
+    return hit;
+}
+
+// Fast path: appends without bounds checks (row buffers have SPARE extra slots).  Returns the
+// chunk offset at which some row exceeded K (the caller switches to the slow path there), or
+// mround when the window is exhausted.
+template <bool WRAP, bool MAPPED, bool WITH_IDX>
+__device__ __forceinline__ int test_fast(const NlistParams &p, const float4 *cand, const int *candidx, int mround,
+                                         RowState &rs, unsigned rowbuf_s, int *rowidx, int stride, int lane)
+{
     const unsigned lt = (1u << lane) - 1u;
-    for (int t0 = 0; t0 < mstage; t0 += 32) {
-        const int t = t0 + lane;
-        const bool valid = t < mstage;
-        float4 c = valid ? cand[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int t0 = 0;
+    for (; t0 < mround; t0 += 32) {
+        const int tl = t0 + lane;
+        const float4 c = cand[tl];
         int cj = 0;
-        if (WITH_IDX) cj = valid ? candidx[t] : -1;
+        if (WITH_IDX) cj = candidx[tl];
+        bool ovf = false;
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_PASS; r++) {
-            if (!rvalid[r]) continue;                       // warp-uniform
-            float dx = __fsub_rn(c.x, pix[r]);
-            float dy = __fsub_rn(c.y, piy[r]);
-            float dz = __fsub_rn(c.z, piz[r]);
-            if (WRAP) {
-                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
-            }
-            float rsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            bool hit = valid && !(rsq > p.rc2) && (vbase + t != vself[r]);
-            if (p.map_type_start >= 0)                       // warp-uniform
-                hit = hit && (((int)c.w >= p.map_type_start) == ((int)pit[r] >= p.map_type_start));
+        for (int r = 0; r < RPP; r++) {
+            float dx, dy, dz;
+            const bool hit = pair_hit<WRAP, MAPPED>(p, c, rs, r, tl, dx, dy, dz);
             const unsigned mask = __ballot_sync(HTF_FULL, hit);
-            if (mask) {                                      // warp-uniform
-                const int nh = __popc(mask);
-                const int rank = __popc(mask & lt);
-                // slot wraps modulo K like htf/TensorflowCompute.cc:370; when one chunk holds
-                // more than K hits only the last writer of a slot may store.
-                if (hit && (rank + K >= nh)) {
-                    int q = cnt[r] + rank;
-                    if (q >= K) q %= K;
-                    rowbuf[r * K + q] = make_float4(dx, dy, dz, c.w);
-                    if (WITH_IDX) rowidx[r * K + q] = cj;
-                }
-                cnt[r] += nh;
+            const unsigned a = rs.wp[r] + (unsigned)__popc(mask & lt) * 16u;
+            if (hit) {
+                sts128(a, dx, dy, dz, c.w);
+                if (WITH_IDX) rowidx[(a - rowbuf_s) >> 4] = cj;
             }
+            rs.wp[r] += (unsigned)__popc(mask) * 16u;
+            ovf |= rs.wp[r] > rs.lim[r];
+        }
+        if (ovf) { t0 += 32; break; }
+    }
+    return t0;
+}
+
+// Slow path (some row overflowed K): slot index wraps modulo K like htf/TensorflowCompute.cc:370;
+// when one chunk holds more than K hits only the last writer of a slot may store.  Always applies
+// the minimum image (a no-op for interior cells) so that a single copy of this cold code exists.
+template <bool MAPPED, bool WITH_IDX>
+__device__ __forceinline__ void test_slow(const NlistParams &p, const float4 *cand, const int *candidx, int t_begin,
+                                          int mround, const RowState &rs, int (&cnt)[RPP], float4 *rowbuf, int *rowidx,
+                                          int stride, int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    const int K = p.K;
+    for (int t0 = t_begin; t0 < mround; t0 += 32) {
+        const int tl = t0 + lane;
+        const float4 c = cand[tl];
+        int cj = 0;
+        if (WITH_IDX) cj = candidx[tl];
+#pragma unroll
+        for (int r = 0; r < RPP; r++) {
+            float dx, dy, dz;
+            const bool hit = pair_hit<true, MAPPED>(p, c, rs, r, tl, dx, dy, dz);
+            const unsigned mask = __ballot_sync(HTF_FULL, hit);
+            const int nh = __popc(mask);
+            const int rank = __popc(mask & lt);
+            if (hit && (rank + K >= nh)) {
+                const int q = (cnt[r] + rank) % K;
+                rowbuf[r * stride + q] = make_float4(dx, dy, dz, c.w);
+                if (WITH_IDX) rowidx[r * stride + q] = cj;
+            }
+            cnt[r] += nh;
         }
     }
 }
 
+// after the chunk that pushed a row past K: move entries K.. down to (q mod K), in order
 template <bool WITH_IDX>
+__device__ __forceinline__ void fold_overflow(const NlistParams &p, const int (&cnt)[RPP], float4 *rowbuf, int *rowidx,
+                                              int stride, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RPP; r++)
+            for (int q = p.K; q < cnt[r]; q++) {
+                rowbuf[r * stride + q % p.K] = rowbuf[r * stride + q];
+                if (WITH_IDX) rowidx[r * stride + q % p.K] = rowidx[r * stride + q];
+            }
+    }
+    __syncwarp();
+}
+
+template <bool WITH_IDX, bool MAPPED>
 __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -106,12 +180,13 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
     if (cell >= p.g.ncell) return;
 
     const int K = p.K;
-    // per-warp carve-up: cand[cap] f4 | rowbuf[R*K] f4 | (candidx[cap] i32 | rowidx[R*K] i32)
-    const size_t per_warp = (size_t)(p.cap + ROWS_PER_PASS * K) * (WITH_IDX ? 20 : 16);
+    const int stride = K + SPARE;        // row buffer pitch in slots
+    // per-warp carve-up: cand[cap] f4 | rowbuf[RPP*stride] f4 | (candidx[cap] i32 | rowidx[RPP*stride] i32)
+    const size_t per_warp = (size_t)(p.cap + RPP * stride) * (WITH_IDX ? 20 : 16);
     unsigned char *base = smem_raw + per_warp * warp;
     float4 *cand = reinterpret_cast<float4 *>(base);
     float4 *rowbuf = cand + p.cap;
-    int *candidx = reinterpret_cast<int *>(rowbuf + ROWS_PER_PASS * K);
+    int *candidx = reinterpret_cast<int *>(rowbuf + RPP * stride);
     int *rowidx = candidx + p.cap;
 
     const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
@@ -166,6 +241,8 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
     const int cap = p.cap;
     const int npass = (m + cap - 1) / cap;
 
+    // stage window `pass` of the virtual candidate list; returns its length rounded up to 32
+    // (the tail is filled with +inf sentinels, which can never be a hit)
     auto stage = [&](int pass) {
         const int w0 = pass * cap, w1 = min(m, w0 + cap);
         unsigned rm = runmask;
@@ -182,61 +259,101 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 if (WITH_IDX) candidx[t - w0] = __ldg(p.sorted_idx + s);
             }
         }
+        const int len = w1 - w0, mround = (len + 31) & ~31;
+        if (len + lane < mround) {
+            cand[len + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+            if (WITH_IDX) candidx[len + lane] = -1;
+        }
         __syncwarp();
-        return w1 - w0;
+        return mround;
     };
 
-    int mstage = 0;
-    if (npass == 1) mstage = stage(0);
+    int mround = 0;
+    if (npass == 1) mround = stage(0);
 
-    for (int s0 = b; s0 < e; s0 += ROWS_PER_PASS) {
-        float pix[ROWS_PER_PASS], piy[ROWS_PER_PASS], piz[ROWS_PER_PASS], pit[ROWS_PER_PASS];
-        int vself[ROWS_PER_PASS], orig[ROWS_PER_PASS], cnt[ROWS_PER_PASS];
-        bool rvalid[ROWS_PER_PASS];
+    const unsigned rowbuf_s = (unsigned)__cvta_generic_to_shared(rowbuf);
+    for (int s0 = b; s0 < e; s0 += RPP) {
+        RowState rs;
+        int orig[RPP], cnt[RPP];
         bool anyrow = false;
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_PASS; r++) {
+        for (int r = 0; r < RPP; r++) {
             const int s = s0 + r;
-            rvalid[r] = s < e;
-            orig[r] = rvalid[r] ? __ldg(p.sorted_idx + s) : -1;
-            rvalid[r] = rvalid[r] && orig[r] >= p.row_lo && orig[r] < p.row_hi;
-            float4 pi = rvalid[r] ? __ldg(p.spos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-            pix[r] = pi.x; piy[r] = pi.y; piz[r] = pi.z; pit[r] = pi.w;
-            vself[r] = self_base + s;
+            bool ok = s < e;
+            orig[r] = ok ? __ldg(p.sorted_idx + s) : -1;
+            ok = ok && orig[r] >= p.row_lo && orig[r] < p.row_hi;
+            if (!ok) orig[r] = -1;
+            const float4 pi = ok ? __ldg(p.spos + s)
+                                 : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);   // never hits
+            rs.x[r] = pi.x; rs.y[r] = pi.y; rs.z[r] = pi.z; rs.t[r] = pi.w;
+            rs.wp[r] = rowbuf_s + (unsigned)(r * stride) * 16u;
+            rs.lim[r] = rs.wp[r] + (unsigned)K * 16u;
             cnt[r] = 0;
-            anyrow |= rvalid[r];
+            anyrow |= ok;
         }
         if (!anyrow) continue;
 
+        bool overflowed = false;
         for (int pass = 0; pass < npass; pass++) {
-            if (npass > 1) { __syncwarp(); mstage = stage(pass); }
-            if (wrap)
-                test_chunks<true, WITH_IDX>(p, cand, candidx, mstage, pass * cap, pix, piy, piz, pit, vself,
-                                            rvalid, cnt, rowbuf, rowidx, lane);
-            else
-                test_chunks<false, WITH_IDX>(p, cand, candidx, mstage, pass * cap, pix, piy, piz, pit, vself,
-                                             rvalid, cnt, rowbuf, rowidx, lane);
+            if (npass > 1) { __syncwarp(); mround = stage(pass); }
+#pragma unroll
+            for (int r = 0; r < RPP; r++) {
+                const int rel = self_base + s0 + r - pass * cap;       // own particle inside this window?
+                rs.self_rel[r] = (orig[r] >= 0 && rel >= 0 && rel < mround) ? rel : -1;
+            }
+            int t = 0;
+            if (!overflowed) {
+                t = wrap ? test_fast<true, MAPPED, WITH_IDX>(p, cand, candidx, mround, rs, rowbuf_s, rowidx, stride, lane)
+                         : test_fast<false, MAPPED, WITH_IDX>(p, cand, candidx, mround, rs, rowbuf_s, rowidx, stride, lane);
+                int cmax = 0;
+#pragma unroll
+                for (int r = 0; r < RPP; r++) {
+                    cnt[r] = (int)((rs.wp[r] - rowbuf_s) >> 4) - r * stride;
+                    cmax = max(cmax, cnt[r]);
+                }
+                if (cmax > K) {
+                    overflowed = true;
+                    fold_overflow<WITH_IDX>(p, cnt, rowbuf, rowidx, stride, lane);
+                }
+            }
+            if (overflowed && t < mround)
+                test_slow<MAPPED, WITH_IDX>(p, cand, candidx, t, mround, rs, cnt, rowbuf, rowidx, stride, lane);
         }
         __syncwarp();
 
         // ---- flush: one contiguous K*16 B store per row, zero padded ----
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_PASS; r++) {
-            if (!rvalid[r]) continue;
+        for (int r = 0; r < RPP; r++) {
+            if (orig[r] < 0) continue;
             const size_t row = (size_t)(orig[r] - p.row_lo);
             float4 *dst = p.out + row * K;
+            const int c = cnt[r];
             for (int s = lane; s < K; s += 32) {
-                float4 v = (s < cnt[r]) ? rowbuf[r * K + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v = (s < c) ? rowbuf[r * stride + s] : make_float4(0.f, 0.f, 0.f, 0.f);
                 dst[s] = v;
-                if (WITH_IDX) p.idx_out[row * K + s] = (s < cnt[r]) ? rowidx[r * K + s] : -1;
+                if (WITH_IDX) p.idx_out[row * K + s] = (s < c) ? rowidx[r * stride + s] : -1;
             }
             if (lane == 0) {
-                if (p.count_out) p.count_out[row] = cnt[r];
-                if (p.overflow && cnt[r] >= K) atomicMax(p.overflow, cnt[r]);
+                if (p.count_out) p.count_out[row] = c;
+                if (p.overflow && c >= K) atomicMax(p.overflow, c);
             }
         }
         __syncwarp();
     }
+}
+
+template <bool WITH_IDX, bool MAPPED>
+cudaError_t launch_variant(const NlistParams &p, int grid, int wpb, size_t smem, cudaStream_t st)
+{
+    static size_t configured = 0;        // per instantiation: largest dynamic smem opted in so far
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nlist_build_kernel<WITH_IDX, MAPPED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    nlist_build_kernel<WITH_IDX, MAPPED><<<grid, wpb * 32, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -268,29 +385,24 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     int cap = (int)(mean + 5.0 * sqrt(mean > 1.0 ? mean : 1.0)) + 32;
     cap = (cap + 31) / 32 * 32;
     const bool with_idx = idx_out != nullptr;
+    const bool mapped = ctx->map_type_start >= 0;
     const int bytes_per = with_idx ? 20 : 16;
+    const int stride = p.K + SPARE;
     int wpb = 4;
     const size_t smem_max = 200 * 1024;
     // keep the per-block footprint within the opt-in limit; shrink the staging window first
     // (the kernel re-stages in passes), then the block
-    while ((size_t)(cap + ROWS_PER_PASS * p.K) * bytes_per * wpb > smem_max) {
+    while ((size_t)(cap + RPP * stride) * bytes_per * wpb > smem_max) {
         if (cap > 64) cap = max(64, cap / 2 / 32 * 32);
         else if (wpb > 1) wpb /= 2;
         else return cudaErrorInvalidValue;
     }
     p.cap = cap;
-    const size_t smem = (size_t)(cap + ROWS_PER_PASS * p.K) * bytes_per * wpb;
+    const size_t smem = (size_t)(cap + RPP * stride) * bytes_per * wpb;
     const int grid = (g.ncell + wpb - 1) / wpb;
-    cudaError_t e;
-    if (with_idx) {
-        e = cudaFuncSetAttribute(nlist_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        nlist_build_kernel<true><<<grid, wpb * 32, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(nlist_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        nlist_build_kernel<false><<<grid, wpb * 32, smem, st>>>(p);
-    }
     ctx->launches += 1;
-    return cudaGetLastError();
+    if (with_idx) return mapped ? launch_variant<true, true>(p, grid, wpb, smem, st)
+                                : launch_variant<true, false>(p, grid, wpb, smem, st);
+    return mapped ? launch_variant<false, true>(p, grid, wpb, smem, st)
+                  : launch_variant<false, false>(p, grid, wpb, smem, st);
 }

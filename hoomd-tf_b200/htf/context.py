@@ -121,28 +121,42 @@ class HtfContext:
 
     def lj_forces(self, nlist, virial=False, virial_components=6, out=None, virial_out=None):
         _check_dev_f32(nlist, "nlist", 4)
-        if nlist.dim() != 3 or nlist.shape[1] != self.K:
-            raise ValueError("nlist must be [rows, %d, 4]" % self.K)
-        rows = nlist.shape[0]
+        if nlist.dim() != 3:
+            raise ValueError("nlist must be [rows, K, 4]")
+        rows, k = nlist.shape[0], nlist.shape[1]
         fe = out if out is not None else torch.empty((rows, 4), dtype=torch.float32, device=self.device)
         vir = None
         if virial:
             vir = virial_out if virial_out is not None else \
                 torch.empty((rows, virial_components), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.htf_lj_forces(self._h, _ptr(nlist), rows, _ptr(fe), _ptr(vir), int(virial_components),
-                                        self._stream()))
+        self._ck(self.lib.htf_lj_forces(self._h, _ptr(nlist), rows, int(k), _ptr(fe), _ptr(vir),
+                                        int(virial_components), self._stream()))
         return (fe, vir) if virial else fe
 
-    def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None):
-        """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given."""
+    def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None,
+                 type_tensor=None):
+        """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given.
+
+        Row types come either from ``row_pos`` ([rows,4] positions, column 3) or from
+        ``type_tensor`` (any 1-D float32 view, e.g. ``positions[:, 3]``; its stride is honoured)."""
         _check_dev_f32(nlist, "nlist", 4)
-        rows = nlist.shape[0]
+        rows, k = nlist.shape[0], nlist.shape[1]
         if bins is None:
             bins = torch.zeros((nbins + 2,), dtype=torch.int64, device=self.device)
+        tptr, tstride = None, 0
         if row_pos is not None:
             _check_dev_f32(row_pos, "row positions", 4)
-        self._ck(self.lib.htf_rdf_hist(self._h, _ptr(nlist), rows, _ptr(row_pos), float(r_range[0]), float(r_range[1]),
-                                       int(nbins), -1 if type_i is None else int(type_i),
+            tptr, tstride = ctypes.c_void_p(row_pos.data_ptr() + 12), 4
+        elif type_tensor is not None:
+            t = type_tensor
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 1):
+                raise ValueError("type_tensor must be a 1-D float32 CUDA tensor")
+            tptr, tstride = ctypes.c_void_p(t.data_ptr()), (t.stride(0) if t.shape[0] > 1 else 1)
+        if tptr is not None and (row_pos if row_pos is not None else type_tensor).shape[0] != rows:
+            raise ValueError("row types must have one entry per nlist row")
+        self._ck(self.lib.htf_rdf_hist(self._h, _ptr(nlist), rows, int(k), tptr, int(tstride),
+                                       float(r_range[0]), float(r_range[1]), int(nbins),
+                                       -1 if type_i is None else int(type_i),
                                        -1 if type_j is None else int(type_j), _ptr(bins), self._stream()))
         return bins
 

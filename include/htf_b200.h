@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 3
+#define HTF_ABI_VERSION 4
 int htf_abi_version(void);
 
 /*
@@ -117,23 +117,26 @@ int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t
  * _add_energy (:558-578) -> _compute_virial (:509-523), and the TfToHoomd copies plus the
  * 3x3 -> 6 virial scatter (htf/tf2hoomd_op/tf2hoomd.cc:48-59, htf/TensorflowCompute.cc:285-301,
  * htf/TensorflowCompute.cu:41-71).
+ *   k               second dimension of d_nlist
  *   d_force_energy  float[rows][4] = (Fx, Fy, Fz, e_i)
  *   d_virial        nullable; virial_components = 6: float[rows][6] (xx,xy,xz,yy,yz,zz);
  *                   = 9: float[rows][9] row-major 3x3 (what get_virial_array returns,
  *                   htf/tensorflowcompute.py:388-392)
  */
-int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, float *d_force_energy,
+int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
                   float *d_virial, int virial_components, void *stream);
 
 /*
  * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,
  * tf.histogram_fixed_width over nbins+2 bins).  Adds this call's counts to d_bins
  * (int64[nbins+2], caller zeroes; bins 0 and nbins+1 are the ones the reference drops).
- *   d_row_type  nullable float[rows][4] positions of the rows (only .w is read) -- needed
- *               when type_i >= 0;  type_i / type_j < 0 = None.
+ *   d_row_type  nullable: type of the particle of each row, read as d_row_type[row * row_type_stride]
+ *               (pass positions + 3 with stride 4 for `positions[:, 3]`) -- needed when
+ *               type_i >= 0;  type_i / type_j < 0 = None.
+ *   k           second dimension of d_nlist (any k >= 1, independent of the context's cutoff).
  */
-int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, const float *d_row_pos,
-                 float r_lo, float r_hi, int nbins, int type_i, int type_j,
+int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_row_type,
+                 int64_t row_type_stride, float r_lo, float r_hi, int nbins, int type_i, int type_j,
                  int64_t *d_bins, void *stream);
 
 /*

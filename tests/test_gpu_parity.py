@@ -133,7 +133,7 @@ def test_lj_step_fused_matches_separate(oracle_mod):
     # and without a caller-provided tensor (context scratch)
     fe3 = ctx.lj_step(dpos)
     torch.cuda.synchronize()
-    assert torch.equal(fe, fe3)
+    assert torch.equal(ctx.lj_forces(nl), fe3)        # same (virial-less) kernel variant -> bit-identical
     nl_o, _, _ = oracle_mod.nlist(pos, lo, hi, r_cut, K)
     fe_o, _, v6_o = oracle_mod.lj(nl_o)
     assert_close_rel(fe.cpu().numpy(), fe_o, what="force+energy")
