@@ -55,6 +55,16 @@ __device__ __forceinline__ float wrap_axis(float d, float lo, float hi, float L)
     return __fsub_rn(d, adj);
 }
 
+__device__ __forceinline__ void cp_async16(unsigned dst_s, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(unsigned dst_s, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s), "l"(src) : "memory");
+}
+
 __device__ __forceinline__ void sts128(unsigned addr, float x, float y, float z, float w)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
@@ -243,6 +253,8 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
 
     // stage window `pass` of the virtual candidate list; returns its length rounded up to 32
     // (the tail is filled with +inf sentinels, which can never be a hit)
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
     auto stage = [&](int pass) {
         const int w0 = pass * cap, w1 = min(m, w0 + cap);
         unsigned rm = runmask;
@@ -253,10 +265,11 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
             const int ql = __shfl_sync(HTF_FULL, rl, q);
             const int qo = __shfl_sync(HTF_FULL, roff, q);
             const int lo = max(qo, w0), hi = min(qo + ql, w1);
+            // asynchronous global->shared copies: every run is in flight before the single wait below
             for (int t = lo + lane; t < hi; t += 32) {
                 const int s = qb + (t - qo);
-                cand[t - w0] = __ldg(p.spos + s);
-                if (WITH_IDX) candidx[t - w0] = __ldg(p.sorted_idx + s);
+                cp_async16(cand_s + (unsigned)(t - w0) * 16u, p.spos + s);
+                if (WITH_IDX) cp_async4(candidx_s + (unsigned)(t - w0) * 4u, p.sorted_idx + s);
             }
         }
         const int len = w1 - w0, mround = (len + 31) & ~31;
@@ -264,6 +277,7 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
             cand[len + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
             if (WITH_IDX) candidx[len + lane] = -1;
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         return mround;
     };
@@ -278,13 +292,12 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
         bool anyrow = false;
 #pragma unroll
         for (int r = 0; r < RPP; r++) {
-            const int s = s0 + r;
-            bool ok = s < e;
-            orig[r] = ok ? __ldg(p.sorted_idx + s) : -1;
-            ok = ok && orig[r] >= p.row_lo && orig[r] < p.row_hi;
-            if (!ok) orig[r] = -1;
-            const float4 pi = ok ? __ldg(p.spos + s)
-                                 : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);   // never hits
+            const int s = min(s0 + r, e - 1);                    // both loads are independent of each other
+            const int o = __ldg(p.sorted_idx + s);
+            float4 pi = __ldg(p.spos + s);
+            const bool ok = (s0 + r < e) && o >= p.row_lo && o < p.row_hi;
+            orig[r] = ok ? o : -1;
+            if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);           // never hits
             rs.x[r] = pi.x; rs.y[r] = pi.y; rs.z[r] = pi.z; rs.t[r] = pi.w;
             rs.wp[r] = rowbuf_s + (unsigned)(r * stride) * 16u;
             rs.lim[r] = rs.wp[r] + (unsigned)K * 16u;

@@ -199,12 +199,12 @@ def test_mapped_nlist_pair_rule(oracle_mod):
     from htf import synthetic
     pos, lo, hi = synthetic.lattice_fluid((8, 8, 8), 0.5, seed=9)
     pos[-40:, 3] = 2.0 + (np.arange(40) % 2)          # beads: types 2,3 ; AA: type 0
-    K, r_cut = 64, 3.0
+    K, r_cut = 96, 3.0
     ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
     ctx.set_mapped_nlist(2)
     nl_g, idx_g, cnt_g = gpu_nlist(ctx, pos)
     nl_o, idx_o, cnt_o = oracle_mod.nlist(pos, lo, hi, r_cut, K, map_type_start=2)
-    assert np.array_equal(cnt_g, cnt_o)
+    assert np.array_equal(cnt_g, cnt_o) and cnt_o.max() <= K
     nls, ids = sort_rows(nl_g.cpu().numpy(), idx_g)
     assert np.array_equal(ids, idx_o) and np.array_equal(nls.view(np.uint32), nl_o.view(np.uint32))
 
