@@ -5,31 +5,36 @@
 // (htf/TensorflowCompute.cu:80-151: one thread per row, 16-byte stores strided by 16*K)
 // and the cudaMemset before it (.cu:180).
 //
-// Work decomposition: one warp per cell.  The warp stages the positions of the 3x3x3
-// stencil (9 contiguous runs of the cell-sorted array when the x-neighbours do not wrap)
-// into shared memory once, then walks the rows of its cell four at a time: every lane
-// holds one candidate, tests it against the four rows, and hits are compacted with
-// ballot/popc into a per-row shared-memory buffer.  A finished row leaves the SM as one
-// contiguous K*16-byte coalesced store, zero padding included -- there is no memset pass
-// and no partial-sector traffic.
+// Work decomposition: one warp per cell.
+//   stage : the positions of the 3x3x3 stencil (9 contiguous runs of the cell-sorted array
+//           when the x-neighbours do not wrap) are copied to shared memory with cp.async;
+//   test  : the rows of the cell are taken four at a time; every lane holds one candidate
+//           per 32-candidate chunk, tests it against the four rows and, on a hit, appends the
+//           candidate's 16-bit index to its own (lane-private) list of that row -- one
+//           predicated store and one predicated add, no ballot / popc / branch;
+//   emit  : per row, an exclusive scan of the lane counts gives every lane its slot range; the
+//           lanes publish "slot -> candidate" in a small shared map, then lane s re-derives d
+//           for slot s, s+32, ... and the row leaves the SM as contiguous coalesced 16-byte
+//           stores, zero padding included -- no memset pass, no partial-sector traffic.
 //
 // Arithmetic is the oracle's, bit for bit: d = p_j - p_i, compare-and-shift minimum image
-// (HOOMD BoxDim::minImage CPU branch), rsq = (dx*dx + dy*dy) + dz*dz with explicit
-// round-to-nearest mul/add (never contracted to FMA), keep iff rsq <= rc^2.
+// (HOOMD BoxDim::minImage CPU branch), rsq = (dx*dx + dy*dy) + dz*dz with round-to-nearest
+// mul/add that are never contracted to FMA, keep iff rsq <= rc^2.  The subtractions and the
+// squares use Blackwell's packed fp32 pipe (add/mul .f32x2: two rows per instruction, each
+// half IEEE-rounded like the scalar op); the sums stay scalar because ptxas contracts a
+// packed mul feeding a packed add into FFMA2 even with .rn.
 //
-// The hot loop is kept branch-light: the staged candidate list is padded to a multiple of
-// 32 with +inf sentinels (never a hit), rows missing from the last group of four sit at
-// +inf too, each row buffer has 32 spare slots so a chunk can be appended without a bounds
-// check, and the modulo-K overflow rule of the reference (htf/TensorflowCompute.cc:370)
-// lives in a separate slow path entered only once a row has more than K neighbors.
+// Slot order inside a row is lane-major (lane 0's hits in candidate order, then lane 1's, ...):
+// deterministic, and as unspecified as the reference's HOOMD-internal order.  When a row has
+// more than K neighbors the slot index wraps modulo K and the last writer wins, exactly like
+// htf/TensorflowCompute.cc:370 (with this kernel's hit order).
 #include "common.cuh"
 
 #include <math_constants.h>
 
 namespace {
 
-constexpr int RPP = 4;            // rows tested against each staged candidate chunk
-constexpr int SPARE = 32;         // spare slots per row buffer (one chunk of hits)
+constexpr int RPP = 4;            // rows tested against each staged candidate chunk (even)
 
 struct NlistParams {
     CellGrid g;
@@ -41,12 +46,37 @@ struct NlistParams {
     int K;
     float rc2;
     int map_type_start;
-    int cap;             // candidates staged per pass, multiple of 32
+    int cap;             // candidates staged per pass, multiple of 32, <= 32768
     float4 *out;
     int *idx_out;
     int *count_out;
     int *overflow;
 };
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 __device__ __forceinline__ float wrap_axis(float d, float lo, float hi, float L)
 {
@@ -59,124 +89,83 @@ __device__ __forceinline__ void cp_async16(unsigned dst_s, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
 }
-
 __device__ __forceinline__ void cp_async4(unsigned dst_s, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s), "l"(src) : "memory");
 }
-
-__device__ __forceinline__ void sts128(unsigned addr, float x, float y, float z, float w)
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v)
 {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ int lds_i32(unsigned addr)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 struct RowState {
-    float x[RPP], y[RPP], z[RPP], t[RPP];
+    f32x2 x[RPP / 2], y[RPP / 2], z[RPP / 2];   // row pairs packed for the f32x2 pipe
+    float t[RPP];                               // row types (mapped-nlist rule)
     int self_rel[RPP];      // index of the row's own particle inside the staged window (or -1)
-    unsigned wp[RPP];       // shared-space byte address of the row's next free slot
-    unsigned lim[RPP];      // shared-space byte address of the row's slot K (fast path may not pass it)
+    unsigned lp[RPP];       // shared-space byte address of this lane's next list entry for row r
 };
 
-// pair test shared by the fast and the slow path
+// ---- test: append the window-relative index of every hit to the lane-private lists ----
 template <bool WRAP, bool MAPPED>
-__device__ __forceinline__ bool pair_hit(const NlistParams &p, const float4 &c, const RowState &rs, int r, int tl,
-                                         float &dx, float &dy, float &dz)
+__device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, RowState &rs,
+                                            int lane)
 {
-    dx = __fsub_rn(c.x, rs.x[r]);
-    dy = __fsub_rn(c.y, rs.y[r]);
-    dz = __fsub_rn(c.z, rs.z[r]);
-    if (WRAP) {
-        dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-        dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-        dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
-    }
-    const float rsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; the +inf sentinels give inf/NaN -> no hit
-    bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]);
-    if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
-    return hit;
-}
-
-// Fast path: appends without bounds checks (row buffers have SPARE extra slots).  Returns the
-// chunk offset at which some row exceeded K (the caller switches to the slow path there), or
-// mround when the window is exhausted.
-template <bool WRAP, bool MAPPED, bool WITH_IDX>
-__device__ __forceinline__ int test_fast(const NlistParams &p, const float4 *cand, const int *candidx, int mround,
-                                         RowState &rs, unsigned rowbuf_s, int *rowidx, int stride, int lane)
-{
-    const unsigned lt = (1u << lane) - 1u;
-    int t0 = 0;
-    for (; t0 < mround; t0 += 32) {
+#pragma unroll 1
+    for (int t0 = 0; t0 < mround; t0 += 32) {
         const int tl = t0 + lane;
         const float4 c = cand[tl];
-        int cj = 0;
-        if (WITH_IDX) cj = candidx[tl];
-        bool ovf = false;
+        const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
 #pragma unroll
-        for (int r = 0; r < RPP; r++) {
-            float dx, dy, dz;
-            const bool hit = pair_hit<WRAP, MAPPED>(p, c, rs, r, tl, dx, dy, dz);
-            const unsigned mask = __ballot_sync(HTF_FULL, hit);
-            const unsigned a = rs.wp[r] + (unsigned)__popc(mask & lt) * 16u;
-            if (hit) {
-                sts128(a, dx, dy, dz, c.w);
-                if (WITH_IDX) rowidx[(a - rowbuf_s) >> 4] = cj;
-            }
-            rs.wp[r] += (unsigned)__popc(mask) * 16u;
-            ovf |= rs.wp[r] > rs.lim[r];
-        }
-        if (ovf) { t0 += 32; break; }
-    }
-    return t0;
-}
-
-// Slow path (some row overflowed K): slot index wraps modulo K like htf/TensorflowCompute.cc:370;
-// when one chunk holds more than K hits only the last writer of a slot may store.  Always applies
-// the minimum image (a no-op for interior cells) so that a single copy of this cold code exists.
-template <bool MAPPED, bool WITH_IDX>
-__device__ __forceinline__ void test_slow(const NlistParams &p, const float4 *cand, const int *candidx, int t_begin,
-                                          int mround, const RowState &rs, int (&cnt)[RPP], float4 *rowbuf, int *rowidx,
-                                          int stride, int lane)
-{
-    const unsigned lt = (1u << lane) - 1u;
-    const int K = p.K;
-    for (int t0 = t_begin; t0 < mround; t0 += 32) {
-        const int tl = t0 + lane;
-        const float4 c = cand[tl];
-        int cj = 0;
-        if (WITH_IDX) cj = candidx[tl];
+        for (int h = 0; h < RPP / 2; h++) {
+            float dx[2], dy[2], dz[2], xx[2], yy[2], zz[2];
+            const f32x2 dx2 = sub2(cx, rs.x[h]), dy2 = sub2(cy, rs.y[h]), dz2 = sub2(cz, rs.z[h]);
+            if (WRAP) {
+                unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
 #pragma unroll
-        for (int r = 0; r < RPP; r++) {
-            float dx, dy, dz;
-            const bool hit = pair_hit<true, MAPPED>(p, c, rs, r, tl, dx, dy, dz);
-            const unsigned mask = __ballot_sync(HTF_FULL, hit);
-            const int nh = __popc(mask);
-            const int rank = __popc(mask & lt);
-            if (hit && (rank + K >= nh)) {
-                const int q = (cnt[r] + rank) % K;
-                rowbuf[r * stride + q] = make_float4(dx, dy, dz, c.w);
-                if (WITH_IDX) rowidx[r * stride + q] = cj;
+                for (int u = 0; u < 2; u++) {
+                    dz[u] = wrap_axis(dz[u], p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                    dy[u] = wrap_axis(dy[u], p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                    dx[u] = wrap_axis(dx[u], p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                    xx[u] = __fmul_rn(dx[u], dx[u]); yy[u] = __fmul_rn(dy[u], dy[u]); zz[u] = __fmul_rn(dz[u], dz[u]);
+                }
+            } else {
+                unpack2(mul2(dx2, dx2), xx[0], xx[1]);
+                unpack2(mul2(dy2, dy2), yy[0], yy[1]);
+                unpack2(mul2(dz2, dz2), zz[0], zz[1]);
             }
-            cnt[r] += nh;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int r = 2 * h + u;
+                const float rsq = __fadd_rn(__fadd_rn(xx[u], yy[u]), zz[u]);
+                // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; the +inf sentinels give inf/NaN -> no hit
+                bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]);
+                if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
+                if (hit) {
+                    sts_u16(rs.lp[r], (unsigned)tl);
+                    rs.lp[r] += 64u;                    // lists are [k][lane] u16: next k is 32 entries on
+                }
+            }
         }
     }
-}
-
-// after the chunk that pushed a row past K: move entries K.. down to (q mod K), in order
-template <bool WITH_IDX>
-__device__ __forceinline__ void fold_overflow(const NlistParams &p, const int (&cnt)[RPP], float4 *rowbuf, int *rowidx,
-                                              int stride, int lane)
-{
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < RPP; r++)
-            for (int q = p.K; q < cnt[r]; q++) {
-                rowbuf[r * stride + q % p.K] = rowbuf[r * stride + q];
-                if (WITH_IDX) rowidx[r * stride + q % p.K] = rowidx[r * stride + q];
-            }
-    }
-    __syncwarp();
 }
 
 template <bool WITH_IDX, bool MAPPED>
@@ -190,14 +179,23 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
     if (cell >= p.g.ncell) return;
 
     const int K = p.K;
-    const int stride = K + SPARE;        // row buffer pitch in slots
-    // per-warp carve-up: cand[cap] f4 | rowbuf[RPP*stride] f4 | (candidx[cap] i32 | rowidx[RPP*stride] i32)
-    const size_t per_warp = (size_t)(p.cap + RPP * stride) * (WITH_IDX ? 20 : 16);
+    const int cap = p.cap;
+    // per-warp carve-up (see per_warp_bytes): cand[cap] f4 | rowstage[K] f4 | lists[RPP][cap] u16 |
+    //   runtab[64] i32 | slotmap[K] u16 (padded to 16 B) | (candidx[cap] i32 | idxstage[K] i32)
+    const size_t slotmap_bytes = ((size_t)K * 2 + 15) & ~(size_t)15;
+    size_t per_warp = (size_t)cap * 16 + (size_t)K * 16 + (size_t)RPP * cap * 2 + 256 + slotmap_bytes;
+    if (WITH_IDX) per_warp += (size_t)cap * 4 + (((size_t)K * 4 + 15) & ~(size_t)15);
     unsigned char *base = smem_raw + per_warp * warp;
     float4 *cand = reinterpret_cast<float4 *>(base);
-    float4 *rowbuf = cand + p.cap;
-    int *candidx = reinterpret_cast<int *>(rowbuf + RPP * stride);
-    int *rowidx = candidx + p.cap;
+    float4 *rowstage = cand + cap;
+    unsigned char *lists = reinterpret_cast<unsigned char *>(rowstage + K);
+    int *runtab = reinterpret_cast<int *>(lists + (size_t)RPP * cap * 2);     // [0..31] run end, [32..63] src - t
+    unsigned short *slotmap = reinterpret_cast<unsigned short *>(runtab + 64);
+    int *candidx = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(slotmap) + slotmap_bytes);
+    int *idxstage = candidx + cap;
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
+    const unsigned lists_s = (unsigned)__cvta_generic_to_shared(lists);
 
     const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
     if (e == b) return;
@@ -240,37 +238,31 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
         int t = __shfl_up_sync(HTF_FULL, incl, o);
         if (lane >= o) incl += t;
     }
-    const int roff = incl - rl;
     const int m = __shfl_sync(HTF_FULL, incl, 31);
-    const unsigned runmask = __ballot_sync(HTF_FULL, rl > 0);
+    // run table: candidate t belongs to the first run q with t < end[q]; its source slot is t + adj[q]
+    runtab[lane] = incl;
+    runtab[32 + lane] = rb - (incl - rl);
     // the run that holds this cell's own particles -> virtual index of "self" for each row
     const unsigned selfmask = __ballot_sync(HTF_FULL, rl > 0 && rb <= b && b < rb + rl);
-    const int qself = __ffs(selfmask) - 1;
-    const int self_base = __shfl_sync(HTF_FULL, roff - rb, qself);
+    const int self_base = __shfl_sync(HTF_FULL, (incl - rl) - rb, __ffs(selfmask) - 1);
+    __syncwarp();
 
-    const int cap = p.cap;
     const int npass = (m + cap - 1) / cap;
 
     // stage window `pass` of the virtual candidate list; returns its length rounded up to 32
     // (the tail is filled with +inf sentinels, which can never be a hit)
-    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
-    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
+    const unsigned runtab_s = (unsigned)__cvta_generic_to_shared(runtab);
     auto stage = [&](int pass) {
         const int w0 = pass * cap, w1 = min(m, w0 + cap);
-        unsigned rm = runmask;
-        while (rm) {
-            const int q = __ffs(rm) - 1;
-            rm &= rm - 1;
-            const int qb = __shfl_sync(HTF_FULL, rb, q);
-            const int ql = __shfl_sync(HTF_FULL, rl, q);
-            const int qo = __shfl_sync(HTF_FULL, roff, q);
-            const int lo = max(qo, w0), hi = min(qo + ql, w1);
-            // asynchronous global->shared copies: every run is in flight before the single wait below
-            for (int t = lo + lane; t < hi; t += 32) {
-                const int s = qb + (t - qo);
-                cp_async16(cand_s + (unsigned)(t - w0) * 16u, p.spos + s);
-                if (WITH_IDX) cp_async4(candidx_s + (unsigned)(t - w0) * 4u, p.sorted_idx + s);
-            }
+        // each lane walks the run table with a private cursor (runs are ~one chunk long, so the cursor
+        // advances 0-2 entries per chunk); the copies are asynchronous, one wait for the whole window
+        unsigned qa = runtab_s;
+        int qend = lds_i32(qa), qadj = lds_i32(qa + 128u);
+        unsigned dsta = cand_s + (unsigned)lane * 16u;
+        for (int t = w0 + lane; t < w1; t += 32, dsta += 512u) {
+            while (t >= qend) { qa += 4u; qend = lds_i32(qa); qadj = lds_i32(qa + 128u); }
+            cp_async16(dsta, p.spos + (t + qadj));
+            if (WITH_IDX) cp_async4(candidx_s + (unsigned)(t - w0) * 4u, p.sorted_idx + (t + qadj));
         }
         const int len = w1 - w0, mround = (len + 31) & ~31;
         if (len + lane < mround) {
@@ -284,74 +276,158 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
 
     int mround = 0;
     if (npass == 1) mround = stage(0);
+    // a dense cell that needs several windows is walked one row at a time: that row's partial
+    // result lives in the shared staging row between windows
+    const int rstep = (npass == 1) ? RPP : 1;
 
-    const unsigned rowbuf_s = (unsigned)__cvta_generic_to_shared(rowbuf);
-    for (int s0 = b; s0 < e; s0 += RPP) {
+    for (int s0 = b; s0 < e; s0 += rstep) {
         RowState rs;
-        int orig[RPP], cnt[RPP];
         bool anyrow = false;
+        {
+            float px[RPP], py[RPP], pz[RPP];
 #pragma unroll
-        for (int r = 0; r < RPP; r++) {
-            const int s = min(s0 + r, e - 1);                    // both loads are independent of each other
-            const int o = __ldg(p.sorted_idx + s);
-            float4 pi = __ldg(p.spos + s);
-            const bool ok = (s0 + r < e) && o >= p.row_lo && o < p.row_hi;
-            orig[r] = ok ? o : -1;
-            if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);           // never hits
-            rs.x[r] = pi.x; rs.y[r] = pi.y; rs.z[r] = pi.z; rs.t[r] = pi.w;
-            rs.wp[r] = rowbuf_s + (unsigned)(r * stride) * 16u;
-            rs.lim[r] = rs.wp[r] + (unsigned)K * 16u;
-            cnt[r] = 0;
-            anyrow |= ok;
+            for (int r = 0; r < RPP; r++) {
+                const int s = min(s0 + r, e - 1);                    // both loads are independent of each other
+                const int o = __ldg(p.sorted_idx + s);
+                float4 pi = __ldg(p.spos + s);
+                const bool ok = (r < rstep) && (s0 + r < e) && o >= p.row_lo && o < p.row_hi;
+                if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);       // never hits
+                px[r] = pi.x; py[r] = pi.y; pz[r] = pi.z; rs.t[r] = pi.w;
+                rs.self_rel[r] = ok ? 0 : -1;                        // refined per window below
+                anyrow |= ok;
+            }
+            if (!anyrow) continue;
+#pragma unroll
+            for (int h = 0; h < RPP / 2; h++) {
+                rs.x[h] = pack2(px[2 * h], px[2 * h + 1]);
+                rs.y[h] = pack2(py[2 * h], py[2 * h + 1]);
+                rs.z[h] = pack2(pz[2 * h], pz[2 * h + 1]);
+            }
         }
-        if (!anyrow) continue;
+        bool rvalid[RPP];
+#pragma unroll
+        for (int r = 0; r < RPP; r++) rvalid[r] = rs.self_rel[r] == 0;
 
-        bool overflowed = false;
+        int cnt_acc = 0;                                             // multi-window mode: hits of the row so far
         for (int pass = 0; pass < npass; pass++) {
             if (npass > 1) { __syncwarp(); mround = stage(pass); }
 #pragma unroll
             for (int r = 0; r < RPP; r++) {
                 const int rel = self_base + s0 + r - pass * cap;       // own particle inside this window?
-                rs.self_rel[r] = (orig[r] >= 0 && rel >= 0 && rel < mround) ? rel : -1;
+                rs.self_rel[r] = (rvalid[r] && rel >= 0 && rel < mround) ? rel : -1;
+                rs.lp[r] = lists_s + (unsigned)(r * cap + lane) * 2u;
             }
-            int t = 0;
-            if (!overflowed) {
-                t = wrap ? test_fast<true, MAPPED, WITH_IDX>(p, cand, candidx, mround, rs, rowbuf_s, rowidx, stride, lane)
-                         : test_fast<false, MAPPED, WITH_IDX>(p, cand, candidx, mround, rs, rowbuf_s, rowidx, stride, lane);
-                int cmax = 0;
-#pragma unroll
-                for (int r = 0; r < RPP; r++) {
-                    cnt[r] = (int)((rs.wp[r] - rowbuf_s) >> 4) - r * stride;
-                    cmax = max(cmax, cnt[r]);
-                }
-                if (cmax > K) {
-                    overflowed = true;
-                    fold_overflow<WITH_IDX>(p, cnt, rowbuf, rowidx, stride, lane);
-                }
-            }
-            if (overflowed && t < mround)
-                test_slow<MAPPED, WITH_IDX>(p, cand, candidx, t, mround, rs, cnt, rowbuf, rowidx, stride, lane);
-        }
-        __syncwarp();
+            if (wrap) test_window<true, MAPPED>(p, cand, mround, rs, lane);
+            else test_window<false, MAPPED>(p, cand, mround, rs, lane);
+            __syncwarp();
 
-        // ---- flush: one contiguous K*16 B store per row, zero padded ----
+            // ---- emit, row by row (kept rolled: this code runs once per row, not once per pair) ----
+            const bool last = pass == npass - 1;
+            const unsigned slotmap_s = (unsigned)__cvta_generic_to_shared(slotmap);
+#pragma unroll 1
+            for (int r = 0; r < rstep; r++) {
+                const int srow = s0 + r;
+                if (srow >= e) break;
+                const int orig = __ldg(p.sorted_idx + srow);
+                if (orig < p.row_lo || orig >= p.row_hi) continue;       // warp-uniform
+                const float4 pi = __ldg(p.spos + srow);
+                const unsigned lp_r = r == 0 ? rs.lp[0] : r == 1 ? rs.lp[1] : r == 2 ? rs.lp[2] : rs.lp[3];
+                const unsigned list_s = lists_s + (unsigned)(r * cap + lane) * 2u;
+                const int c_l = (int)((lp_r - list_s) >> 6);
+                int incl_c = c_l;                                        // scan of the lane counts
 #pragma unroll
-        for (int r = 0; r < RPP; r++) {
-            if (orig[r] < 0) continue;
-            const size_t row = (size_t)(orig[r] - p.row_lo);
-            float4 *dst = p.out + row * K;
-            const int c = cnt[r];
-            for (int s = lane; s < K; s += 32) {
-                float4 v = (s < c) ? rowbuf[r * stride + s] : make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[s] = v;
-                if (WITH_IDX) p.idx_out[row * K + s] = (s < c) ? rowidx[r * stride + s] : -1;
-            }
-            if (lane == 0) {
-                if (p.count_out) p.count_out[row] = c;
-                if (p.overflow && c >= K) atomicMax(p.overflow, c);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(HTF_FULL, incl_c, o);
+                    if (lane >= o) incl_c += t;
+                }
+                const int wtotal = __shfl_sync(HTF_FULL, incl_c, 31);
+                const int total = cnt_acc + wtotal;
+                float4 *grow = p.out + (size_t)(orig - p.row_lo) * K;
+
+                if (npass == 1 && total <= K) {
+                    // ---- fast path: slots [0,total) are exactly this window's hits, lane-major ----
+                    const unsigned qa = slotmap_s + (unsigned)(incl_c - c_l) * 2u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k < c_l) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+                    if (__any_sync(HTF_FULL, c_l > 4))
+                        for (int k = 4; k < c_l; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+                    __syncwarp();
+                    for (int sl = lane; sl < K; sl += 32) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int vi = -1;
+                        if (sl < total) {
+                            const unsigned ci = lds_u16(slotmap_s + 2u * sl);
+                            const float4 cd = lds_f4(cand_s + ci * 16u);
+                            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+                            if (wrap) {
+                                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                            }
+                            v = make_float4(dx, dy, dz, cd.w);
+                            if (WITH_IDX) vi = candidx[ci];
+                        }
+                        grow[sl] = v;
+                        if (WITH_IDX) p.idx_out[(size_t)(orig - p.row_lo) * K + sl] = vi;
+                    }
+                    if (p.count_out && lane == 0) p.count_out[orig - p.row_lo] = total;
+                    if (total == K && p.overflow && lane == 0) atomicMax(p.overflow, total);
+                    __syncwarp();
+                    continue;
+                }
+
+                // ---- general path: row overflows K and/or the cell needs several windows ----
+                const int first = total - K;            // > 0: more than K hits so far, only the last K survive
+                for (int sl = lane; sl < K; sl += 32) slotmap[sl] = 0xffffu;     // 0xffff = none from this window
+                __syncwarp();
+                int q = cnt_acc + incl_c - c_l;
+                for (int k = 0; k < c_l; k++, q++) {
+                    const unsigned ci = lds_u16(list_s + (unsigned)k * 64u);
+                    // htf/TensorflowCompute.cc:370: slot = q mod K, the last writer of a slot wins
+                    if (first <= 0) slotmap[q] = (unsigned short)ci;
+                    else if (q >= first) slotmap[q % K] = (unsigned short)ci;
+                }
+                __syncwarp();
+                const size_t row = (size_t)(orig - p.row_lo);
+                const bool direct = npass == 1;         // single window: straight to the global row
+                float4 *dst = direct ? grow : rowstage;
+                int *idst = WITH_IDX ? (direct ? p.idx_out + row * K : idxstage) : nullptr;
+                for (int sl = lane; sl < K; sl += 32) {
+                    const unsigned ci = slotmap[sl];
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int vi = -1;
+                    if (ci != 0xffffu) {
+                        const float4 cd = cand[ci];
+                        float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+                        dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);     // a no-op for interior cells
+                        dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                        dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                        v = make_float4(dx, dy, dz, cd.w);
+                        if (WITH_IDX) vi = candidx[ci];
+                    }
+                    if (direct || ci != 0xffffu || (pass == 0)) {        // multi-window: keep earlier windows' slots
+                        dst[sl] = v;
+                        if (WITH_IDX) idst[sl] = vi;
+                    }
+                }
+                if (!direct) {
+                    cnt_acc = total;
+                    __syncwarp();
+                    if (last) {
+                        for (int sl = lane; sl < K; sl += 32) {
+                            grow[sl] = rowstage[sl];
+                            if (WITH_IDX) p.idx_out[row * K + sl] = idxstage[sl];
+                        }
+                    }
+                }
+                if (last && lane == 0) {
+                    if (p.count_out) p.count_out[row] = total;
+                    if (p.overflow && total >= K) atomicMax(p.overflow, total);
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
 }
 
@@ -367,6 +443,13 @@ cudaError_t launch_variant(const NlistParams &p, int grid, int wpb, size_t smem,
     }
     nlist_build_kernel<WITH_IDX, MAPPED><<<grid, wpb * 32, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+size_t per_warp_bytes(int cap, int K, bool with_idx)
+{
+    size_t b = (size_t)cap * 16 + (size_t)K * 16 + (size_t)RPP * cap * 2 + 256 + (((size_t)K * 2 + 15) & ~(size_t)15);
+    if (with_idx) b += (size_t)cap * 4 + (((size_t)K * 4 + 15) & ~(size_t)15);
+    return b;
 }
 
 }  // namespace
@@ -397,21 +480,20 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     const double mean = (double)stencil * (double)ctx->n_binned / (double)g.ncell;
     int cap = (int)(mean + 5.0 * sqrt(mean > 1.0 ? mean : 1.0)) + 32;
     cap = (cap + 31) / 32 * 32;
+    if (cap > 32768) cap = 32768;        // candidate indices are 16 bit
     const bool with_idx = idx_out != nullptr;
     const bool mapped = ctx->map_type_start >= 0;
-    const int bytes_per = with_idx ? 20 : 16;
-    const int stride = p.K + SPARE;
     int wpb = 4;
     const size_t smem_max = 200 * 1024;
     // keep the per-block footprint within the opt-in limit; shrink the staging window first
     // (the kernel re-stages in passes), then the block
-    while ((size_t)(cap + RPP * stride) * bytes_per * wpb > smem_max) {
+    while (per_warp_bytes(cap, p.K, with_idx) * wpb > smem_max) {
         if (cap > 64) cap = max(64, cap / 2 / 32 * 32);
         else if (wpb > 1) wpb /= 2;
         else return cudaErrorInvalidValue;
     }
     p.cap = cap;
-    const size_t smem = (size_t)(cap + RPP * stride) * bytes_per * wpb;
+    const size_t smem = per_warp_bytes(cap, p.K, with_idx) * wpb;
     const int grid = (g.ncell + wpb - 1) / wpb;
     ctx->launches += 1;
     if (with_idx) return mapped ? launch_variant<true, true>(p, grid, wpb, smem, st)

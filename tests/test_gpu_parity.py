@@ -267,3 +267,28 @@ def test_full_size_properties(oracle_mod, name):
     fe_o, _, v6_o = oracle_mod.lj(nl_o)
     assert_close_rel(fe[a0:b0].cpu().numpy(), fe_o, what="force+energy slice")
     assert_close_rel(vir[a0:b0].cpu().numpy(), v6_o, what="virial slice")
+
+
+def test_inhomogeneous_multi_window(oracle_mod):
+    """all particles in one corner of a large box: the stencil population is far above the box
+    average, so the build kernel has to re-stage candidates in several windows (dense-cell path)."""
+    rng = np.random.default_rng(21)
+    n, L = 3000, 40.0
+    pos = np.zeros((n, 4), dtype=np.float32)
+    pos[:, :3] = (rng.random((n, 3)) * 6.0 - 20.0).astype(np.float32)      # a 6^3 blob in a 40^3 box
+    pos[:, 3] = rng.integers(0, 3, n)
+    lo, hi = np.full(3, -L / 2, np.float32), np.full(3, L / 2, np.float32)
+    for K in (256, 64):                      # 64 overflows: counts must still be exact
+        ctx = _ctx(n, K, 2.0, lo, hi)
+        nl_g, idx_g, cnt_g = gpu_nlist(ctx, pos)
+        nl_o, idx_o, cnt_o = oracle_mod.nlist(pos, lo, hi, 2.0, K, cells=False)
+        assert np.array_equal(cnt_g, cnt_o)
+        ok = cnt_o <= K
+        nls, ids = sort_rows(nl_g.cpu().numpy(), idx_g)
+        nlo, ido = sort_rows(nl_o, idx_o)
+        assert np.array_equal(ids[ok], ido[ok]) and np.array_equal(nls[ok].view(np.uint32), nlo[ok].view(np.uint32))
+        if K == 64:
+            assert (~ok).any() and ctx.overflow() == cnt_o.max()
+            full_o, idx_all, _ = oracle_mod.nlist(pos, lo, hi, 2.0, 512, cells=False)
+            for r in np.where(~ok)[0][:50]:                   # overflowed rows hold K distinct genuine neighbors
+                assert len(set(idx_g[r])) == K and set(idx_g[r]).issubset(set(idx_all[r][idx_all[r] >= 0]))
