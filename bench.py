@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- particle-timesteps/s of the nlist -> forces+virial hot path (BASELINE.json metric).
+
+One "step" = one pass of the path over one synthetic LJ fluid: cell binning, padded neighbor
+tensor [N,K,4], LJ forces + per-particle energy + 6-component virial.  Default workload:
+1,048,576 particles, K=64, r_cut=2.5, rho=0.7 (BASELINE.json configs[2] geometry with the LJ
+model, the size the north-star target is quoted on); the 1 GiB neighbor tensor is larger than
+L2, so no flush is needed between steps.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1|cfg5] [--rdf]
+  python bench.py --impl reference ...      # the CPU restatement (oracle/) on the host cores
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): rows are sharded by particle index,
+positions are all-gathered every step (weak scaling: N x 1M particles), the RDF histogram is
+all-reduced when --rdf is on.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "hoomd-tf_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle-timesteps/s (nlist->forces+virial)"
+UNIT = "particle-timesteps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "nlist_build_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def workload(args, world):
+    from htf import synthetic
+    c = dict(synthetic.CONFIGS[args.workload])
+    sites = list(c["sites"])
+    sites[2] *= world                      # weak scaling: the box grows along z, 1 config-size slab per GPU
+    pos, lo, hi = synthetic.lattice_fluid(tuple(sites), c["rho"], c["seed"])
+    return pos, lo, hi, c["r_cut"], c["K"]
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's path (oracle/), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import oracle
+    oracle.build()
+    pos, lo, hi, r_cut, K = workload(args, 1)
+    n = pos.shape[0]
+    rows = min(n, 262144)                  # bounded sample: a row slab of the same system
+    a0 = (n - rows) // 2
+
+    def step():
+        nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
+        fe, _, v6 = oracle.lj(nl, virial=True)
+        if args.rdf:
+            oracle.rdf_hist(nl, (0.0, r_cut), 100)
+        return fe
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    sample = "%d-row slab of the %d-particle system per step (cell binning over all particles included)" % (rows, n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg_dict(args, n, K, r_cut, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of TensorflowCompute::prepareNeighbors + closed-form LJModel (oracle/), "
+                "not HOOMD+TensorFlow: the reference stack cannot be built or imported here",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cfg_dict(args, n, K, r_cut, world):
+    return {"workload": "lj_fluid_%s%s" % (args.workload, "+rdf100" if args.rdf else ""),
+            "particles": n, "particles_per_gpu": n // world, "nneighbor_cutoff": K, "r_cut": r_cut,
+            "model": "LJ (nlist_rinv closed form) + 6-component virial",
+            "sharding": "particle rows, positions all-gathered per step" if world > 1 else "single GPU",
+            "l2": "per-GPU working set %.0f MiB/step > 126 MB L2, no flush needed" % (n // world * K * 16 / 2 ** 20)}
+
+
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import htf
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pos, lo, hi, r_cut, K = workload(args, world)
+    n = pos.shape[0]
+    per = n // world
+    row_lo, row_hi = rank * per, (rank + 1) * per if rank < world - 1 else n
+    rows = row_hi - row_lo
+
+    ctx = htf.HtfContext(n, K, r_cut, device=dev)
+    ctx.set_box(lo, hi)
+    d_pos_all = torch.from_numpy(pos).to(dev)
+    d_shard = d_pos_all[row_lo:row_hi].clone()
+    nl = torch.empty((rows, K, 4), dtype=torch.float32, device=dev)
+    fe = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    vir = torch.empty((rows, 6), dtype=torch.float32, device=dev)
+    bins = torch.zeros(102, dtype=torch.int64, device=dev) if args.rdf else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(marks=None):
+        if world > 1:
+            dist.all_gather_into_tensor(d_pos_all, d_shard)           # the path's one exchange step
+        ctx.bin_particles(d_pos_all)
+        if marks is not None:
+            marks[0].record()
+        ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
+        if marks is not None:
+            marks[1].record()
+        if bins is not None:
+            bins.zero_()
+            ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
+            if world > 1:
+                dist.all_reduce(bins)
+        else:
+            ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
+        if marks is not None:
+            marks[2].record()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    assert ctx.overflow() == 0, "neighbor list overflowed K: the run is void"
+
+    # ---- timed region: exactly --steps steps, device timed, clocks sampled meanwhile ----
+    marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    e0, e1 = ev(), ev()
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        step(marks[i])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    build_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
+    force_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
+    value = n * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (tfcompute + built-in LJ virial model) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_build = rows * (16 * K + 16)
+        achieved = alg_build / (build_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg_dict(args, n, K, r_cut, world),
+            "roofline": {"bound": "hbm", "kernel": "nlist_build_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_build, "kernel_ms": build_ms,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "path_frac": (rows * (32 * K + 56)) / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "force_kernel_ms": force_ms,
+                         "force_kernel_frac": rows * (16 * K + 40) / (force_ms * 1e-3) / 1e9 / peak},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": e2e,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, pos, lo, hi, r_cut, K)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi):
+    """Same metric through tfcompute (the user-facing call) with HOST buffers: every step copies the
+    rank's positions from pinned host memory and reads forces+virial back into pinned host memory."""
+    n = pos.shape[0]
+    rows = row_hi - row_lo
+    system = htf.sim.System(pos, lo, hi, device=dev)
+    model = htf.models.LJVirialModel(K, virial=True)
+    tfc = htf.tfcompute(model)
+    tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
+    h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
+    h_f = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
+    h_v = torch.empty((rows, 9), dtype=torch.float32).pin_memory()
+    d_shard = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    tfc.shard = (row_lo, row_hi)
+
+    def step(t):
+        d_shard.copy_(h_pos, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(system.positions, d_shard)
+        else:
+            system.positions.copy_(d_shard)
+        f = tfc.compute_forces(t)
+        h_f.copy_(f[row_lo:row_hi], non_blocking=True)
+        h_v.copy_(tfc._virial[row_lo:row_hi], non_blocking=True)
+
+    steps = max(3, min(args.steps, 10))
+    for t in range(3):
+        step(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(steps):
+        step(t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4),
+            "d2h_bytes_per_step": int(h_f.numel() * 4 + h_v.numel() * 4), "steps": steps,
+            "api": "htf.tfcompute(LJVirialModel).compute_forces with pinned host positions in, forces+virial out"}
+
+
+def cpu_baseline(args, pos, lo, hi, r_cut, K):
+    """The CPU restatement (oracle/) timed on this box's host cores on a bounded sample of the workload."""
+    import oracle
+    oracle.build()
+    n = pos.shape[0]
+    rows = min(n, 262144)
+    a0 = (n - rows) // 2
+    reps, t_tot = 0, 0.0
+    while t_tot < 8.0 and reps < 6:
+        t0 = time.perf_counter()
+        nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
+        oracle.lj(nl, virial=True)
+        if args.rdf:
+            oracle.rdf_hist(nl, (0.0, r_cut), 100)
+        t_tot += time.perf_counter() - t0
+        reps += 1
+    return {"value": rows * reps / t_tot, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d x a %d-row slab of the %d-particle system (cell binning of all particles included)" % (reps, rows, n),
+            "host_cores": os.cpu_count()}
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

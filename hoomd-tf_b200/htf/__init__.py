@@ -5,7 +5,17 @@ that path.  The compute path is libhtf_b200.so (hand-written sm_100a CUDA behind
 ABI); torch provides device memory, streams and torch.distributed only.
 """
 from . import _lib
-from .context import HtfContext
 from . import synthetic
+from .context import HtfContext
+from . import ops
+from .simmodel import (SimModel, compute_nlist_forces, compute_positions_forces, nlist_rinv, safe_norm, box_size,
+                       wrap_vector, compute_rdf, masked_nlist, rdf_from_hist, Mean, MeanTensor)
+from .layers import RBFExpansion, WCARepulsion, EDSLayer
+from .tensorflowcompute import tfcompute
+from .utils import compute_nlist, compute_pairwise, iter_from_trajectory
+from . import models
+from . import sim
+from . import parallel
+from .ops import lj_forces, rdf_hist
 
 __version__ = "0.1.0"

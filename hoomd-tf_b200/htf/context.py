@@ -133,6 +133,15 @@ class HtfContext:
                                         int(virial_components), self._stream()))
         return (fe, vir) if virial else fe
 
+    def lj_step_forces_only(self, nlist, force_out, virial_out, bins, r_range, nbins=100):
+        """LJ forces+virial with the compute_rdf histogram fused into the same pass over ``nlist``."""
+        _check_dev_f32(nlist, "nlist", 4)
+        vc = virial_out.shape[1] if virial_out is not None else 6
+        self._ck(self.lib.htf_lj_forces_rdf(self._h, _ptr(nlist), nlist.shape[0], int(nlist.shape[1]),
+                                            _ptr(force_out), _ptr(virial_out), int(vc), _ptr(bins),
+                                            float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
+        return force_out
+
     def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None,
                  type_tensor=None):
         """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given.

@@ -1,0 +1,208 @@
+"""Built-in models of the hot path.
+
+Each class is the drop-in for one of the reference's example models
+(/root/reference htf/test-py/build_examples.py, htf/test-py/benchmark.py): same name, same
+``compute`` signature, same outputs -- but the body calls the fused sm_100a kernels
+(``ops.lj_forces``, ``compute_rdf``) instead of building a differentiable graph.  The
+``*Autograd`` variants keep the reference's literal bodies on torch autograd; they are the
+semantic cross-check for the fused ones and the template for user models.
+"""
+import torch
+
+from . import ops
+from .layers import EDSLayer, RBFExpansion
+from .simmodel import (MeanTensor, Mean, SimModel, compute_nlist_forces, compute_positions_forces, compute_rdf,
+                       nlist_rinv, safe_norm, wrap_vector)
+
+
+class LJModel(SimModel):
+    """build_examples.py:67-77 / benchmark.py:12-23, fused."""
+
+    def compute(self, nlist, positions, box):
+        return ops.lj_forces(nlist)
+
+
+class LJVirialModel(SimModel):
+    """build_examples.py:104-115 (construct with ``virial=True``), fused."""
+
+    def compute(self, nlist, positions, box):
+        return ops.lj_forces(nlist, virial=True)
+
+
+class LJRDF(SimModel):
+    """build_examples.py:297-314: LJ forces + running mean of the RDF over [3, 5]."""
+
+    def setup(self, r_range=(3.0, 5.0), nbins=100):
+        self.avg_rdf = MeanTensor()
+        self.r_range, self.nbins = tuple(r_range), nbins
+
+    def compute(self, nlist, positions, box):
+        rdf, rs = compute_rdf(nlist, self.r_range, positions[:, 3], nbins=self.nbins)
+        self.avg_rdf.update_state(rdf)
+        return ops.lj_forces(nlist)
+
+
+class LJTypedModel(SimModel):
+    """build_examples.py:80-101: typed RDFs A->B and B->A next to (scaled-down) LJ forces."""
+
+    def setup(self):
+        self.avg_rdfa = MeanTensor()
+        self.avg_rdfb = MeanTensor()
+
+    def compute(self, nlist, positions, box):
+        forces = ops.lj_forces(nlist) * (1e-10 / 2.0)
+        rdfa, rs = compute_rdf(nlist, [0, 10], positions[:, 3], type_i=0, type_j=1)
+        rdfb, rs = compute_rdf(nlist, [0, 10], positions[:, 3], type_i=1, type_j=0)
+        self.avg_rdfa.update_state(rdfa)
+        self.avg_rdfb.update_state(rdfb)
+        return forces
+
+
+# ---- literal restatements on autograd (user-model style) ----
+class LJModelAutograd(SimModel):
+    def compute(self, nlist, positions, box):
+        rinv = nlist_rinv(nlist)
+        inv_r6 = rinv ** 6
+        p_energy = 4.0 / 2.0 * (inv_r6 * inv_r6 - inv_r6)
+        energy = p_energy.sum(dim=1)
+        return compute_nlist_forces(nlist, energy)
+
+
+class LJVirialModelAutograd(SimModel):
+    def compute(self, nlist, positions, box):
+        rinv = nlist_rinv(nlist)
+        inv_r6 = rinv ** 6
+        p_energy = 4.0 / 2.0 * (inv_r6 * inv_r6 - inv_r6)
+        energy = p_energy.sum(dim=1)
+        return compute_nlist_forces(nlist, energy, virial=True)
+
+
+class SimplePotential(SimModel):
+    """build_examples.py:9-24: F = -sum_j d/|d| (no energy)."""
+
+    def compute(self, nlist, positions):
+        nlist = nlist[:, :, :3]
+        neighs_rs = torch.linalg.norm(nlist, dim=2, keepdim=True)
+        fr = -1.0 * (1.0 / neighs_rs) * nlist
+        real_fr = torch.where(torch.isfinite(fr), fr, torch.zeros_like(nlist))
+        return real_fr.sum(dim=1)
+
+
+class BenchmarkPotential(SimModel):
+    """build_examples.py:27-32."""
+
+    def compute(self, nlist):
+        rinv = nlist_rinv(nlist)
+        return compute_nlist_forces(nlist, rinv)
+
+
+class NoForceModel(SimModel):
+    """build_examples.py:35-43."""
+
+    def compute(self, nlist, positions):
+        neighs_rs = torch.linalg.norm(nlist[:, :, :3], dim=2)
+        energy = torch.where(neighs_rs == 0, torch.zeros_like(neighs_rs), 1.0 / neighs_rs)
+        pos_norm = torch.linalg.norm(positions, dim=1)
+        return energy, pos_norm
+
+
+class WrapModel(SimModel):
+    """build_examples.py:52-59."""
+
+    def compute(self, nlist, positions, box):
+        return wrap_vector(positions[0, :3] - positions[-1, :3], box)
+
+
+class BenchmarkNonlistModel(SimModel):
+    """build_examples.py:62-66."""
+
+    def compute(self, nlist, positions, box):
+        ps = torch.linalg.norm(positions, dim=1)
+        energy = torch.where(ps == 0, torch.zeros_like(ps), 1.0 / ps)
+        return compute_positions_forces(positions, energy)
+
+
+class EDSModel(SimModel):
+    """build_examples.py:118-135: EDS bias on the distance of particle 0 from the origin."""
+
+    def setup(self, set_point):
+        self.cv_avg = Mean()
+        self.eds_bias = EDSLayer(float(set_point), 5, 1 / 5)
+
+    def compute(self, nlist, positions, box):
+        rvec = wrap_vector(positions[0, :3], box)
+        cv = torch.linalg.norm(rvec)
+        self.cv_avg.update_state(cv)
+        alpha = self.eds_bias(cv)
+        energy = (cv - 5) ** 2 + cv * alpha
+        forces = compute_positions_forces(positions, energy)
+        return forces, alpha
+
+
+class MappedNlist(SimModel):
+    """build_examples.py:183-196."""
+
+    @staticmethod
+    def my_map(pos, box):
+        x = pos[:, :3].mean(dim=0, keepdim=True)
+        cg1 = torch.cat((x, torch.zeros((1, 1), dtype=x.dtype, device=x.device)), -1)
+        cg2 = torch.tensor([[0, 0, 0.1, 1]], dtype=x.dtype, device=x.device)
+        return torch.cat((cg1, cg2), dim=0)
+
+    def compute(self, nlist, positions, box):
+        nlist, cnlist = self.mapped_nlist(nlist)
+        return positions, nlist, cnlist
+
+
+class NlistNN(SimModel):
+    """build_examples.py:199-218 / examples/08: sorted 1/r of the nearest neighbors -> 3 Dense layers."""
+
+    def setup(self, dim, top_neighs):
+        self.dense1 = torch.nn.Linear(top_neighs, dim)
+        self.dense2 = torch.nn.Linear(dim, dim)
+        self.last = torch.nn.Linear(dim, 1)
+        self.top_neighs = top_neighs
+
+    def compute(self, nlist, positions, box):
+        rinv = nlist_rinv(nlist)
+        top_n = torch.sort(rinv, dim=1, descending=True).values[:, :self.top_neighs]
+        x = self.dense1(top_n.reshape(-1, self.top_neighs))
+        x = self.dense2(x)
+        energy = self.last(x)
+        return compute_nlist_forces(nlist, energy)
+
+
+class TrainModel(SimModel):
+    """build_examples.py:246-268."""
+
+    def setup(self, dim, top_neighs):
+        self.dense1 = torch.nn.Linear(top_neighs, dim)
+        self.dense2 = torch.nn.Linear(dim, dim)
+        self.last = torch.nn.Linear(dim, 1)
+        self.top_neighs = top_neighs
+        self.output_zero = False
+
+    def compute(self, nlist, positions, training):
+        rinv = nlist_rinv(nlist)
+        top_n = torch.sort(rinv, dim=1, descending=True).values[:, :self.top_neighs]
+        x = self.dense2(self.dense1(top_n))
+        energy = self.last(x)
+        if training:
+            energy = energy * 2
+        forces = compute_nlist_forces(nlist, energy)
+        if self.output_zero:
+            energy = energy * 0.0
+        return forces, energy.sum()
+
+
+class RBF(SimModel):
+    """build_examples.py:231-241: per-pair radial basis features -> Dense(1)."""
+
+    def setup(self, low, high, count):
+        self.rbf = RBFExpansion(low, high, count)
+        self.dense = torch.nn.Linear(count, 1)
+
+    def compute(self, nlist):
+        r = safe_norm(nlist[:, :, :3], axis=2)
+        energy = self.dense(self.rbf(r)).sum()
+        return compute_nlist_forces(nlist, energy)

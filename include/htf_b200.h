@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 4
+#define HTF_ABI_VERSION 5
 int htf_abi_version(void);
 
 /*
@@ -125,6 +125,15 @@ int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t
  */
 int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
                   float *d_virial, int virial_components, void *stream);
+
+/*
+ * htf_lj_forces with the compute_rdf histogram (below) fused into the same read of the neighbor
+ * tensor: the LJ + RDF model of BASELINE config 2 (htf/test-py/build_examples.py:297-314) in one
+ * pass.  No type filter; d_bins as in htf_rdf_hist.
+ */
+int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
+                      float *d_virial, int virial_components, int64_t *d_bins, float r_lo, float r_hi,
+                      int nbins, void *stream);
 
 /*
  * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,

@@ -1,0 +1,184 @@
+"""CPU tests of the host side: C-ABI surface, SimModel plumbing, EDS layer vs the oracle, and the
+world_size-2 row sharding over gloo (the N>1 path without GPUs)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import htf
+from htf import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """the library loads and exports every function include/htf_b200.h declares (no compute calls here)."""
+    hdr = open(os.path.join(ROOT, "include", "htf_b200.h")).read()
+    declared = set(re.findall(r"\b(htf_[a-z0-9_]+)\s*\(", hdr))
+    assert {"htf_create", "htf_build_nlist", "htf_lj_forces", "htf_rdf_hist", "htf_lj_step"} <= declared
+    lib = htf._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(htf._lib.SYMBOLS), "ctypes table out of sync with the header"
+    assert lib.htf_abi_version() == htf._lib.ABI_VERSION == int(re.search(r"HTF_ABI_VERSION (\d+)", hdr).group(1))
+    # error convention: negative code + message, never a throw; no GPU here -> create must fail cleanly
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        rc = lib.htf_create(ctypes.byref(h), 0, 16, 8, 1.0, 0)
+        assert rc < 0 and not h.value and len(lib.htf_last_error(None)) > 0
+    h = ctypes.c_void_p()
+    assert lib.htf_create(ctypes.byref(h), 0, 16, 0, 1.0, 0) == htf._lib.EINVAL       # K < 1
+    assert b"nneighbor_cutoff" in lib.htf_last_error(None)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        htf.HtfContext(16, 8, 1.0)
+    with pytest.raises(ValueError):
+        htf.lj_forces(torch.zeros((4, 8, 4)))
+    with pytest.raises(ValueError):
+        htf.compute_rdf(torch.zeros((4, 8, 4)), [0, 1])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hoomd-tf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "htf_oracle" not in src, f
+
+
+def test_simmodel_argument_introspection():
+    """htf/simmodel.py:51-68: 1-3 positional args, optional trailing `training`."""
+    class A(htf.SimModel):
+        def compute(self, nlist):
+            return nlist.sum(dim=(1, 2))
+
+    class B(htf.SimModel):
+        def compute(self, nlist, positions, training):
+            return positions[:, :3] * (2.0 if training else 1.0)
+
+    class C(htf.SimModel):
+        def setup(self, scale):
+            self.scale = scale
+
+        def compute(self, nlist, positions, box):
+            return htf.box_size(box) * self.scale
+
+    a, b, c = A(4), B(4, output_forces=False), C(4, scale=3.0)
+    assert (a._arg_count, a._pass_training) == (1, False)
+    assert (b._arg_count, b._pass_training) == (2, True)
+    assert (c._arg_count, c._pass_training) == (3, False)
+    nl, pos = torch.ones((5, 4, 4)), torch.ones((5, 4))
+    box = torch.tensor([[-1.0, -2, -3], [1, 2, 3], [0, 0, 0]])
+    assert a([nl, pos, box], False)[0].shape == (5,)
+    assert torch.equal(b([nl, pos, box], True)[0], 2 * pos[:, :3])
+    assert torch.equal(c([nl, pos, box], False)[0], torch.tensor([6.0, 12.0, 18.0]))
+    with pytest.raises(AttributeError):
+        htf.SimModel(4)
+    with pytest.raises(ValueError):
+        a.mapped_nlist(nl)
+    assert a.get_config()["nneighbor_cutoff"] == 4
+
+
+def test_autograd_force_math_matches_oracle(oracle_mod):
+    """compute_nlist_forces / _compute_virial / nlist_rinv on torch (CPU tensors) vs the C oracle."""
+    pos, lo, hi = synthetic.lattice_fluid((6, 6, 6), 0.7, seed=2)
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 2.5, 64)
+    fe_o, v9_o, _ = oracle_mod.lj(nl)
+    m = htf.models.LJVirialModelAutograd(64, virial=True)
+    f, v = m([torch.from_numpy(nl), torch.from_numpy(pos), torch.zeros(3, 3)], False)
+    np.testing.assert_allclose(f.detach().numpy(), fe_o, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(v.detach().numpy().reshape(-1, 9), v9_o, rtol=2e-4, atol=2e-4)
+    s = htf.models.SimplePotential(64)
+    fs = s([torch.from_numpy(nl), torch.from_numpy(pos)], False)[0]
+    d = nl[:, :, :3].astype(np.float64)
+    r = np.sqrt((d ** 2).sum(-1, keepdims=True))
+    want = np.where(r > 0, -d / np.where(r > 0, r, 1), 0).sum(1)
+    np.testing.assert_allclose(fs.detach().numpy(), want, atol=1e-4)
+
+
+def test_wrap_vector_and_rdf_normalisation():
+    box = torch.tensor([[-5.0, -5, -5], [5, 5, 5], [0, 0, 0]])
+    r = torch.tensor([9.0, -7.0, 2.0])
+    assert torch.allclose(htf.wrap_vector(r, box), torch.tensor([-1.0, 3.0, 2.0]))
+    hist = torch.arange(102, dtype=torch.int64)
+    rdf, rs = htf.rdf_from_hist(hist, (0.0, 2.5), 100)
+    assert rdf.shape == (100,) and rs.shape == (100,)
+    shell = np.linspace(0, 2.5, 101, dtype=np.float32)
+    np.testing.assert_allclose(rdf.numpy(), np.arange(1, 101) / (shell[1:] ** 3 - shell[:-1] ** 3), rtol=1e-5)
+
+
+def test_eds_layer_matches_oracle(oracle_mod):
+    """torch EDSLayer (masked, device resident) == scalar oracle restatement of htf/layers.py:142-195."""
+    rng = np.random.default_rng(3)
+    lay = htf.EDSLayer(4.0, 10, learning_rate=0.5, cv_scale=2.0)
+    ora = oracle_mod.EDSLayer(4.0, 10, learning_rate=0.5, cv_scale=2.0)
+    for i in range(95):
+        cv = np.float32(5.0 + 0.3 * rng.standard_normal())
+        a = float(lay(torch.tensor(cv)))
+        b = float(ora(cv))
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (i, a, b)
+    assert int(lay.n) == ora.n and float(lay.adam_t) == ora.t
+    with pytest.raises(ValueError):
+        htf.EDSLayer(4, 10)
+
+
+def test_row_shard_partition():
+    for n, w in [(10, 2), (10, 3), (1048576, 8), (7, 8)]:
+        rows = [htf.parallel.row_shard(n, w, r) for r in range(w)]
+        assert rows[0][0] == 0 and rows[-1][1] == n
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(w - 1))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hoomd-tf_b200"))
+    import oracle
+    from htf import parallel, synthetic as syn
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos, lo, hi = syn.lattice_fluid((8, 8, 9), 0.7, seed=4)            # 576 particles: ragged over 2 ranks? no: even
+    n = pos.shape[0]
+    a, b = parallel.row_shard(n, world, rank)
+    shard = torch.from_numpy(pos[a:b].copy())
+    full = parallel.allgather_positions(shard, out=torch.empty((n, 4)))
+    assert np.array_equal(full.numpy(), pos)
+    nl, idx, cnt = oracle.nlist(full.numpy(), lo, hi, 2.5, 64, a, b)     # this rank's rows only
+    fe, _, v6 = oracle.lj(nl)
+    bins = torch.from_numpy(oracle.rdf_hist(nl, (0.0, 2.5), 100))
+    parallel.allreduce_bins(bins)
+    cv = parallel.allreduce_scalar(torch.tensor(float((nl[:, :, :3] ** 2).sum())))
+    q.put((rank, a, b, fe, bins.numpy(), float(cv)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_sharding_gloo(oracle_mod):
+    """world_size 2 over gloo: all-gather of the position shards, per-rank rows, all-reduced RDF bins."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 9), 0.7, seed=4)
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 2.5, 64)
+    fe, _, _ = oracle_mod.lj(nl)
+    got = np.concatenate([r[3] for r in res])
+    assert np.array_equal(got, fe)                                        # row sharding changes nothing
+    bins = oracle_mod.rdf_hist(nl, (0.0, 2.5), 100)
+    assert np.array_equal(res[0][4], bins) and np.array_equal(res[1][4], bins)
+    assert abs(res[0][5] - float((nl[:, :, :3].astype(np.float64) ** 2).sum())) < 1e-3 * res[0][5]
