@@ -62,48 +62,65 @@ def ncu_traffic():
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the benchmark runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.f = open(self.path, "w")
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        t0 = time.time()
+        while self.p is not None and self.lines() == 0 and time.time() - t0 < 5.0:
+            time.sleep(0.02)                 # nvidia-smi needs a moment before its first sample
 
-    def stop(self):
+    def lines(self):
+        try:
+            with open(self.path) as f:
+                return sum(1 for _ in f)
+        except OSError:
+            return 0
+
+    def stop(self, first_line=0, last_line=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        self.f.close()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        with open(self.path) as f:
+            for line in f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    rows.append((float(c[1]), float(c[2]), float(c[3]),
+                                 [nme for nme, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
+                except ValueError:
+                    continue
+        os.unlink(self.path)
+        window = rows[first_line:last_line] if last_line is not None else rows[first_line:]
+        label = "timed region"
+        if len(window) < 3:                  # very short timed region: use every sample taken under load
+            window, label = rows, "warm-up + timed region"
+        if window:
+            sm = sorted(r[0] for r in window)
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in window),
+                   "power_w_max": max(r[2] for r in window),
+                   "reasons": sorted({x for r in window for x in r[3]}), "samples": len(window), "window": label}
         return out
 
 
@@ -227,6 +244,7 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
@@ -234,7 +252,7 @@ def run_b200(args):
 
     # ---- timed region: exactly --steps steps, device timed, clocks sampled meanwhile ----
     marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
-    sampler = ClockSampler(local) if rank == 0 else None
+    line0 = sampler.lines() if sampler else 0
     launches0 = ctx.launches
     e0, e1 = ev(), ev()
     sync_all()
@@ -245,7 +263,7 @@ def run_b200(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(line0) if sampler else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -204,7 +204,11 @@ def test_training_force_matching():
     tfc.set_reference_forces(lj)
     system.run(300)
     assert abs(float(model.metrics[0].result())) < 1e-5
+    # the label buffer holds the summed reference forces of the last update (w column = per-particle energy)
+    tfc.period = 1
+    system.run(1)
     np.testing.assert_allclose(tfc.get_forces_array(), lj.forces.cpu().numpy(), rtol=1e-6)
+    system.half_step_hooks.remove(tfc)
     tm = htf.models.TrainModel(16, output_forces=False, dim=8, top_neighs=5)
     tm.compile(loss=["MeanSquaredError", None])
     w0 = tm.dense1.weight.detach().clone()
