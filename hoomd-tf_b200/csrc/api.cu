@@ -132,6 +132,16 @@ int upload_rdf_table(htf_ctx *ctx, float r_lo, float r_hi, int nbins, cudaStream
 
 }  // namespace
 
+cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles)
+{
+    if (ntiles <= ctx->tile_flag_cap) return cudaSuccess;
+    if (ctx->d_tile_flag) cudaFree(ctx->d_tile_flag);
+    ctx->d_tile_flag = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_tile_flag), (size_t)ntiles);
+    if (e == cudaSuccess) ctx->tile_flag_cap = ntiles;
+    return e;
+}
+
 // bin(q) of the reference for a squared distance q: r = fp32 sqrt, TF CPU
 // histogram_fixed_width rule (double step, truncation).  Monotone in q, so the kernel only
 // needs the nb-1 switch points; they are found by bisection over fp32 bit patterns.
@@ -209,7 +219,7 @@ void htf_destroy(htf_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaFree(ctx->d_cell_cnt); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_block_sums);
     cudaFree(ctx->d_cell_of); cudaFree(ctx->d_sorted_idx); cudaFree(ctx->d_spos);
-    cudaFree(ctx->d_nlist_scratch); cudaFree(ctx->d_rdf_thr);
+    cudaFree(ctx->d_nlist_scratch); cudaFree(ctx->d_rdf_thr); cudaFree(ctx->d_tile_flag);
     delete ctx;
 }
 

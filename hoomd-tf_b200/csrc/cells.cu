@@ -5,8 +5,8 @@
 //   count   : cell id per particle, atomic count per cell
 //   scan    : exclusive prefix sum of the counts (3 small kernels)
 //   scatter : particle index -> slot of its cell (count-down atomics, no second zeroing)
-//   order   : (deterministic mode) sort the indices inside each cell
-//   gather  : cell-sorted copy of the positions, the only array the build kernel reads
+//   order+gather : one warp per cell: (deterministic mode) bitonic sort of the cell's indices,
+//             then the cell-sorted copy of the positions, the only array the build kernel reads
 #include "common.cuh"
 
 namespace {
@@ -130,33 +130,58 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict
     sorted_idx[cell_start[c] + k] = i;
 }
 
-// one thread per cell: insertion sort of the (few) particle indices of the cell
-__global__ void __launch_bounds__(128) cell_order_kernel(const int *__restrict__ cell_start, int ncell,
-                                                         int *__restrict__ sorted_idx)
+// One warp per cell: (deterministic mode) bitonic-sort the cell's particle indices across the
+// lanes, then gather the positions into the cell-sorted copy.  The count-down scatter leaves the
+// indices of a cell in atomic order; sorting them makes the row-internal slot order of the
+// neighbor tensor -- and therefore every fp32 force sum -- reproducible run to run.
+template <bool SORT>
+__global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__restrict__ pos,
+                                                                const int *__restrict__ cell_start, int ncell,
+                                                                int *__restrict__ sorted_idx,
+                                                                float4 *__restrict__ spos)
 {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= ncell) return;
-    const int b = cell_start[c], e = cell_start[c + 1];
-    for (int a = b + 1; a < e; a++) {
-        int key = sorted_idx[a];
-        int q = a - 1;
-        while (q >= b) {
-            int t = sorted_idx[q];
-            if (t <= key) break;
-            sorted_idx[q + 1] = t;
-            q--;
+    const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
+    const int n = e - b;
+    if (n == 0) return;
+    if (n <= 32) {
+        int v = (lane < n) ? sorted_idx[b + lane] : 0x7fffffff;
+        if (SORT && n > 1) {
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const int o = __shfl_xor_sync(HTF_FULL, v, j);
+                    const bool up = ((lane & k) == 0);          // ascending block?
+                    const bool lower = ((lane & j) == 0);       // this lane keeps the smaller one?
+                    v = (lower == up) ? min(v, o) : max(v, o);
+                }
+            }
+            if (lane < n) sorted_idx[b + lane] = v;
         }
-        sorted_idx[q + 1] = key;
+        if (lane < n) spos[b + lane] = __ldg(pos + v);
+        return;
     }
-}
-
-__global__ void __launch_bounds__(256) cell_gather_kernel(const float4 *__restrict__ pos,
-                                                          const int *__restrict__ sorted_idx, int n,
-                                                          float4 *__restrict__ spos)
-{
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    spos[s] = __ldg(pos + sorted_idx[s]);
+    // crowded cell (> 32 particles): serial insertion sort by one lane, then a strided gather
+    if (SORT) {
+        if (lane == 0) {
+            for (int a = b + 1; a < e; a++) {
+                const int key = sorted_idx[a];
+                int q = a - 1;
+                while (q >= b) {
+                    const int t = sorted_idx[q];
+                    if (t <= key) break;
+                    sorted_idx[q + 1] = t;
+                    q--;
+                }
+                sorted_idx[q + 1] = key;
+            }
+        }
+        __syncwarp();
+    }
+    for (int s = b + lane; s < e; s += 32) spos[s] = __ldg(pos + sorted_idx[s]);
 }
 
 }  // namespace
@@ -179,12 +204,11 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
     cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_sorted_idx);
-    ctx->launches += 5;
-    if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */) {
-        cell_order_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ctx->d_cell_start, ncell, ctx->d_sorted_idx);
-        ctx->launches += 1;
-    }
-    cell_gather_kernel<<<pb, 256, 0, st>>>(pos, ctx->d_sorted_idx, n, ctx->d_spos);
-    ctx->launches += 1;
+    const int cb = (ncell + 7) / 8;
+    if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */)
+        cell_order_gather_kernel<true><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell, ctx->d_sorted_idx, ctx->d_spos);
+    else
+        cell_order_gather_kernel<false><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell, ctx->d_sorted_idx, ctx->d_spos);
+    ctx->launches += 6;
     return cudaGetLastError();
 }

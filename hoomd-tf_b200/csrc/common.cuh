@@ -37,6 +37,8 @@ struct htf_ctx {
     int *d_sorted_idx;    // [n_cap] cell-sorted slot -> particle index
     float4 *d_spos;       // [n_cap] cell-sorted positions
     int64_t n_cap;
+    unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
+    int tile_flag_cap;
     float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
     int64_t nlist_scratch_elems;
     // RDF threshold table (device) and the key it was built for
@@ -60,6 +62,8 @@ cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K
 cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *row_type,
                            long long row_type_stride, const float *thr, int nb, int type_i, int type_j,
                            unsigned long long *bins, cudaStream_t st);
+
+cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
 
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -46,7 +46,10 @@ struct NlistParams {
     int K;
     float rc2;
     int map_type_start;
-    int cap;             // candidates staged per pass, multiple of 32, <= 32768
+    int cap;             // per-warp window capacity (candidates), multiple of 32, <= 32768
+    int cap_tile;        // tile kernel: candidates staged per block
+    unsigned char *tile_flag;   // [tiles]: 1 = the tile kernel left this tile to the per-cell kernel
+    int use_flags;       // per-cell kernel: process only cells of flagged tiles
     float4 *out;
     int *idx_out;
     int *count_out;
@@ -125,13 +128,14 @@ struct RowState {
 };
 
 // ---- test: append the window-relative index of every hit to the lane-private lists ----
-template <bool WRAP, bool MAPPED>
-__device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, RowState &rs,
-                                            int lane)
+template <bool WRAP, bool MAPPED, bool MASKED>
+__device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, int mlen,
+                                            RowState &rs, int lane)
 {
 #pragma unroll 1
     for (int t0 = 0; t0 < mround; t0 += 32) {
         const int tl = t0 + lane;
+        const bool pv = !MASKED || tl < mlen;       // tile kernel: the window is not sentinel padded
         const float4 c = cand[tl];
         const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
 #pragma unroll
@@ -157,7 +161,7 @@ __device__ __forceinline__ void test_window(const NlistParams &p, const float4 *
                 const int r = 2 * h + u;
                 const float rsq = __fadd_rn(__fadd_rn(xx[u], yy[u]), zz[u]);
                 // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; the +inf sentinels give inf/NaN -> no hit
-                bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]);
+                bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]) & pv;
                 if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
                 if (hit) {
                     sts_u16(rs.lp[r], (unsigned)tl);
@@ -168,6 +172,69 @@ __device__ __forceinline__ void test_window(const NlistParams &p, const float4 *
     }
 }
 
+// ---- emit one row whose hits all come from the single staged window ----
+// Scan of the lane counts -> slot ranges; "slot -> candidate" published in a small shared map; then lane s
+// re-derives d for slots s, s+32, ... and stores them coalesced, zero padding included.
+template <bool WITH_IDX>
+__device__ __forceinline__ void emit_single_window(const NlistParams &p, unsigned cand_s, const int *candidx,
+                                                   unsigned slotmap_s, unsigned list_s, int c_l, bool wrap,
+                                                   const float4 &pi, int orig, int lane)
+{
+    const int K = p.K;
+    int incl_c = c_l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(HTF_FULL, incl_c, o);
+        if (lane >= o) incl_c += t;
+    }
+    const int total = __shfl_sync(HTF_FULL, incl_c, 31);
+    const size_t row = (size_t)(orig - p.row_lo);
+    float4 *grow = p.out + row * K;
+    if (total <= K) {
+        // slots [0,total) are exactly the hits, lane-major
+        const unsigned qa = slotmap_s + (unsigned)(incl_c - c_l) * 2u;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < c_l) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+        if (__any_sync(HTF_FULL, c_l > 4))
+            for (int k = 4; k < c_l; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+    } else {
+        // htf/TensorflowCompute.cc:370: slot = q mod K, the last writer of a slot wins -> only the last K hits
+        const int first = total - K;
+        int q = incl_c - c_l;
+        for (int k = 0; k < c_l; k++, q++)
+            if (q >= first) sts_u16(slotmap_s + 2u * (unsigned)(q % K), lds_u16(list_s + 64u * k));
+    }
+    __syncwarp();
+    const int nvalid = min(total, K);
+    for (int sl = lane; sl < K; sl += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int vi = -1;
+        if (sl < nvalid) {
+            const unsigned ci = lds_u16(slotmap_s + 2u * sl);
+            const float4 cd = lds_f4(cand_s + ci * 16u);
+            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+            if (wrap) {
+                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+            }
+            v = make_float4(dx, dy, dz, cd.w);
+            if (WITH_IDX) vi = candidx[ci];
+        }
+        grow[sl] = v;
+        if (WITH_IDX) p.idx_out[row * K + sl] = vi;
+    }
+    if (lane == 0) {
+        if (p.count_out) p.count_out[row] = total;
+        if (total >= K && p.overflow) atomicMax(p.overflow, total);
+    }
+    __syncwarp();
+}
+
+constexpr int TILE = 4;           // cells per block along x in the tile kernel (= warps per block)
+constexpr int TILE_HDR = 576;     // bytes: piece table end[64] + adj[64] + colstart[16]
+
 template <bool WITH_IDX, bool MAPPED>
 __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
 {
@@ -177,6 +244,11 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
     const int wpb = blockDim.x >> 5;
     const int cell = blockIdx.x * wpb + warp;
     if (cell >= p.g.ncell) return;
+    if (p.use_flags) {                    // second pass after the tile kernel: only the tiles it gave up on
+        const int nx_ = p.g.n[0], tiles_x = (nx_ + TILE - 1) / TILE;
+        const int tile = (cell / nx_) * tiles_x + (cell % nx_) / TILE;
+        if (!p.tile_flag[tile]) return;
+    }
 
     const int K = p.K;
     const int cap = p.cap;
@@ -317,8 +389,8 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 rs.self_rel[r] = (rvalid[r] && rel >= 0 && rel < mround) ? rel : -1;
                 rs.lp[r] = lists_s + (unsigned)(r * cap + lane) * 2u;
             }
-            if (wrap) test_window<true, MAPPED>(p, cand, mround, rs, lane);
-            else test_window<false, MAPPED>(p, cand, mround, rs, lane);
+            if (wrap) test_window<true, MAPPED, false>(p, cand, mround, mround, rs, lane);
+            else test_window<false, MAPPED, false>(p, cand, mround, mround, rs, lane);
             __syncwarp();
 
             // ---- emit, row by row (kept rolled: this code runs once per row, not once per pair) ----
@@ -334,6 +406,10 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 const unsigned lp_r = r == 0 ? rs.lp[0] : r == 1 ? rs.lp[1] : r == 2 ? rs.lp[2] : rs.lp[3];
                 const unsigned list_s = lists_s + (unsigned)(r * cap + lane) * 2u;
                 const int c_l = (int)((lp_r - list_s) >> 6);
+                if (npass == 1) {
+                    emit_single_window<WITH_IDX>(p, cand_s, candidx, slotmap_s, list_s, c_l, wrap, pi, orig, lane);
+                    continue;
+                }
                 int incl_c = c_l;                                        // scan of the lane counts
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -344,40 +420,7 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 const int total = cnt_acc + wtotal;
                 float4 *grow = p.out + (size_t)(orig - p.row_lo) * K;
 
-                if (npass == 1 && total <= K) {
-                    // ---- fast path: slots [0,total) are exactly this window's hits, lane-major ----
-                    const unsigned qa = slotmap_s + (unsigned)(incl_c - c_l) * 2u;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (k < c_l) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
-                    if (__any_sync(HTF_FULL, c_l > 4))
-                        for (int k = 4; k < c_l; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
-                    __syncwarp();
-                    for (int sl = lane; sl < K; sl += 32) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        int vi = -1;
-                        if (sl < total) {
-                            const unsigned ci = lds_u16(slotmap_s + 2u * sl);
-                            const float4 cd = lds_f4(cand_s + ci * 16u);
-                            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
-                            if (wrap) {
-                                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
-                            }
-                            v = make_float4(dx, dy, dz, cd.w);
-                            if (WITH_IDX) vi = candidx[ci];
-                        }
-                        grow[sl] = v;
-                        if (WITH_IDX) p.idx_out[(size_t)(orig - p.row_lo) * K + sl] = vi;
-                    }
-                    if (p.count_out && lane == 0) p.count_out[orig - p.row_lo] = total;
-                    if (total == K && p.overflow && lane == 0) atomicMax(p.overflow, total);
-                    __syncwarp();
-                    continue;
-                }
-
-                // ---- general path: row overflows K and/or the cell needs several windows ----
+                // ---- dense cell, several windows: the row accumulates in the shared staging row ----
                 const int first = total - K;            // > 0: more than K hits so far, only the last K survive
                 for (int sl = lane; sl < K; sl += 32) slotmap[sl] = 0xffffu;     // 0xffff = none from this window
                 __syncwarp();
@@ -390,9 +433,9 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 }
                 __syncwarp();
                 const size_t row = (size_t)(orig - p.row_lo);
-                const bool direct = npass == 1;         // single window: straight to the global row
-                float4 *dst = direct ? grow : rowstage;
-                int *idst = WITH_IDX ? (direct ? p.idx_out + row * K : idxstage) : nullptr;
+                const bool direct = false;
+                float4 *dst = rowstage;
+                int *idst = WITH_IDX ? idxstage : nullptr;
                 for (int sl = lane; sl < K; sl += 32) {
                     const unsigned ci = slotmap[sl];
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -429,6 +472,193 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile kernel: one block = TILE x-adjacent cells (one warp each) of one (y,z) cell row.  The block
+// stages the (TILE+2) x 3 x 3 cell neighbourhood ONCE, column-major, so that each warp's 3x3x3
+// stencil is one contiguous window of the shared buffer: per-cell staging traffic drops from 3 to
+// (TILE+2)/TILE columns, the stencil / prefix set-up is paid once per block, and the smaller
+// shared-memory footprint per warp doubles the resident warps.  Tiles whose neighbourhood does
+// not fit (dense clusters) are flagged and left to the per-cell kernel above.
+template <bool WITH_IDX, bool MAPPED>
+__global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, capB = p.cap_tile, capW = p.cap;
+    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [64] inclusive prefix of piece lengths
+    int *ptab_adj = ptab_end + 64;                              // [64] source slot - staged index
+    int *colstart = ptab_adj + 64;                              // [<= TILE+3] staged offset of each column
+    float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE_HDR);
+    int *candidx = reinterpret_cast<int *>(cand + capB + 32);
+    unsigned char *wbase = WITH_IDX ? reinterpret_cast<unsigned char *>(candidx + capB + 32)
+                                    : reinterpret_cast<unsigned char *>(candidx);
+    const size_t per_warp = (size_t)RPP * capW * 2 + (((size_t)K * 2 + 15) & ~(size_t)15);
+    unsigned char *lists = wbase + per_warp * warp;
+    const unsigned lists_s = (unsigned)__cvta_generic_to_shared(lists);
+    const unsigned slotmap_s = lists_s + (unsigned)(RPP * capW * 2);
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
+
+    const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
+    const int tiles_x = (nx + TILE - 1) / TILE;
+    const int bid = blockIdx.x;
+    const int tx = bid % tiles_x, cy = (bid / tiles_x) % ny, cz = bid / (tiles_x * ny);
+    const int cx0 = tx * TILE;
+    const int nact = min(TILE, nx - cx0);                       // cells of this tile
+    const int nly = min(ny, 3), nlz = min(nz, 3), nyz = nly * nlz;
+    const bool xs = nx >= 3;                                    // x stencil = {c-1, c, c+1}; else every x cell
+    const int ncol = xs ? nact + 2 : nx;
+    const int npieces = ncol * nyz;                             // <= 6 * 9
+
+    // ---- piece table: piece (col, j) = one stencil cell; prefix sums give the staged layout ----
+    int pl = 0, pb = 0;
+    if (tid < npieces) {
+        const int col = tid / nyz, j = tid - col * nyz, jy = j % nly, jz = j / nly;
+        int sx = xs ? cx0 - 1 + col : col;
+        sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
+        int sy = ny <= 3 ? jy : cy + jy - 1;
+        sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
+        int sz = nz <= 3 ? jz : cz + jz - 1;
+        sz = sz < 0 ? sz + nz : (sz >= nz ? sz - nz : sz);
+        const int c0 = (sz * ny + sy) * nx + sx;
+        pb = __ldg(p.cell_start + c0);
+        pl = __ldg(p.cell_start + c0 + 1) - pb;
+    }
+    int incl = pl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(HTF_FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (tid == 31) colstart[15] = incl;                         // total of the first 32 pieces
+    __syncthreads();
+    if (warp == 1) incl += colstart[15];
+    if (tid < 64) {
+        ptab_end[tid] = incl;
+        ptab_adj[tid] = pb - (incl - pl);
+        if (tid < npieces && tid % nyz == 0) colstart[tid / nyz] = incl - pl;
+        if (tid == npieces - 1) colstart[ncol] = incl;
+    }
+    __syncthreads();
+    const int mblock = colstart[ncol];
+    bool fits = mblock <= capB;
+    for (int w = 0; w < nact; w++) {
+        const int wl = xs ? colstart[w + 3] - colstart[w] : mblock;
+        fits = fits && wl <= capW;
+    }
+    if (tid == 0) p.tile_flag[bid] = fits ? 0 : 1;
+    if (!fits) return;                                          // block-uniform
+
+    // ---- stage the whole neighbourhood once (asynchronous copies, one wait) ----
+    for (int t = tid; t < mblock; t += TILE * 32) {
+        int lo = 0, hi = npieces - 1;                           // first piece q with t < end[q]
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (t < ptab_end[mid]) hi = mid; else lo = mid + 1;
+        }
+        const int src = t + ptab_adj[lo];
+        cp_async16(cand_s + (unsigned)t * 16u, p.spos + src);
+        if (WITH_IDX) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + src);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    // ---- one warp per cell of the tile ----
+    if (warp >= nact) return;
+    const int cx = cx0 + warp;
+    const int cell = (cz * ny + cy) * nx + cx;
+    const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
+    if (e == b) return;
+    const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
+    if (!full) {
+        bool any = false;
+        for (int s = b + lane; s < e; s += 32) {
+            const int o = __ldg(p.sorted_idx + s);
+            any |= (o >= p.row_lo && o < p.row_hi);
+        }
+        if (!__any_sync(HTF_FULL, any)) return;
+    }
+    const bool wrap = !((nx >= 5 && cx >= 1 && cx <= nx - 2) && (ny >= 5 && cy >= 1 && cy <= ny - 2) &&
+                        (nz >= 5 && cz >= 1 && cz <= nz - 2));
+    const int ws = xs ? colstart[warp] : 0;
+    const int mlen = (xs ? colstart[warp + 3] : mblock) - ws;
+    const int mround = (mlen + 31) & ~31;
+    // staged position of this cell's own particles: piece (own column, own (y,z))
+    const int ps = (xs ? warp + 1 : cx) * nyz + (nz <= 3 ? cz : 1) * nly + (ny <= 3 ? cy : 1);
+    const int self_base = (ps == 0 ? 0 : ptab_end[ps - 1]) - ws - b;
+    const float4 *cand_w = cand + ws;
+    const unsigned cand_ws = cand_s + (unsigned)ws * 16u;
+    const int *candidx_w = candidx + ws;
+
+    for (int s0 = b; s0 < e; s0 += RPP) {
+        RowState rs;
+        bool anyrow = false;
+        {
+            float px[RPP], py[RPP], pz[RPP];
+#pragma unroll
+            for (int r = 0; r < RPP; r++) {
+                const int s = min(s0 + r, e - 1);
+                const int rel = self_base + s;                       // the row's own particle in the window
+                float4 pi = cand_w[rel];
+                bool ok = s0 + r < e;
+                if (!full) {
+                    const int o = __ldg(p.sorted_idx + s);
+                    ok = ok && o >= p.row_lo && o < p.row_hi;
+                }
+                if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);       // never hits
+                px[r] = pi.x; py[r] = pi.y; pz[r] = pi.z; rs.t[r] = pi.w;
+                rs.self_rel[r] = ok ? rel : -1;
+                rs.lp[r] = lists_s + (unsigned)(r * capW + lane) * 2u;
+                anyrow |= ok;
+            }
+            if (!anyrow) continue;
+#pragma unroll
+            for (int h = 0; h < RPP / 2; h++) {
+                rs.x[h] = pack2(px[2 * h], px[2 * h + 1]);
+                rs.y[h] = pack2(py[2 * h], py[2 * h + 1]);
+                rs.z[h] = pack2(pz[2 * h], pz[2 * h + 1]);
+            }
+        }
+        if (wrap) test_window<true, MAPPED, true>(p, cand_w, mround, mlen, rs, lane);
+        else test_window<false, MAPPED, true>(p, cand_w, mround, mlen, rs, lane);
+        __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < RPP; r++) {
+            const int srow = s0 + r;
+            if (srow >= e) break;
+            const int orig = __ldg(p.sorted_idx + srow);
+            if (orig < p.row_lo || orig >= p.row_hi) continue;           // warp-uniform
+            const float4 pi = cand_w[self_base + srow];
+            const unsigned lp_r = r == 0 ? rs.lp[0] : r == 1 ? rs.lp[1] : r == 2 ? rs.lp[2] : rs.lp[3];
+            const unsigned list_s = lists_s + (unsigned)(r * capW + lane) * 2u;
+            const int c_l = (int)((lp_r - list_s) >> 6);
+            emit_single_window<WITH_IDX>(p, cand_ws, candidx_w, slotmap_s, list_s, c_l, wrap, pi, orig, lane);
+        }
+    }
+}
+
+template <bool WITH_IDX, bool MAPPED>
+cudaError_t launch_tile_variant(const NlistParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nlist_tile_kernel<WITH_IDX, MAPPED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    nlist_tile_kernel<WITH_IDX, MAPPED><<<grid, TILE * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+size_t tile_block_bytes(int capB, int capW, int K, bool with_idx)
+{
+    size_t b = TILE_HDR + (size_t)(capB + 32) * 16;
+    if (with_idx) b += (size_t)(capB + 32) * 4;
+    b += (size_t)TILE * ((size_t)RPP * capW * 2 + (((size_t)K * 2 + 15) & ~(size_t)15));
+    return b;
 }
 
 template <bool WITH_IDX, bool MAPPED>
@@ -477,12 +707,44 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     // stencil population: mean + 5 sigma (Poisson) + slack, rounded to a chunk
     const CellGrid &g = ctx->grid;
     const int stencil = min(g.n[0], 3) * min(g.n[1], 3) * min(g.n[2], 3);
-    const double mean = (double)stencil * (double)ctx->n_binned / (double)g.ncell;
+    const double cell_mean = (double)ctx->n_binned / (double)g.ncell;
+    const double mean = (double)stencil * cell_mean;
     int cap = (int)(mean + 5.0 * sqrt(mean > 1.0 ? mean : 1.0)) + 32;
     cap = (cap + 31) / 32 * 32;
     if (cap > 32768) cap = 32768;        // candidate indices are 16 bit
     const bool with_idx = idx_out != nullptr;
     const bool mapped = ctx->map_type_start >= 0;
+    cudaError_t e;
+
+    // ---- pass 1: tile kernel (TILE cells per block share one staged neighbourhood) ----
+    const int tiles_x = (g.n[0] + TILE - 1) / TILE;
+    const int ntiles = tiles_x * g.n[1] * g.n[2];
+    p.use_flags = 0;
+    p.tile_flag = nullptr;
+    bool tiled = false;
+    {
+        const int ncol = g.n[0] >= 3 ? min(TILE, g.n[0]) + 2 : g.n[0];
+        const double bmean = (double)ncol * min(g.n[1], 3) * min(g.n[2], 3) * cell_mean;
+        int capB = (int)(bmean + 5.0 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
+        capB = (capB + 31) / 32 * 32;
+        const size_t bytes = tile_block_bytes(capB, cap, p.K, with_idx);
+        if (capB <= 32768 && bytes <= 100 * 1024) {           // keep >= 2 blocks per SM, else per-cell only
+            if ((e = htf_ensure_tile_flags(ctx, ntiles)) != cudaSuccess) return e;
+            p.cap = cap;
+            p.cap_tile = capB;
+            p.tile_flag = ctx->d_tile_flag;
+            ctx->launches += 1;
+            e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, ntiles, bytes, st)
+                                   : launch_tile_variant<true, false>(p, ntiles, bytes, st))
+                         : (mapped ? launch_tile_variant<false, true>(p, ntiles, bytes, st)
+                                   : launch_tile_variant<false, false>(p, ntiles, bytes, st));
+            if (e != cudaSuccess) return e;
+            tiled = true;
+        }
+    }
+
+    // ---- pass 2: per-cell kernel; after the tile kernel it only walks the tiles that were flagged ----
+    p.use_flags = tiled ? 1 : 0;
     int wpb = 4;
     const size_t smem_max = 200 * 1024;
     // keep the per-block footprint within the opt-in limit; shrink the staging window first

@@ -68,7 +68,8 @@ class tfcompute:
         if system is None:
             raise RuntimeError("Must initialize a system first")
         self.system = system
-        self.force_mode = "tf2hoomd" if self.model.output_forces else "hoomd2tf"
+        self.model.to(system.device)          # parameters / layer state live next to the particles
+        self.force_mode ="tf2hoomd" if self.model.output_forces else "hoomd2tf"
         n = system.N
         self.ctx = HtfContext(max(n, 1), max(1, self.nneighbor_cutoff), r_cut if r_cut > 0 else 1.0,
                               device=system.device)
