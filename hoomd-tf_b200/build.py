@@ -41,8 +41,14 @@ def find_nvcc():
     return None
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into lib/libhtf_b200.so (returns the path)."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every .cu under csrc/ into lib/libhtf_b200.so (returns the path).
+    ``defines`` / ``out`` build an experimental variant next to it (kernel A/B timing)."""
+    if out is not None:
+        nvcc = find_nvcc()
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + sources()
+        subprocess.check_call(cmd)
+        return out
     if not force and not _stale():
         return LIB_PATH
     nvcc = find_nvcc()

@@ -34,7 +34,13 @@
 
 namespace {
 
-constexpr int RPP = 4;            // rows tested against each staged candidate chunk (even)
+#ifndef HTF_RPP
+#define HTF_RPP 4
+#endif
+#ifndef HTF_TILE
+#define HTF_TILE 4
+#endif
+constexpr int RPP = HTF_RPP;      // rows tested against each staged candidate chunk (even)
 
 struct NlistParams {
     CellGrid g;
@@ -62,6 +68,17 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
     f32x2 r;
     asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+// same, but pinned: used for loop-invariant operands so that the pair is built once, not per iteration
+__device__ __forceinline__ f32x2 pack2_pinned(float lo, float hi)
+{
+    f32x2 r;
+#ifdef HTF_EXP_NOPIN
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+#else
+    asm volatile("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+#endif
     return r;
 }
 __device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
@@ -128,47 +145,67 @@ struct RowState {
 };
 
 // ---- test: append the window-relative index of every hit to the lane-private lists ----
-template <bool WRAP, bool MAPPED, bool MASKED>
-__device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, int mlen,
-                                            RowState &rs, int lane)
+// One 32-candidate chunk against the RPP rows.  CHECKED chunks also apply the two lane-dependent
+// conditions (the candidate is the row's own particle; the candidate lies past the end of the
+// window); only the chunk(s) holding the rows' own particles and the last chunk need them, so the
+// steady-state body is: 1 LDS.128, 6 packed subs, 6 packed squares, 8 adds, 4 compares and the
+// predicated list appends.
+template <bool WRAP, bool MAPPED, bool CHECKED>
+__device__ __forceinline__ void test_chunk(const NlistParams &p, const float4 *cand, int t0, int mlen, RowState &rs,
+                                           int lane)
 {
-#pragma unroll 1
-    for (int t0 = 0; t0 < mround; t0 += 32) {
-        const int tl = t0 + lane;
-        const bool pv = !MASKED || tl < mlen;       // tile kernel: the window is not sentinel padded
-        const float4 c = cand[tl];
-        const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
+    const int tl = t0 + lane;
+    const float4 c = cand[tl];
+    const bool pv = !CHECKED || tl < mlen;
+    const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
 #pragma unroll
-        for (int h = 0; h < RPP / 2; h++) {
-            float dx[2], dy[2], dz[2], xx[2], yy[2], zz[2];
-            const f32x2 dx2 = sub2(cx, rs.x[h]), dy2 = sub2(cy, rs.y[h]), dz2 = sub2(cz, rs.z[h]);
-            if (WRAP) {
-                unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    dz[u] = wrap_axis(dz[u], p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                    dy[u] = wrap_axis(dy[u], p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                    dx[u] = wrap_axis(dx[u], p.g.lo[0], p.g.hi[0], p.g.L[0]);
-                    xx[u] = __fmul_rn(dx[u], dx[u]); yy[u] = __fmul_rn(dy[u], dy[u]); zz[u] = __fmul_rn(dz[u], dz[u]);
-                }
-            } else {
-                unpack2(mul2(dx2, dx2), xx[0], xx[1]);
-                unpack2(mul2(dy2, dy2), yy[0], yy[1]);
-                unpack2(mul2(dz2, dz2), zz[0], zz[1]);
-            }
+    for (int h = 0; h < RPP / 2; h++) {
+        float dx[2], dy[2], dz[2], xx[2], yy[2], zz[2];
+        const f32x2 dx2 = sub2(cx, rs.x[h]), dy2 = sub2(cy, rs.y[h]), dz2 = sub2(cz, rs.z[h]);
+        if (WRAP) {
+            unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const int r = 2 * h + u;
-                const float rsq = __fadd_rn(__fadd_rn(xx[u], yy[u]), zz[u]);
-                // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; the +inf sentinels give inf/NaN -> no hit
-                bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]) & pv;
-                if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
-                if (hit) {
-                    sts_u16(rs.lp[r], (unsigned)tl);
-                    rs.lp[r] += 64u;                    // lists are [k][lane] u16: next k is 32 entries on
-                }
+                dz[u] = wrap_axis(dz[u], p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                dy[u] = wrap_axis(dy[u], p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                dx[u] = wrap_axis(dx[u], p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                xx[u] = __fmul_rn(dx[u], dx[u]); yy[u] = __fmul_rn(dy[u], dy[u]); zz[u] = __fmul_rn(dz[u], dz[u]);
+            }
+        } else {
+            unpack2(mul2(dx2, dx2), xx[0], xx[1]);
+            unpack2(mul2(dy2, dy2), yy[0], yy[1]);
+            unpack2(mul2(dz2, dz2), zz[0], zz[1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int r = 2 * h + u;
+            const float rsq = __fadd_rn(__fadd_rn(xx[u], yy[u]), zz[u]);
+            // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
+            bool hit = rsq <= p.rc2;
+            if (CHECKED) hit = hit & (tl != rs.self_rel[r]) & pv;
+            if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
+            if (hit) {
+                sts_u16(rs.lp[r], (unsigned)tl);
+                rs.lp[r] += 64u;                    // lists are [k][lane] u16: next k is 32 entries on
             }
         }
+    }
+}
+
+// all chunks of a window; [chk_lo, chk_hi] = chunk offsets that hold the rows' own particles
+template <bool WRAP, bool MAPPED>
+__device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, int mlen,
+                                            int chk_lo, int chk_hi, RowState &rs, int lane)
+{
+    const int last = mround - 32;
+#pragma unroll 1
+    for (int t0 = 0; t0 < mround; t0 += 32) {
+#ifndef HTF_EXP_SPLIT
+        test_chunk<WRAP, MAPPED, true>(p, cand, t0, mlen, rs, lane);
+#else
+        if ((t0 >= chk_lo && t0 <= chk_hi) || t0 == last) test_chunk<WRAP, MAPPED, true>(p, cand, t0, mlen, rs, lane);
+        else test_chunk<WRAP, MAPPED, false>(p, cand, t0, mlen, rs, lane);
+#endif
     }
 }
 
@@ -232,7 +269,7 @@ __device__ __forceinline__ void emit_single_window(const NlistParams &p, unsigne
     __syncwarp();
 }
 
-constexpr int TILE = 4;           // cells per block along x in the tile kernel (= warps per block)
+constexpr int TILE = HTF_TILE;    // cells per block along x in the tile kernel (= warps per block)
 constexpr int TILE_HDR = 576;     // bytes: piece table end[64] + adj[64] + colstart[16]
 
 template <bool WITH_IDX, bool MAPPED>
@@ -371,9 +408,9 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
             if (!anyrow) continue;
 #pragma unroll
             for (int h = 0; h < RPP / 2; h++) {
-                rs.x[h] = pack2(px[2 * h], px[2 * h + 1]);
-                rs.y[h] = pack2(py[2 * h], py[2 * h + 1]);
-                rs.z[h] = pack2(pz[2 * h], pz[2 * h + 1]);
+                rs.x[h] = pack2_pinned(px[2 * h], px[2 * h + 1]);
+                rs.y[h] = pack2_pinned(py[2 * h], py[2 * h + 1]);
+                rs.z[h] = pack2_pinned(pz[2 * h], pz[2 * h + 1]);
             }
         }
         bool rvalid[RPP];
@@ -389,8 +426,12 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 rs.self_rel[r] = (rvalid[r] && rel >= 0 && rel < mround) ? rel : -1;
                 rs.lp[r] = lists_s + (unsigned)(r * cap + lane) * 2u;
             }
-            if (wrap) test_window<true, MAPPED, false>(p, cand, mround, mround, rs, lane);
-            else test_window<false, MAPPED, false>(p, cand, mround, mround, rs, lane);
+            int chk_lo = 0x7fffffff, chk_hi = -1;
+#pragma unroll
+            for (int r = 0; r < RPP; r++)
+                if (rs.self_rel[r] >= 0) { chk_lo = min(chk_lo, rs.self_rel[r] & ~31); chk_hi = max(chk_hi, rs.self_rel[r] & ~31); }
+            if (wrap) test_window<true, MAPPED>(p, cand, mround, mround, chk_lo, chk_hi, rs, lane);
+            else test_window<false, MAPPED>(p, cand, mround, mround, chk_lo, chk_hi, rs, lane);
             __syncwarp();
 
             // ---- emit, row by row (kept rolled: this code runs once per row, not once per pair) ----
@@ -403,7 +444,9 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 const int orig = __ldg(p.sorted_idx + srow);
                 if (orig < p.row_lo || orig >= p.row_hi) continue;       // warp-uniform
                 const float4 pi = __ldg(p.spos + srow);
-                const unsigned lp_r = r == 0 ? rs.lp[0] : r == 1 ? rs.lp[1] : r == 2 ? rs.lp[2] : rs.lp[3];
+                unsigned lp_r = rs.lp[0];
+#pragma unroll
+                for (int q = 1; q < RPP; q++) if (r == q) lp_r = rs.lp[q];
                 const unsigned list_s = lists_s + (unsigned)(r * cap + lane) * 2u;
                 const int c_l = (int)((lp_r - list_s) >> 6);
                 if (npass == 1) {
@@ -594,6 +637,7 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
 
     for (int s0 = b; s0 < e; s0 += RPP) {
         RowState rs;
+        int orig[RPP];
         bool anyrow = false;
         {
             float px[RPP], py[RPP], pz[RPP];
@@ -602,11 +646,9 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
                 const int s = min(s0 + r, e - 1);
                 const int rel = self_base + s;                       // the row's own particle in the window
                 float4 pi = cand_w[rel];
-                bool ok = s0 + r < e;
-                if (!full) {
-                    const int o = __ldg(p.sorted_idx + s);
-                    ok = ok && o >= p.row_lo && o < p.row_hi;
-                }
+                const int o = __ldg(p.sorted_idx + s);               // needed for the row address anyway
+                const bool ok = (s0 + r < e) && o >= p.row_lo && o < p.row_hi;
+                orig[r] = ok ? o : -1;
                 if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);       // never hits
                 px[r] = pi.x; py[r] = pi.y; pz[r] = pi.z; rs.t[r] = pi.w;
                 rs.self_rel[r] = ok ? rel : -1;
@@ -616,25 +658,76 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
             if (!anyrow) continue;
 #pragma unroll
             for (int h = 0; h < RPP / 2; h++) {
-                rs.x[h] = pack2(px[2 * h], px[2 * h + 1]);
-                rs.y[h] = pack2(py[2 * h], py[2 * h + 1]);
-                rs.z[h] = pack2(pz[2 * h], pz[2 * h + 1]);
+                rs.x[h] = pack2_pinned(px[2 * h], px[2 * h + 1]);
+                rs.y[h] = pack2_pinned(py[2 * h], py[2 * h + 1]);
+                rs.z[h] = pack2_pinned(pz[2 * h], pz[2 * h + 1]);
             }
         }
-        if (wrap) test_window<true, MAPPED, true>(p, cand_w, mround, mlen, rs, lane);
-        else test_window<false, MAPPED, true>(p, cand_w, mround, mlen, rs, lane);
+        // the rows of a batch are consecutive particles of the own cell: their chunks are s0's .. s0+RPP-1's
+        const int chk_lo = (self_base + s0) & ~31, chk_hi = (self_base + min(s0 + RPP, e) - 1) & ~31;
+        if (wrap) test_window<true, MAPPED>(p, cand_w, mround, mlen, chk_lo, chk_hi, rs, lane);
+        else test_window<false, MAPPED>(p, cand_w, mround, mlen, chk_lo, chk_hi, rs, lane);
         __syncwarp();
-#pragma unroll 1
+
+        // ---- emit the batch.  Lane counts of two rows share one 32-bit scan (16 bits each). ----
+        int cl[RPP], excl[RPP], tot[RPP];
+#pragma unroll
+        for (int r = 0; r < RPP; r++) cl[r] = (int)((rs.lp[r] - (lists_s + (unsigned)(r * capW + lane) * 2u)) >> 6);
+#pragma unroll
+        for (int h = 0; h < RPP / 2; h++) {
+            const unsigned packed = (unsigned)cl[2 * h] | ((unsigned)cl[2 * h + 1] << 16);
+            unsigned inc = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(HTF_FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const unsigned all = __shfl_sync(HTF_FULL, inc, 31);
+            const unsigned ex = inc - packed;
+            excl[2 * h] = (int)(ex & 0xffffu); excl[2 * h + 1] = (int)(ex >> 16);
+            tot[2 * h] = (int)(all & 0xffffu); tot[2 * h + 1] = (int)(all >> 16);
+        }
+#pragma unroll
         for (int r = 0; r < RPP; r++) {
-            const int srow = s0 + r;
-            if (srow >= e) break;
-            const int orig = __ldg(p.sorted_idx + srow);
-            if (orig < p.row_lo || orig >= p.row_hi) continue;           // warp-uniform
-            const float4 pi = cand_w[self_base + srow];
-            const unsigned lp_r = r == 0 ? rs.lp[0] : r == 1 ? rs.lp[1] : r == 2 ? rs.lp[2] : rs.lp[3];
+            if (orig[r] < 0) continue;                                   // warp-uniform
             const unsigned list_s = lists_s + (unsigned)(r * capW + lane) * 2u;
-            const int c_l = (int)((lp_r - list_s) >> 6);
-            emit_single_window<WITH_IDX>(p, cand_ws, candidx_w, slotmap_s, list_s, c_l, wrap, pi, orig, lane);
+            const int total = tot[r];
+            const size_t row = (size_t)(orig[r] - p.row_lo);
+            if (total > K) {
+                // overflowing row: modulo-K rule of htf/TensorflowCompute.cc:370 (cold path)
+                const float4 pi = cand_w[self_base + s0 + r];
+                emit_single_window<WITH_IDX>(p, cand_ws, candidx_w, slotmap_s, list_s, cl[r], wrap, pi, orig[r], lane);
+                continue;
+            }
+            // slot -> candidate map: slots [0,total) are exactly the hits, lane-major
+            const unsigned qa = slotmap_s + (unsigned)excl[r] * 2u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < cl[r]) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+            if (__any_sync(HTF_FULL, cl[r] > 4))
+                for (int k = 4; k < cl[r]; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
+            __syncwarp();
+            const float4 pi = lds_f4(cand_ws + (unsigned)(self_base + s0 + r) * 16u);
+            float4 *dst = p.out + row * K + lane;
+            int *idst = WITH_IDX ? p.idx_out + row * K + lane : nullptr;
+            unsigned sa = slotmap_s + 2u * lane;
+            for (int sl = lane; sl < K; sl += 32, dst += 32, sa += 64u) {
+                const bool valid = sl < total;
+                const unsigned ci = valid ? lds_u16(sa) : 0u;            // stale map entries are never dereferenced
+                const float4 cd = lds_f4(cand_ws + ci * 16u);
+                float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+                if (wrap) {
+                    dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                    dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                    dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                }
+                const float4 v = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *dst = v;
+                if (WITH_IDX) { *idst = valid ? candidx_w[ci] : -1; idst += 32; }
+            }
+            if (p.count_out && lane == 0) p.count_out[row] = total;
+            if (total == K && p.overflow && lane == 0) atomicMax(p.overflow, total);
+            __syncwarp();
         }
     }
 }

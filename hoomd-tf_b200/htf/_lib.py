@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
+LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
 ABI_VERSION = 5
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
