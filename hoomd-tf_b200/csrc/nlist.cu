@@ -545,9 +545,9 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
 
     const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
-    const int tiles_x = (nx + TILE - 1) / TILE;
-    const int bid = blockIdx.x;
-    const int tx = bid % tiles_x, cy = (bid / tiles_x) % ny, cz = bid / (tiles_x * ny);
+    const int tiles_x = gridDim.x;                              // = ceil(nx / TILE)
+    const int tx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+    const int bid = (cz * ny + cy) * tiles_x + tx;
     const int cx0 = tx * TILE;
     const int nact = min(TILE, nx - cx0);                       // cells of this tile
     const int nly = min(ny, 3), nlz = min(nz, 3), nyz = nly * nlz;
@@ -595,15 +595,14 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     if (!fits) return;                                          // block-uniform
 
     // ---- stage the whole neighbourhood once (asynchronous copies, one wait) ----
-    for (int t = tid; t < mblock; t += TILE * 32) {
-        int lo = 0, hi = npieces - 1;                           // first piece q with t < end[q]
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (t < ptab_end[mid]) hi = mid; else lo = mid + 1;
+    // warp w copies pieces w, w+TILE, ...: a piece is one cell (a dozen particles), one lane each
+    for (int q = warp; q < npieces; q += TILE) {
+        const int qend = ptab_end[q], qadj = ptab_adj[q];
+        const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
+        for (int t = qbeg + lane; t < qend; t += 32) {
+            cp_async16(cand_s + (unsigned)t * 16u, p.spos + (t + qadj));
+            if (WITH_IDX) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
         }
-        const int src = t + ptab_adj[lo];
-        cp_async16(cand_s + (unsigned)t * 16u, p.spos + src);
-        if (WITH_IDX) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + src);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -733,7 +732,7 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
 }
 
 template <bool WITH_IDX, bool MAPPED>
-cudaError_t launch_tile_variant(const NlistParams &p, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_tile_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     static size_t configured = 0;
     if (smem > configured) {
@@ -821,16 +820,17 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
         int capB = (int)(bmean + 5.0 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
         capB = (capB + 31) / 32 * 32;
         const size_t bytes = tile_block_bytes(capB, cap, p.K, with_idx);
-        if (capB <= 32768 && bytes <= 100 * 1024) {           // keep >= 2 blocks per SM, else per-cell only
+        if (capB <= 32768 && bytes <= 100 * 1024 && g.n[1] <= 65535 && g.n[2] <= 65535) {           // keep >= 2 blocks per SM, else per-cell only
             if ((e = htf_ensure_tile_flags(ctx, ntiles)) != cudaSuccess) return e;
             p.cap = cap;
             p.cap_tile = capB;
             p.tile_flag = ctx->d_tile_flag;
             ctx->launches += 1;
-            e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, ntiles, bytes, st)
-                                   : launch_tile_variant<true, false>(p, ntiles, bytes, st))
-                         : (mapped ? launch_tile_variant<false, true>(p, ntiles, bytes, st)
-                                   : launch_tile_variant<false, false>(p, ntiles, bytes, st));
+            const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)g.n[2]);
+            e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, tg, bytes, st)
+                                   : launch_tile_variant<true, false>(p, tg, bytes, st))
+                         : (mapped ? launch_tile_variant<false, true>(p, tg, bytes, st)
+                                   : launch_tile_variant<false, false>(p, tg, bytes, st));
             if (e != cudaSuccess) return e;
             tiled = true;
         }
