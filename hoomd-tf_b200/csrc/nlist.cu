@@ -35,7 +35,7 @@
 namespace {
 
 #ifndef HTF_RPP
-#define HTF_RPP 4
+#define HTF_RPP 2
 #endif
 #ifndef HTF_TILE
 #define HTF_TILE 4
@@ -61,6 +61,12 @@ struct NlistParams {
     int *count_out;
     int *overflow;
 };
+
+#ifdef HTF_EXP_COLD_NOINLINE
+#define HTF_EMIT_INLINE __noinline__
+#else
+#define HTF_EMIT_INLINE __forceinline__
+#endif
 
 typedef unsigned long long f32x2;
 
@@ -145,18 +151,16 @@ struct RowState {
 };
 
 // ---- test: append the window-relative index of every hit to the lane-private lists ----
-// One 32-candidate chunk against the RPP rows.  CHECKED chunks also apply the two lane-dependent
-// conditions (the candidate is the row's own particle; the candidate lies past the end of the
-// window); only the chunk(s) holding the rows' own particles and the last chunk need them, so the
-// steady-state body is: 1 LDS.128, 6 packed subs, 6 packed squares, 8 adds, 4 compares and the
-// predicated list appends.
-template <bool WRAP, bool MAPPED, bool CHECKED>
+// One 32-candidate chunk against the RPP rows: 1 LDS.128, 6 packed subs, 6 packed squares, 8 adds,
+// 4 compares (+ the "is this the row's own particle" compare) and the predicated list appends.
+// MASKED adds the "candidate lies past the end of the window" test (only tiny grids need it).
+template <bool WRAP, bool MAPPED, bool MASKED>
 __device__ __forceinline__ void test_chunk(const NlistParams &p, const float4 *cand, int t0, int mlen, RowState &rs,
                                            int lane)
 {
     const int tl = t0 + lane;
     const float4 c = cand[tl];
-    const bool pv = !CHECKED || tl < mlen;
+    const bool pv = !MASKED || tl < mlen;
     const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
 #pragma unroll
     for (int h = 0; h < RPP / 2; h++) {
@@ -181,8 +185,8 @@ __device__ __forceinline__ void test_chunk(const NlistParams &p, const float4 *c
             const int r = 2 * h + u;
             const float rsq = __fadd_rn(__fadd_rn(xx[u], yy[u]), zz[u]);
             // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
-            bool hit = rsq <= p.rc2;
-            if (CHECKED) hit = hit & (tl != rs.self_rel[r]) & pv;
+            bool hit = (rsq <= p.rc2) & (tl != rs.self_rel[r]);
+            if (MASKED) hit = hit & pv;
             if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
             if (hit) {
                 sts_u16(rs.lp[r], (unsigned)tl);
@@ -192,28 +196,19 @@ __device__ __forceinline__ void test_chunk(const NlistParams &p, const float4 *c
     }
 }
 
-// all chunks of a window; [chk_lo, chk_hi] = chunk offsets that hold the rows' own particles
-template <bool WRAP, bool MAPPED>
+template <bool WRAP, bool MAPPED, bool MASKED>
 __device__ __forceinline__ void test_window(const NlistParams &p, const float4 *cand, int mround, int mlen,
-                                            int chk_lo, int chk_hi, RowState &rs, int lane)
+                                            RowState &rs, int lane)
 {
-    const int last = mround - 32;
 #pragma unroll 1
-    for (int t0 = 0; t0 < mround; t0 += 32) {
-#ifndef HTF_EXP_SPLIT
-        test_chunk<WRAP, MAPPED, true>(p, cand, t0, mlen, rs, lane);
-#else
-        if ((t0 >= chk_lo && t0 <= chk_hi) || t0 == last) test_chunk<WRAP, MAPPED, true>(p, cand, t0, mlen, rs, lane);
-        else test_chunk<WRAP, MAPPED, false>(p, cand, t0, mlen, rs, lane);
-#endif
-    }
+    for (int t0 = 0; t0 < mround; t0 += 32) test_chunk<WRAP, MAPPED, MASKED>(p, cand, t0, mlen, rs, lane);
 }
 
 // ---- emit one row whose hits all come from the single staged window ----
 // Scan of the lane counts -> slot ranges; "slot -> candidate" published in a small shared map; then lane s
 // re-derives d for slots s, s+32, ... and stores them coalesced, zero padding included.
 template <bool WITH_IDX>
-__device__ __forceinline__ void emit_single_window(const NlistParams &p, unsigned cand_s, const int *candidx,
+__device__ HTF_EMIT_INLINE void emit_single_window(const NlistParams &p, unsigned cand_s, const int *candidx,
                                                    unsigned slotmap_s, unsigned list_s, int c_l, bool wrap,
                                                    const float4 &pi, int orig, int lane)
 {
@@ -269,8 +264,56 @@ __device__ __forceinline__ void emit_single_window(const NlistParams &p, unsigne
     __syncwarp();
 }
 
+// Slot phase of the emit: lane s derives (d, type) for slots s, s+32, ... of one row and stores them
+// coalesced.  KCH = K/32 when that is a compile-time-friendly value (fully unrolled, immediate offsets),
+// 0 = generic K.
+template <bool WITH_IDX, int KCH>
+__device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_ws, const int *candidx_w,
+                                           unsigned slotmap_s, const float4 &pi, bool wrap, int total, size_t row,
+                                           int lane)
+{
+    const int K = KCH ? KCH * 32 : p.K;
+    float4 *dst = p.out + row * K + lane;
+    int *idst = WITH_IDX ? p.idx_out + row * K + lane : nullptr;
+    const unsigned sa = slotmap_s + 2u * lane;
+    if (KCH) {
+#pragma unroll
+        for (int i = 0; i < (KCH ? KCH : 1); i++) {
+            const int sl = lane + 32 * i;
+            const bool valid = sl < total;
+            const unsigned ci = valid ? lds_u16(sa + 64u * i) : 0u;      // stale map entries are never dereferenced
+            const float4 cd = lds_f4(cand_ws + ci * 16u);
+            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+            if (wrap) {
+                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+            }
+            dst[32 * i] = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (WITH_IDX) idst[32 * i] = valid ? candidx_w[ci] : -1;
+        }
+    } else {
+        unsigned sb = sa;
+        for (int sl = lane; sl < K; sl += 32, dst += 32, sb += 64u) {
+            const bool valid = sl < total;
+            const unsigned ci = valid ? lds_u16(sb) : 0u;
+            const float4 cd = lds_f4(cand_ws + ci * 16u);
+            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
+            if (wrap) {
+                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
+                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
+                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+            }
+            *dst = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (WITH_IDX) { *idst = valid ? candidx_w[ci] : -1; idst += 32; }
+        }
+    }
+}
+
 constexpr int TILE = HTF_TILE;    // cells per block along x in the tile kernel (= warps per block)
-constexpr int TILE_HDR = 576;     // bytes: piece table end[64] + adj[64] + colstart[16]
+constexpr int NPMAX = 128;        // piece table capacity: (TILE + 2) * 9 <= NPMAX  ->  TILE <= 12
+constexpr int TILE_HDR = (2 * NPMAX + 32) * 4;   // bytes: piece table end[NPMAX] + adj[NPMAX] + colstart[24] + warp totals[8]
+static_assert((TILE + 2) * 9 <= NPMAX && TILE * 32 >= (TILE + 2) * 9 && TILE + 3 <= 24, "tile size");
 
 template <bool WITH_IDX, bool MAPPED>
 __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
@@ -426,12 +469,8 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 rs.self_rel[r] = (rvalid[r] && rel >= 0 && rel < mround) ? rel : -1;
                 rs.lp[r] = lists_s + (unsigned)(r * cap + lane) * 2u;
             }
-            int chk_lo = 0x7fffffff, chk_hi = -1;
-#pragma unroll
-            for (int r = 0; r < RPP; r++)
-                if (rs.self_rel[r] >= 0) { chk_lo = min(chk_lo, rs.self_rel[r] & ~31); chk_hi = max(chk_hi, rs.self_rel[r] & ~31); }
-            if (wrap) test_window<true, MAPPED>(p, cand, mround, mround, chk_lo, chk_hi, rs, lane);
-            else test_window<false, MAPPED>(p, cand, mround, mround, chk_lo, chk_hi, rs, lane);
+            if (wrap) test_window<true, MAPPED, false>(p, cand, mround, mround, rs, lane);
+            else test_window<false, MAPPED, false>(p, cand, mround, mround, rs, lane);
             __syncwarp();
 
             // ---- emit, row by row (kept rolled: this code runs once per row, not once per pair) ----
@@ -530,9 +569,10 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = p.K, capB = p.cap_tile, capW = p.cap;
-    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [64] inclusive prefix of piece lengths
-    int *ptab_adj = ptab_end + 64;                              // [64] source slot - staged index
-    int *colstart = ptab_adj + 64;                              // [<= TILE+3] staged offset of each column
+    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [NPMAX] inclusive prefix of piece lengths
+    int *ptab_adj = ptab_end + NPMAX;                           // [NPMAX] source slot - staged index
+    int *colstart = ptab_adj + NPMAX;                           // [<= TILE+3] staged offset of each column
+    int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
     float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE_HDR);
     int *candidx = reinterpret_cast<int *>(cand + capB + 32);
     unsigned char *wbase = WITH_IDX ? reinterpret_cast<unsigned char *>(candidx + capB + 32)
@@ -575,10 +615,10 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
         const int t = __shfl_up_sync(HTF_FULL, incl, o);
         if (lane >= o) incl += t;
     }
-    if (tid == 31) colstart[15] = incl;                         // total of the first 32 pieces
+    if (lane == 31 && warp < 4) wtot[warp] = incl;              // totals of pieces [32w, 32w+32)
     __syncthreads();
-    if (warp == 1) incl += colstart[15];
-    if (tid < 64) {
+    for (int w = 0; w < warp && w < 4; w++) incl += wtot[w];
+    if (tid < NPMAX) {
         ptab_end[tid] = incl;
         ptab_adj[tid] = pb - (incl - pl);
         if (tid < npieces && tid % nyz == 0) colstart[tid / nyz] = incl - pl;
@@ -604,6 +644,8 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
             if (WITH_IDX) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
         }
     }
+    // 32 sentinels behind the staged data: the last chunk of the last window may read past its end
+    if (warp == 0) cand[mblock + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
@@ -625,13 +667,24 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     const bool wrap = !((nx >= 5 && cx >= 1 && cx <= nx - 2) && (ny >= 5 && cy >= 1 && cy <= ny - 2) &&
                         (nz >= 5 && cz >= 1 && cz <= nz - 2));
     const int ws = xs ? colstart[warp] : 0;
-    const int mlen = (xs ? colstart[warp + 3] : mblock) - ws;
-    const int mround = (mlen + 31) & ~31;
+    const int mlen_true = (xs ? colstart[warp + 3] : mblock) - ws;
+    const int mround = (mlen_true + 31) & ~31;
+    // With >= 4 cells in x, whatever follows the window in the buffer is the x-column two cells away (or the
+    // sentinels): farther than r_cut in x by construction of the grid, so it can never pass the cutoff test
+    // and the "past the end of the window" mask is unnecessary.  Tiny grids keep the mask.
+    // (test_window<..., MASKED = true> is used for nx < 4 only)
     // staged position of this cell's own particles: piece (own column, own (y,z))
     const int ps = (xs ? warp + 1 : cx) * nyz + (nz <= 3 ? cz : 1) * nly + (ny <= 3 ? cy : 1);
     const int self_base = (ps == 0 ? 0 : ptab_end[ps - 1]) - ws - b;
     const float4 *cand_w = cand + ws;
     const unsigned cand_ws = cand_s + (unsigned)ws * 16u;
+#ifdef HTF_EXP_NOUNROLL
+    const int kch = 0;
+#elif defined(HTF_EXP_UNROLL3)
+    const int kch = (K == 64) ? 2 : (K == 96 ? 3 : 0);
+#else
+    const int kch = (K == 64) ? 2 : 0;          // unrolled slot phase for K = 64; more copies cost more in I-cache
+#endif
     const int *candidx_w = candidx + ws;
 
     for (int s0 = b; s0 < e; s0 += RPP) {
@@ -662,10 +715,14 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
                 rs.z[h] = pack2_pinned(pz[2 * h], pz[2 * h + 1]);
             }
         }
-        // the rows of a batch are consecutive particles of the own cell: their chunks are s0's .. s0+RPP-1's
-        const int chk_lo = (self_base + s0) & ~31, chk_hi = (self_base + min(s0 + RPP, e) - 1) & ~31;
-        if (wrap) test_window<true, MAPPED>(p, cand_w, mround, mlen, chk_lo, chk_hi, rs, lane);
-        else test_window<false, MAPPED>(p, cand_w, mround, mlen, chk_lo, chk_hi, rs, lane);
+#ifdef HTF_EXP_MASKALL
+        if (!wrap) test_window<false, MAPPED, true>(p, cand_w, mround, mlen_true, rs, lane);
+        else test_window<true, MAPPED, true>(p, cand_w, mround, mlen_true, rs, lane);
+#else
+        if (!wrap) test_window<false, MAPPED, false>(p, cand_w, mround, mround, rs, lane);
+        else if (nx >= 4) test_window<true, MAPPED, false>(p, cand_w, mround, mround, rs, lane);
+        else test_window<true, MAPPED, true>(p, cand_w, mround, mlen_true, rs, lane);
+#endif
         __syncwarp();
 
         // ---- emit the batch.  Lane counts of two rows share one 32-bit scan (16 bits each). ----
@@ -707,25 +764,15 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
                 for (int k = 4; k < cl[r]; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
             __syncwarp();
             const float4 pi = lds_f4(cand_ws + (unsigned)(self_base + s0 + r) * 16u);
-            float4 *dst = p.out + row * K + lane;
-            int *idst = WITH_IDX ? p.idx_out + row * K + lane : nullptr;
-            unsigned sa = slotmap_s + 2u * lane;
-            for (int sl = lane; sl < K; sl += 32, dst += 32, sa += 64u) {
-                const bool valid = sl < total;
-                const unsigned ci = valid ? lds_u16(sa) : 0u;            // stale map entries are never dereferenced
-                const float4 cd = lds_f4(cand_ws + ci * 16u);
-                float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
-                if (wrap) {
-                    dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                    dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                    dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
-                }
-                const float4 v = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
-                *dst = v;
-                if (WITH_IDX) { *idst = valid ? candidx_w[ci] : -1; idst += 32; }
+            if (kch == 2) emit_slots<WITH_IDX, 2>(p, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
+#ifdef HTF_EXP_UNROLL3
+            else if (kch == 3) emit_slots<WITH_IDX, 3>(p, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
+#endif
+            else emit_slots<WITH_IDX, 0>(p, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
+            if (lane == 0 && (p.count_out != nullptr || total == K)) {
+                if (p.count_out) p.count_out[row] = total;
+                if (total == K && p.overflow) atomicMax(p.overflow, total);
             }
-            if (p.count_out && lane == 0) p.count_out[row] = total;
-            if (total == K && p.overflow && lane == 0) atomicMax(p.overflow, total);
             __syncwarp();
         }
     }
