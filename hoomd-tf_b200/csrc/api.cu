@@ -238,6 +238,7 @@ int htf_set_box(htf_ctx *ctx, const float h_lo[3], const float h_hi[3], const fl
     for (int a = 0; a < 3; a++) {
         if (!(h_hi[a] > h_lo[a])) { set_err(ctx, "htf_set_box: hi <= lo on axis %d", a); return HTF_EINVAL; }
         ctx->grid.lo[a] = h_lo[a]; ctx->grid.hi[a] = h_hi[a]; ctx->grid.L[a] = h_hi[a] - h_lo[a];
+        ctx->grid.half[a] = 0.5f * ctx->grid.L[a];
     }
     ctx->box_set = true;
     DeviceGuard guard(ctx->device);

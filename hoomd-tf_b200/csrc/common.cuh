@@ -11,6 +11,8 @@
 // when the fp32 cell index of a particle on a cell face rounds to either side.
 struct CellGrid {
     float lo[3], hi[3], L[3];
+    float half[3];       // L / 2: minimum image is "d >= half -> d -= L; d < -half -> d += L" (HOOMD boxes are
+                         // centred, so half == hi and -half == lo there; other origins work the same way)
     float inv_w[3];      // n / L
     int n[3];
     int ncell;

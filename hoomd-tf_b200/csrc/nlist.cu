@@ -170,9 +170,9 @@ __device__ __forceinline__ void test_chunk(const NlistParams &p, const float4 *c
             unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                dz[u] = wrap_axis(dz[u], p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                dy[u] = wrap_axis(dy[u], p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                dx[u] = wrap_axis(dx[u], p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
                 xx[u] = __fmul_rn(dx[u], dx[u]); yy[u] = __fmul_rn(dy[u], dy[u]); zz[u] = __fmul_rn(dz[u], dz[u]);
             }
         } else {
@@ -247,9 +247,9 @@ __device__ HTF_EMIT_INLINE void emit_single_window(const NlistParams &p, unsigne
             const float4 cd = lds_f4(cand_s + ci * 16u);
             float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
             if (wrap) {
-                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
             }
             v = make_float4(dx, dy, dz, cd.w);
             if (WITH_IDX) vi = candidx[ci];
@@ -285,9 +285,9 @@ __device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_w
             const float4 cd = lds_f4(cand_ws + ci * 16u);
             float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
             if (wrap) {
-                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
             }
             dst[32 * i] = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (WITH_IDX) idst[32 * i] = valid ? candidx_w[ci] : -1;
@@ -300,9 +300,9 @@ __device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_w
             const float4 cd = lds_f4(cand_ws + ci * 16u);
             float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
             if (wrap) {
-                dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);
-                dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
             }
             *dst = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (WITH_IDX) { *idst = valid ? candidx_w[ci] : -1; idst += 32; }
@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                     if (ci != 0xffffu) {
                         const float4 cd = cand[ci];
                         float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
-                        dz = wrap_axis(dz, p.g.lo[2], p.g.hi[2], p.g.L[2]);     // a no-op for interior cells
-                        dy = wrap_axis(dy, p.g.lo[1], p.g.hi[1], p.g.L[1]);
-                        dx = wrap_axis(dx, p.g.lo[0], p.g.hi[0], p.g.L[0]);
+                        dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);     // a no-op for interior cells
+                        dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                        dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
                         v = make_float4(dx, dy, dz, cd.w);
                         if (WITH_IDX) vi = candidx[ci];
                     }

@@ -18,7 +18,9 @@
  * Third-party arithmetic that is NOT under /root/reference and is restated from
  * its published behaviour (see DESIGN.md "Oracle"):
  *   - HOOMD-blue (>=2.6, CI pins 2.7.0/2.8.2/2.9.2) BoxDim::minImage, CPU branch:
- *     per axis "if (w >= hi) w -= L; else if (w < lo) w += L", single image.
+ *     per axis "if (w >= hi) w -= L; else if (w < lo) w += L", single image.  HOOMD boxes are
+ *     centred on the origin (lo = -L/2, hi = L/2); the rule is applied with +-L/2 so that boxes
+ *     with another origin (iter_from_trajectory uses lo = 0, htf/utils.py:702) behave the same.
  *   - TensorFlow (>=2.3, CI pins 2.3.2/2.4.1) tf.norm = sqrt(sum(x*x)),
  *     tf.histogram_fixed_width CPU kernel: step = double(hi-lo)/nbins,
  *     bin = int32(min(double(max(v,lo)-lo)/step, nbins-1)).
@@ -43,19 +45,22 @@
 #include <omp.h>
 #endif
 
-typedef struct { float lo[3], hi[3], L[3]; } obox_t;
+typedef struct { float lo[3], hi[3], L[3], half[3]; } obox_t;
 
 static void make_box(const float *lo, const float *hi, obox_t *b)
 {
-    for (int a = 0; a < 3; a++) { b->lo[a] = lo[a]; b->hi[a] = hi[a]; b->L[a] = hi[a] - lo[a]; }
+    for (int a = 0; a < 3; a++) {
+        b->lo[a] = lo[a]; b->hi[a] = hi[a]; b->L[a] = hi[a] - lo[a];
+        b->half[a] = 0.5f * b->L[a];       /* HOOMD boxes are centred: half == hi, -half == lo */
+    }
 }
 
 /* HOOMD BoxDim::minImage, CPU branch (called at htf/TensorflowCompute.cc:358). */
 static inline void min_image(const obox_t *b, float *d)
 {
     for (int a = 2; a >= 0; a--) {          /* z, then y, then x */
-        if (d[a] >= b->hi[a]) d[a] -= b->L[a];
-        else if (d[a] < b->lo[a]) d[a] += b->L[a];
+        if (d[a] >= b->half[a]) d[a] -= b->L[a];
+        else if (d[a] < -b->half[a]) d[a] += b->L[a];
     }
 }
 

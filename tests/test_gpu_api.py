@@ -216,7 +216,7 @@ def test_training_force_matching():
     tfc2.attach(htf.sim.nlist_cell(system), train=True, r_cut=rcut, save_output_period=2)
     tfc2.set_reference_forces(lj)
     system.run(40)
-    assert float((tm.dense1.weight.detach() - w0).abs().max()) > 1e-4
+    assert float((tm.dense1.weight.detach().cpu() - w0.cpu()).abs().max()) > 1e-4
     assert tfc2.outputs[0].shape[0] >= 10
 
 

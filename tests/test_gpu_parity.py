@@ -292,3 +292,14 @@ def test_inhomogeneous_multi_window(oracle_mod):
             full_o, idx_all, _ = oracle_mod.nlist(pos, lo, hi, 2.0, 512, cells=False)
             for r in np.where(~ok)[0][:50]:                   # overflowed rows hold K distinct genuine neighbors
                 assert len(set(idx_g[r])) == K and set(idx_g[r]).issubset(set(idx_all[r][idx_all[r] >= 0]))
+
+
+def test_box_with_origin_at_zero(oracle_mod):
+    """iter_from_trajectory hands boxes with lo = 0 (htf/utils.py:702): minimum image is +-L/2, not lo/hi."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 8), 0.7, seed=13)
+    shift = (hi - lo) * 0.5
+    pos2 = pos.copy()
+    pos2[:, :3] += shift.astype(np.float32)
+    lo2, hi2 = np.zeros(3, np.float32), (hi - lo).astype(np.float32)
+    check_nlist_case(oracle_mod, pos2, lo2, hi2, 2.5, 64, cells=False)
