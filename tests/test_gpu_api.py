@@ -262,7 +262,7 @@ def test_nlist_compare_and_pairwise():
     assert out[0].shape[0] == 5
     e = out[0][:, 0, 3]
     rr = np.linspace(0.5, 1.5, 5)
-    np.testing.assert_allclose(e, 2 * (rr ** -12 - rr ** -6), rtol=1e-3)
+    np.testing.assert_allclose(e, 2 * (rr ** -12 - rr ** -6), rtol=1e-3, atol=1e-4)
 
 
 def test_eds_bias_converges():
