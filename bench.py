@@ -287,7 +287,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg_dict(args, n, K, r_cut, world),
-            "roofline": {"bound": "hbm", "kernel": "nlist_build_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "nlist_tile_kernel (+ per-cell fallback pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_build, "kernel_ms": build_ms,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,

@@ -315,21 +315,13 @@ constexpr int NPMAX = 128;        // piece table capacity: (TILE + 2) * 9 <= NPM
 constexpr int TILE_HDR = (2 * NPMAX + 32) * 4;   // bytes: piece table end[NPMAX] + adj[NPMAX] + colstart[24] + warp totals[8]
 static_assert((TILE + 2) * 9 <= NPMAX && TILE * 32 >= (TILE + 2) * 9 && TILE + 3 <= 24, "tile size");
 
+// One warp builds all rows of one cell with its own staging buffer (any density: candidates are
+// re-staged in windows when they do not fit).
 template <bool WITH_IDX, bool MAPPED>
-__global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
+__device__ __forceinline__ void build_cell(const NlistParams &p, const int cell, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int wpb = blockDim.x >> 5;
-    const int cell = blockIdx.x * wpb + warp;
-    if (cell >= p.g.ncell) return;
-    if (p.use_flags) {                    // second pass after the tile kernel: only the tiles it gave up on
-        const int nx_ = p.g.n[0], tiles_x = (nx_ + TILE - 1) / TILE;
-        const int tile = (cell / nx_) * tiles_x + (cell % nx_) / TILE;
-        if (!p.tile_flag[tile]) return;
-    }
-
     const int K = p.K;
     const int cap = p.cap;
     // per-warp carve-up (see per_warp_bytes): cand[cap] f4 | rowstage[K] f4 | lists[RPP][cap] u16 |
@@ -553,6 +545,29 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
                 __syncwarp();
             }
         }
+    }
+}
+
+// Per-cell kernel.  Stand-alone it walks every cell (one warp each).  As the second pass behind the
+// tile kernel it is a small persistent grid that scans the tile flags and builds only the cells of
+// flagged tiles -- with no flagged tile it costs a few microseconds.
+template <bool WITH_IDX, bool MAPPED>
+__global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    if (!p.use_flags) {
+        const int cell = blockIdx.x * wpb + warp;
+        if (cell < p.g.ncell) build_cell<WITH_IDX, MAPPED>(p, cell, smem_raw);
+        return;
+    }
+    const int nx = p.g.n[0], tiles_x = (nx + TILE - 1) / TILE;
+    const int ntiles = tiles_x * p.g.n[1] * p.g.n[2];
+    for (int tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
+        if (!p.tile_flag[tile]) continue;
+        const int tx = tile % tiles_x, row = tile / tiles_x;        // row = cz * ny + cy
+        for (int c = 0; c < TILE && tx * TILE + c < nx; c++) build_cell<WITH_IDX, MAPPED>(p, row * nx + tx * TILE + c, smem_raw);
     }
 }
 
@@ -896,7 +911,8 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     }
     p.cap = cap;
     const size_t smem = per_warp_bytes(cap, p.K, with_idx) * wpb;
-    const int grid = (g.ncell + wpb - 1) / wpb;
+    int grid = (g.ncell + wpb - 1) / wpb;
+    if (tiled) grid = min((ntiles + wpb - 1) / wpb, 2 * ctx->sm_count);    // persistent scan of the tile flags
     ctx->launches += 1;
     if (with_idx) return mapped ? launch_variant<true, true>(p, grid, wpb, smem, st)
                                 : launch_variant<true, false>(p, grid, wpb, smem, st);
