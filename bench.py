@@ -211,6 +211,9 @@ def run_b200(args):
 
     ctx = htf.HtfContext(n, K, r_cut, device=dev)
     ctx.set_box(lo, hi)
+    if world > 1:
+        # bin only what can matter for this rank's rows (slab +- (r_cut + skin)), like HOOMD's ghost layer
+        ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
     d_pos_all = torch.from_numpy(pos).to(dev)
     d_shard = d_pos_all[row_lo:row_hi].clone()
     nl = torch.empty((rows, K, 4), dtype=torch.float32, device=dev)

@@ -206,6 +206,7 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device; ctx->sm_count = sms; ctx->flags = flags; ctx->n_max = n_max; ctx->K = k;
     ctx->r_cut = r_cut; ctx->map_type_start = -1;
+    for (int a = 0; a < 3; a++) ctx->grid.roi_h[a] = -1.0f;
     DeviceGuard guard(device);
     int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
     if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
@@ -243,6 +244,18 @@ int htf_set_box(htf_ctx *ctx, const float h_lo[3], const float h_hi[3], const fl
     ctx->box_set = true;
     DeviceGuard guard(ctx->device);
     return make_grid(ctx);
+}
+
+int htf_set_roi(htf_ctx *ctx, const float h_center[3], const float h_half_width[3])
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    for (int a = 0; a < 3; a++) {
+        ctx->grid.roi_c[a] = (h_center && h_half_width) ? h_center[a] : 0.0f;
+        ctx->grid.roi_h[a] = (h_center && h_half_width) ? h_half_width[a] : -1.0f;
+    }
+    ctx->binned = false;
+    return HTF_OK;
 }
 
 int htf_set_mapped_nlist(htf_ctx *ctx, int map_type_start)

@@ -28,6 +28,19 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const float4 *__restric
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = __ldg(pos + i);
+    {   // region of interest (sharded builds): particles that cannot be within r_cut of a local row are skipped
+        const float q[3] = {p.x, p.y, p.z};
+        bool in = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (g.roi_h[a] >= 0.0f) {
+                float d = q[a] - g.roi_c[a];
+                d = d >= g.half[a] ? d - g.L[a] : (d < -g.half[a] ? d + g.L[a] : d);
+                in = in && fabsf(d) <= g.roi_h[a];
+            }
+        }
+        if (!in) { cell_of[i] = -1; return; }
+    }
     int cx = cell_coord(p.x, g.lo[0], g.inv_w[0], g.n[0]);
     int cy = cell_coord(p.y, g.lo[1], g.inv_w[1], g.n[1]);
     int cz = cell_coord(p.z, g.lo[2], g.inv_w[2], g.n[2]);
@@ -126,6 +139,7 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int c = cell_of[i];
+    if (c < 0) return;                      // outside the region of interest
     int k = atomicSub(cell_cnt + c, 1) - 1;
     sorted_idx[cell_start[c] + k] = i;
 }

@@ -16,6 +16,9 @@ struct CellGrid {
     float inv_w[3];      // n / L
     int n[3];
     int ncell;
+    // region of interest for binning (row sharding over GPUs): only particles whose minimum-image distance
+    // from roi_c is <= roi_h on every axis are binned; roi_h < 0 disables the test on that axis
+    float roi_c[3], roi_h[3];
 };
 
 struct htf_ctx {

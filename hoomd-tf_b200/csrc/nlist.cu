@@ -648,6 +648,20 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     }
     if (tid == 0) p.tile_flag[bid] = fits ? 0 : 1;
     if (!fits) return;                                          // block-uniform
+    const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
+    if (!full) {
+        // sharded build: skip the tile (before staging anything) when none of its cells holds a local row
+        bool any = false;
+        if (warp < nact) {
+            const int c = (cz * ny + cy) * nx + cx0 + warp;
+            const int cb_ = __ldg(p.cell_start + c), ce_ = __ldg(p.cell_start + c + 1);
+            for (int s = cb_ + lane; s < ce_; s += 32) {
+                const int o = __ldg(p.sorted_idx + s);
+                any |= (o >= p.row_lo && o < p.row_hi);
+            }
+        }
+        if (!__syncthreads_or(any)) return;
+    }
 
     // ---- stage the whole neighbourhood once (asynchronous copies, one wait) ----
     // warp w copies pieces w, w+TILE, ...: a piece is one cell (a dozen particles), one lane each
@@ -670,7 +684,6 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     const int cell = (cz * ny + cy) * nx + cx;
     const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
     if (e == b) return;
-    const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
     if (!full) {
         bool any = false;
         for (int s = b + lane; s < e; s += 32) {

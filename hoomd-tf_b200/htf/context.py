@@ -71,6 +71,14 @@ class HtfContext:
         self._ck(self.lib.htf_set_cutoff(self._h, float(r_cut), int(nneighbor_cutoff)))
         self.r_cut, self.K = float(r_cut), int(nneighbor_cutoff)
 
+    def set_roi(self, center=None, half_width=None):
+        """Bin only particles within ``half_width`` (per axis, minimum image) of ``center``; None switches it off."""
+        if center is None:
+            self._ck(self.lib.htf_set_roi(self._h, None, None))
+            return
+        a3 = ctypes.c_float * 3
+        self._ck(self.lib.htf_set_roi(self._h, a3(*[float(x) for x in center]), a3(*[float(x) for x in half_width])))
+
     def set_mapped_nlist(self, map_type_start):
         self._ck(self.lib.htf_set_mapped_nlist(self._h, -1 if map_type_start is None else int(map_type_start)))
 

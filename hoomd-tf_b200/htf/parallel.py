@@ -55,3 +55,20 @@ def allreduce_scalar(x, group=None):
     t = x.detach().to(torch.float64).reshape(1).clone()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t[0]
+
+
+def roi_for_rows(pos_rows, box_lo, box_hi, r_cut, skin=0.4):
+    """Region of interest for ``HtfContext.set_roi``: per axis, the bounding interval of this rank's rows
+    widened by ``r_cut + skin``.  Axes whose widened interval covers the whole box get half-width -1 (no
+    restriction).  ``skin`` plays the role of HOOMD's ``r_buff``: the region stays valid until a local
+    particle has moved more than ``skin`` out of the interval it was computed for."""
+    import numpy as np
+    p = pos_rows.detach().cpu().numpy() if torch.is_tensor(pos_rows) else np.asarray(pos_rows)
+    lo = np.asarray(box_lo, dtype=np.float64)
+    L = np.asarray(box_hi, dtype=np.float64) - lo
+    a = p[:, :3].min(axis=0).astype(np.float64)
+    b = p[:, :3].max(axis=0).astype(np.float64)
+    center = 0.5 * (a + b)
+    half = 0.5 * (b - a) + float(r_cut) + float(skin)
+    half = np.where(2.0 * half >= L, -1.0, half)
+    return center.astype(np.float32), half.astype(np.float32)

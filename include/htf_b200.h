@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 5
+#define HTF_ABI_VERSION 6
 int htf_abi_version(void);
 
 /*
@@ -84,6 +84,15 @@ int htf_set_mapped_nlist(htf_ctx *ctx, int map_type_start);
 /* Change r_cut / nneighbor_cutoff of an existing context (tfcompute.attach arguments,
  * htf/tensorflowcompute.py:38-39). */
 int htf_set_cutoff(htf_ctx *ctx, float r_cut, int k);
+
+/*
+ * Row sharding over GPUs: restrict the binning to the particles that can matter for this rank's rows.
+ * Only particles whose minimum-image distance from h_center is <= h_half_width on every axis are binned
+ * (h_half_width[a] < 0: no restriction on axis a; pass NULL, NULL to switch the region off).  The caller
+ * chooses the region as the bounding interval of its rows plus r_cut plus a skin, the role HOOMD's ghost
+ * layer width plays under MPI domain decomposition (htf/test-py/test_mpi_tensorflow.py:59-80).
+ */
+int htf_set_roi(htf_ctx *ctx, const float h_center[3], const float h_half_width[3]);
 
 /*
  * Replaces HOOMD's NeighborList::compute (called at htf/TensorflowCompute.cc:163) for this

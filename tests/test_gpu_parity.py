@@ -303,3 +303,25 @@ def test_box_with_origin_at_zero(oracle_mod):
     pos2[:, :3] += shift.astype(np.float32)
     lo2, hi2 = np.zeros(3, np.float32), (hi - lo).astype(np.float32)
     check_nlist_case(oracle_mod, pos2, lo2, hi2, 2.5, 64, cells=False)
+
+
+def test_sharded_build_with_region_of_interest(oracle_mod):
+    """row sharding as bench.py --gpus N does it: a z-slab of rows, binning restricted to the slab +- (r_cut+skin);
+    the rows must be bit-identical to the same rows of the unrestricted build, for every slab incl. the periodic ones."""
+    from htf import synthetic, parallel
+    pos, lo, hi = synthetic.lattice_fluid((12, 12, 48), 0.7, seed=17)        # z-slowest order: a row range is a z-slab
+    n, K, r_cut = pos.shape[0], 64, 2.5
+    ctx = _ctx(n, K, r_cut, lo, hi)
+    dpos = torch.from_numpy(pos).cuda()
+    full, idx_full = ctx.build_nlist(dpos, want_idx=True)
+    world = 4
+    for rank in range(world):
+        a, b = parallel.row_shard(n, world, rank)
+        c, h = parallel.roi_for_rows(pos[a:b], lo, hi, r_cut)
+        assert h[2] > 0 and h[0] < 0 and h[1] < 0                             # only z is restricted
+        ctx.set_roi(c, h)
+        part, idx_part = ctx.build_nlist(dpos, a, b, want_idx=True)
+        assert torch.equal(part, full[a:b]) and torch.equal(idx_part, idx_full[a:b])
+    ctx.set_roi(None)
+    again = ctx.build_nlist(dpos)
+    assert torch.equal(again, full)
