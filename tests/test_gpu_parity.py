@@ -307,13 +307,16 @@ def test_box_with_origin_at_zero(oracle_mod):
 
 def test_sharded_build_with_region_of_interest(oracle_mod):
     """row sharding as bench.py --gpus N does it: a z-slab of rows, binning restricted to the slab +- (r_cut+skin);
-    the rows must be bit-identical to the same rows of the unrestricted build, for every slab incl. the periodic ones."""
+    the rows must hold bit-identical neighbor sets to the same rows of the unrestricted build (slot order may differ:
+    it follows the staged candidate order, and boundary cells are only partially binned), for every slab incl. the
+    periodic ones."""
     from htf import synthetic, parallel
     pos, lo, hi = synthetic.lattice_fluid((12, 12, 48), 0.7, seed=17)        # z-slowest order: a row range is a z-slab
     n, K, r_cut = pos.shape[0], 64, 2.5
     ctx = _ctx(n, K, r_cut, lo, hi)
     dpos = torch.from_numpy(pos).cuda()
     full, idx_full = ctx.build_nlist(dpos, want_idx=True)
+    full_s, idx_full_s = sort_rows(full.cpu().numpy(), idx_full.cpu().numpy())
     world = 4
     for rank in range(world):
         a, b = parallel.row_shard(n, world, rank)
@@ -321,7 +324,9 @@ def test_sharded_build_with_region_of_interest(oracle_mod):
         assert h[2] > 0 and h[0] < 0 and h[1] < 0                             # only z is restricted
         ctx.set_roi(c, h)
         part, idx_part = ctx.build_nlist(dpos, a, b, want_idx=True)
-        assert torch.equal(part, full[a:b]) and torch.equal(idx_part, idx_full[a:b])
+        part_s, idx_part_s = sort_rows(part.cpu().numpy(), idx_part.cpu().numpy())
+        assert np.array_equal(idx_part_s, idx_full_s[a:b])
+        assert np.array_equal(part_s.view(np.uint32), full_s[a:b].view(np.uint32))
     ctx.set_roi(None)
     again = ctx.build_nlist(dpos)
     assert torch.equal(again, full)
