@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
+                    help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -180,7 +182,8 @@ def cfg_dict(args, n, K, r_cut, world):
     return {"workload": "lj_fluid_%s%s" % (args.workload, "+rdf100" if args.rdf else ""),
             "particles": n, "particles_per_gpu": n // world, "nneighbor_cutoff": K, "r_cut": r_cut,
             "model": "LJ (nlist_rinv closed form) + 6-component virial",
-            "sharding": "particle rows, positions all-gathered per step" if world > 1 else "single GPU",
+            "sharding": ("particle rows (z-slabs), %s per step" % ("halo exchange of the two slab faces"
+                         if args.exchange == "halo" else "all-gather of all positions")) if world > 1 else "single GPU",
             "l2": "per-GPU working set %.0f MiB/step > 126 MB L2, no flush needed" % (n // world * K * 16 / 2 ** 20)}
 
 
@@ -214,8 +217,19 @@ def run_b200(args):
     if world > 1:
         # bin only what can matter for this rank's rows (slab +- (r_cut + skin)), like HOOMD's ghost layer
         ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
-    d_pos_all = torch.from_numpy(pos).to(dev)
-    d_shard = d_pos_all[row_lo:row_hi].clone()
+    halo = world > 1 and args.exchange == "halo"
+    if halo:
+        # rows are z-slabs (the generator's particle order is z-slowest): exchange only the two faces
+        lo_face, hi_face, width, cap_h = htf.parallel.slab_plan(pos[row_lo:row_hi], 2, r_cut)
+        t = torch.tensor([cap_h], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        xch = htf.parallel.SlabExchange(ctx, rows, 2, lo_face, hi_face, width, int(t.item()))
+        xch.own.copy_(torch.from_numpy(pos[row_lo:row_hi]).to(dev))
+        d_pos_all, d_shard = xch.local, xch.own
+        row_lo, row_hi = 0, rows                     # local indexing: own rows come first
+    else:
+        d_pos_all = torch.from_numpy(pos).to(dev)
+        d_shard = d_pos_all[row_lo:row_hi].clone()
     nl = torch.empty((rows, K, 4), dtype=torch.float32, device=dev)
     fe = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     vir = torch.empty((rows, 6), dtype=torch.float32, device=dev)
@@ -223,8 +237,10 @@ def run_b200(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):
-        if world > 1:
-            dist.all_gather_into_tensor(d_pos_all, d_shard)           # the path's one exchange step
+        if halo:
+            xch.exchange()                                            # the path's one exchange step (2 faces)
+        elif world > 1:
+            dist.all_gather_into_tensor(d_pos_all, d_shard)           # ... or every position
         ctx.bin_particles(d_pos_all)
         if marks is not None:
             marks[0].record()

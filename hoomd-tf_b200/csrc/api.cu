@@ -74,6 +74,25 @@ int ensure_cells(htf_ctx *ctx, int ncell)
     return HTF_OK;
 }
 
+// Cell layers in z that the region of interest can touch (+ one layer of slack on both sides).
+void update_z_window(htf_ctx *ctx)
+{
+    CellGrid &g = ctx->grid;
+    g.z0 = 0;
+    g.zcount = g.n[2];
+    if (!(g.roi_h[2] >= 0.0f) || g.n[2] < 1) return;
+    const double w = (double)g.L[2] / (double)g.n[2];
+    const double a = (double)g.roi_c[2] - (double)g.roi_h[2] - (double)g.lo[2];
+    const double b = (double)g.roi_c[2] + (double)g.roi_h[2] - (double)g.lo[2];
+    long long la = (long long)std::floor(a / w) - 1, lb = (long long)std::floor(b / w) + 1;
+    long long cnt = lb - la + 1;
+    if (cnt >= g.n[2]) return;
+    long long z0 = la % g.n[2];
+    if (z0 < 0) z0 += g.n[2];
+    g.z0 = (int)z0;
+    g.zcount = (int)cnt;
+}
+
 // Cell grid for the current box and cutoff.  Any cell edge >= r_cut is correct; the edge
 // is kept 1e-4 above r_cut (see CellGrid) and the cell count is capped so that a huge,
 // nearly empty box (e.g. compute_pairwise's 1e10 box) cannot exhaust memory.
@@ -103,6 +122,7 @@ int make_grid(htf_ctx *ctx)
         g.ncell *= g.n[a];
     }
     ctx->binned = false;
+    update_z_window(ctx);
     return ensure_cells(ctx, g.ncell);
 }
 
@@ -136,6 +156,7 @@ cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles)
 {
     if (ntiles <= ctx->tile_flag_cap) return cudaSuccess;
     if (ctx->d_tile_flag) cudaFree(ctx->d_tile_flag);
+    cudaFree(ctx->d_sel_cnt); cudaFree(ctx->d_sel_off); cudaFree(ctx->d_sel_sums);
     ctx->d_tile_flag = nullptr;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_tile_flag), (size_t)ntiles);
     if (e == cudaSuccess) ctx->tile_flag_cap = ntiles;
@@ -221,6 +242,7 @@ void htf_destroy(htf_ctx *ctx)
     cudaFree(ctx->d_cell_cnt); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_block_sums);
     cudaFree(ctx->d_cell_of); cudaFree(ctx->d_sorted_idx); cudaFree(ctx->d_spos);
     cudaFree(ctx->d_nlist_scratch); cudaFree(ctx->d_rdf_thr); cudaFree(ctx->d_tile_flag);
+    cudaFree(ctx->d_sel_cnt); cudaFree(ctx->d_sel_off); cudaFree(ctx->d_sel_sums);
     delete ctx;
 }
 
@@ -255,6 +277,30 @@ int htf_set_roi(htf_ctx *ctx, const float h_center[3], const float h_half_width[
         ctx->grid.roi_h[a] = (h_center && h_half_width) ? h_half_width[a] : -1.0f;
     }
     ctx->binned = false;
+    if (ctx->box_set) update_z_window(ctx);
+    return HTF_OK;
+}
+
+int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold, int below,
+                  float *d_out, int64_t capacity, int32_t *d_count, int32_t *d_overflow, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n < 0 || n > 2000000000LL || capacity < 1 || capacity > 2000000000LL || axis < 0 || axis > 2 || !d_out ||
+        (n > 0 && !d_pos)) {
+        set_err(ctx, "htf_pack_halo: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    const int64_t nb = (n + 255) / 256 + 1;
+    if (nb > ctx->sel_cap) {
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_cnt, (size_t)nb))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_off, (size_t)nb))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_sums, (size_t)nb / 1024 + 4))) return rc;
+        ctx->sel_cap = nb;
+    }
+    HTF_CUDA(ctx, htf_launch_select(ctx, reinterpret_cast<const float4 *>(d_pos), n, axis, threshold, below != 0,
+                                    reinterpret_cast<float4 *>(d_out), (int)capacity, d_count, d_overflow,
+                                    (cudaStream_t)stream));
     return HTF_OK;
 }
 

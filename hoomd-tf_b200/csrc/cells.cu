@@ -150,13 +150,16 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict
 // neighbor tensor -- and therefore every fp32 force sum -- reproducible run to run.
 template <bool SORT>
 __global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__restrict__ pos,
-                                                                const int *__restrict__ cell_start, int ncell,
+                                                                const int *__restrict__ cell_start, int ncell_win,
+                                                                int layer, int z0, int nz,
                                                                 int *__restrict__ sorted_idx,
                                                                 float4 *__restrict__ spos)
 {
     const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= ncell) return;
+    const int cw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // cell inside the z-window
+    if (cw >= ncell_win) return;
+    const int lz = cw / layer;
+    const int c = ((z0 + lz) % nz) * layer + (cw - lz * layer);
     const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
     const int n = e - b;
     if (n == 0) return;
@@ -198,6 +201,63 @@ __global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__
     for (int s = b + lane; s < e; s += 32) spos[s] = __ldg(pos + sorted_idx[s]);
 }
 
+// ---- stable selection of the particles beyond a plane (halo packing for the slab exchange) ----
+// out[k] = k-th particle (in index order) with pos[axis] < thr (LESS) or > thr; the rest of out[0..cap)
+// is filled with a far-away sentinel that the region-of-interest test of the binning rejects.
+template <bool LESS>
+__device__ __forceinline__ bool beyond(const float4 &p, int axis, float thr)
+{
+    const float v = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    return LESS ? v < thr : v > thr;
+}
+
+template <bool LESS>
+__global__ void __launch_bounds__(256) select_count_kernel(const float4 *__restrict__ pos, int n, int axis, float thr,
+                                                           int *__restrict__ block_cnt)
+{
+    __shared__ int wsum[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool sel = i < n && beyond<LESS>(__ldg(pos + i), axis, thr);
+    const unsigned m = __ballot_sync(HTF_FULL, sel);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        block_cnt[blockIdx.x] = t;
+    }
+}
+
+template <bool LESS>
+__global__ void __launch_bounds__(256) select_scatter_kernel(const float4 *__restrict__ pos, int n, int axis, float thr,
+                                                             const int *__restrict__ block_off, float4 *__restrict__ out,
+                                                             int cap, int *__restrict__ overflow)
+{
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) p = __ldg(pos + i);
+    const bool sel = i < n && beyond<LESS>(p, axis, thr);
+    const unsigned m = __ballot_sync(HTF_FULL, sel);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int base = block_off[blockIdx.x];
+    for (int q = 0; q < w; q++) base += wsum[q];
+    const int k = base + __popc(m & ((1u << lane) - 1u));
+    if (sel) {
+        if (k < cap) out[k] = p;
+        else if (overflow) atomicMax(overflow, k + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_sentinel_kernel(float4 *__restrict__ out, int cap)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < cap) out[i] = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+}
+
 }  // namespace
 
 cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cudaStream_t st)
@@ -218,11 +278,37 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
     cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_sorted_idx);
-    const int cb = (ncell + 7) / 8;
+    const int layer = g.n[0] * g.n[1];
+    const int ncell_win = layer * g.zcount;                     // only the cell layers the region of interest touches
+    const int cb = (ncell_win + 7) / 8;
     if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */)
-        cell_order_gather_kernel<true><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell, ctx->d_sorted_idx, ctx->d_spos);
+        cell_order_gather_kernel<true><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
+                                                           ctx->d_sorted_idx, ctx->d_spos);
     else
-        cell_order_gather_kernel<false><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell, ctx->d_sorted_idx, ctx->d_spos);
+        cell_order_gather_kernel<false><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
+                                                            ctx->d_sorted_idx, ctx->d_spos);
     ctx->launches += 6;
+    return cudaGetLastError();
+}
+
+
+cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n64, int axis, float thr, bool less,
+                              float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st)
+{
+    const int n = (int)n64;
+    fill_sentinel_kernel<<<(cap + 255) / 256, 256, 0, st>>>(out, cap);
+    ctx->launches += 1;
+    if (n == 0) return d_count ? cudaMemsetAsync(d_count, 0, sizeof(int), st) : cudaGetLastError();
+    const int nb = (n + 255) / 256;
+    int *cnt = ctx->d_sel_cnt, *off = ctx->d_sel_off, *sums = ctx->d_sel_sums;
+    if (less) select_count_kernel<true><<<nb, 256, 0, st>>>(pos, n, axis, thr, cnt);
+    else select_count_kernel<false><<<nb, 256, 0, st>>>(pos, n, axis, thr, cnt);
+    const int ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, nb, sums);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, ntiles, d_count ? d_count : sums + ntiles + 1);
+    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, nb, sums, off);
+    if (less) select_scatter_kernel<true><<<nb, 256, 0, st>>>(pos, n, axis, thr, off, out, cap, d_overflow);
+    else select_scatter_kernel<false><<<nb, 256, 0, st>>>(pos, n, axis, thr, off, out, cap, d_overflow);
+    ctx->launches += 5;
     return cudaGetLastError();
 }

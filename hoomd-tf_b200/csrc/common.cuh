@@ -19,6 +19,9 @@ struct CellGrid {
     // region of interest for binning (row sharding over GPUs): only particles whose minimum-image distance
     // from roi_c is <= roi_h on every axis are binned; roi_h < 0 disables the test on that axis
     float roi_c[3], roi_h[3];
+    // z-window of cell layers that can hold binned particles: layers (z0 + i) % n[2], i < zcount
+    // (the whole grid when the region of interest does not restrict z)
+    int z0, zcount;
 };
 
 struct htf_ctx {
@@ -42,6 +45,8 @@ struct htf_ctx {
     int *d_sorted_idx;    // [n_cap] cell-sorted slot -> particle index
     float4 *d_spos;       // [n_cap] cell-sorted positions
     int64_t n_cap;
+    int *d_sel_cnt, *d_sel_off, *d_sel_sums;   // halo selection scratch (per 256-particle block)
+    int64_t sel_cap;
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
     int tile_flag_cap;
     float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
@@ -69,6 +74,8 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
                            unsigned long long *bins, cudaStream_t st);
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
+cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,
+                              float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st);
 
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -558,13 +558,19 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     if (!p.use_flags) {
-        const int cell = blockIdx.x * wpb + warp;
-        if (cell < p.g.ncell) build_cell<WITH_IDX, MAPPED>(p, cell, smem_raw);
+        const int cw = blockIdx.x * wpb + warp, layer = p.g.n[0] * p.g.n[1];
+        if (cw < layer * p.g.zcount) {
+            const int lz = cw / layer;
+            build_cell<WITH_IDX, MAPPED>(p, ((p.g.z0 + lz) % p.g.n[2]) * layer + (cw - lz * layer), smem_raw);
+        }
         return;
     }
     const int nx = p.g.n[0], tiles_x = (nx + TILE - 1) / TILE;
-    const int ntiles = tiles_x * p.g.n[1] * p.g.n[2];
-    for (int tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
+    const int per_layer = tiles_x * p.g.n[1];
+    const int ntiles_win = per_layer * p.g.zcount;                  // tiles of the z-window only
+    for (int tw = blockIdx.x * wpb + warp; tw < ntiles_win; tw += gridDim.x * wpb) {
+        const int lz = tw / per_layer;
+        const int tile = ((p.g.z0 + lz) % p.g.n[2]) * per_layer + (tw - lz * per_layer);
         if (!p.tile_flag[tile]) continue;
         const int tx = tile % tiles_x, row = tile / tiles_x;        // row = cz * ny + cy
         for (int c = 0; c < TILE && tx * TILE + c < nx; c++) build_cell<WITH_IDX, MAPPED>(p, row * nx + tx * TILE + c, smem_raw);
@@ -601,7 +607,8 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
 
     const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
     const int tiles_x = gridDim.x;                              // = ceil(nx / TILE)
-    const int tx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+    const int tx = blockIdx.x, cy = blockIdx.y;
+    const int cz = (p.g.z0 + (int)blockIdx.z) % nz;            // grid.z = cell layers of the z-window
     const int bid = (cz * ny + cy) * tiles_x + tx;
     const int cx0 = tx * TILE;
     const int nact = min(TILE, nx - cx0);                       // cells of this tile
@@ -901,7 +908,7 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             p.cap_tile = capB;
             p.tile_flag = ctx->d_tile_flag;
             ctx->launches += 1;
-            const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)g.n[2]);
+            const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)g.zcount);
             e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, tg, bytes, st)
                                    : launch_tile_variant<true, false>(p, tg, bytes, st))
                          : (mapped ? launch_tile_variant<false, true>(p, tg, bytes, st)
@@ -924,8 +931,8 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     }
     p.cap = cap;
     const size_t smem = per_warp_bytes(cap, p.K, with_idx) * wpb;
-    int grid = (g.ncell + wpb - 1) / wpb;
-    if (tiled) grid = min((ntiles + wpb - 1) / wpb, 2 * ctx->sm_count);    // persistent scan of the tile flags
+    int grid = (g.n[0] * g.n[1] * g.zcount + wpb - 1) / wpb;
+    if (tiled) grid = min((tiles_x * g.n[1] * g.zcount + wpb - 1) / wpb, 2 * ctx->sm_count);   // persistent flag scan
     ctx->launches += 1;
     if (with_idx) return mapped ? launch_variant<true, true>(p, grid, wpb, smem, st)
                                 : launch_variant<true, false>(p, grid, wpb, smem, st);

@@ -79,6 +79,14 @@ class HtfContext:
         a3 = ctypes.c_float * 3
         self._ck(self.lib.htf_set_roi(self._h, a3(*[float(x) for x in center]), a3(*[float(x) for x in half_width])))
 
+    def pack_halo(self, pos, axis, threshold, below, out, count=None):
+        """Stable copy of the particles beyond a plane into the fixed-capacity buffer ``out`` (sentinel padded)."""
+        _check_dev_f32(pos, "positions", 4)
+        _check_dev_f32(out, "halo buffer", 4)
+        self._ck(self.lib.htf_pack_halo(self._h, _ptr(pos), pos.shape[0], int(axis), float(threshold), int(bool(below)),
+                                        _ptr(out), out.shape[0], _ptr(count), _ptr(self._overflow), self._stream()))
+        return out
+
     def set_mapped_nlist(self, map_type_start):
         self._ck(self.lib.htf_set_mapped_nlist(self._h, -1 if map_type_start is None else int(map_type_start)))
 

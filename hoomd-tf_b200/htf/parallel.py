@@ -72,3 +72,61 @@ def roi_for_rows(pos_rows, box_lo, box_hi, r_cut, skin=0.4):
     half = 0.5 * (b - a) + float(r_cut) + float(skin)
     half = np.where(2.0 * half >= L, -1.0, half)
     return center.astype(np.float32), half.astype(np.float32)
+
+
+class SlabExchange:
+    """Halo exchange for row shards that are slabs along one axis (particles spatially sorted along it).
+
+    Instead of all-gathering every position (16 B x N_total per rank and step), each rank sends the particles
+    within ``width = r_cut + skin`` of its two slab faces to the two neighbouring ranks (periodic) and bins
+    ``[own rows | halo from below | halo from above]``.  The buffers have a fixed capacity; unused entries
+    carry a sentinel that the region-of-interest test of the binning rejects, so no count ever has to reach the
+    host.  ``libhtf_b200`` packs the halos (stable, index order); NCCL send/recv moves them.
+    """
+
+    def __init__(self, ctx, n_local, axis, lo_face, hi_face, width, capacity, group=None):
+        self.ctx, self.n_local, self.axis, self.cap = ctx, int(n_local), int(axis), int(capacity)
+        self.lo_thr, self.hi_thr = float(lo_face) + float(width), float(hi_face) - float(width)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = ctx.device
+        extra = 2 * self.cap if self.world > 1 else 0
+        self.local = torch.empty((self.n_local + extra, 4), dtype=torch.float32, device=dev)
+        self.send_lo = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
+        self.send_hi = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
+
+    @property
+    def own(self):
+        """View of this rank's rows inside the local array (write the shard's positions here)."""
+        return self.local[:self.n_local]
+
+    def exchange(self):
+        """Pack both faces, swap with the neighbours, return the local array ``[own | halo | halo]``."""
+        if self.world == 1:
+            return self.local
+        own = self.own
+        self.ctx.pack_halo(own, self.axis, self.lo_thr, True, self.send_lo)
+        self.ctx.pack_halo(own, self.axis, self.hi_thr, False, self.send_hi)
+        prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        a = self.local[self.n_local:self.n_local + self.cap]
+        b = self.local[self.n_local + self.cap:]
+        ops = [dist.P2POp(dist.isend, self.send_lo, prev, self.group), dist.P2POp(dist.isend, self.send_hi, nxt, self.group),
+               dist.P2POp(dist.irecv, a, nxt, self.group), dist.P2POp(dist.irecv, b, prev, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return self.local
+
+
+def slab_plan(pos_rows, axis, r_cut, skin=0.4, slack=1.5):
+    """(lo_face, hi_face, width, capacity) of a slab shard from its current positions (host side, at set-up or
+    whenever the region of interest is refreshed)."""
+    import numpy as np
+    p = pos_rows.detach().cpu().numpy() if torch.is_tensor(pos_rows) else np.asarray(pos_rows)
+    x = p[:, axis]
+    lo_face, hi_face = float(x.min()), float(x.max())
+    width = float(r_cut) + float(skin)
+    n_lo = int((x < lo_face + width).sum())
+    n_hi = int((x > hi_face - width).sum())
+    cap = int(max(n_lo, n_hi) * slack) + 256
+    return lo_face, hi_face, width, (cap + 255) // 256 * 256

@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 6
+#define HTF_ABI_VERSION 7
 int htf_abi_version(void);
 
 /*
@@ -93,6 +93,17 @@ int htf_set_cutoff(htf_ctx *ctx, float r_cut, int k);
  * layer width plays under MPI domain decomposition (htf/test-py/test_mpi_tensorflow.py:59-80).
  */
 int htf_set_roi(htf_ctx *ctx, const float h_center[3], const float h_half_width[3]);
+
+/*
+ * Slab (halo) exchange between row shards: copies, in index order, every particle of d_pos[n] whose
+ * coordinate on `axis` is < threshold (below != 0) or > threshold (below == 0) into d_out[capacity][4];
+ * unused entries are set to a far-away sentinel that the region of interest rejects, so the buffer can be
+ * sent to the neighbouring rank and appended to its positions as is.  d_count (nullable) receives the number
+ * selected, d_overflow (nullable) is max'ed with it when it exceeds capacity.  This is the role of HOOMD's
+ * ghost-particle exchange under MPI (htf/test-py/test_mpi_tensorflow.py:59-80); the reference has no code for it.
+ */
+int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold, int below,
+                  float *d_out, int64_t capacity, int32_t *d_count, int32_t *d_overflow, void *stream);
 
 /*
  * Replaces HOOMD's NeighborList::compute (called at htf/TensorflowCompute.cc:163) for this

@@ -330,3 +330,50 @@ def test_sharded_build_with_region_of_interest(oracle_mod):
     ctx.set_roi(None)
     again = ctx.build_nlist(dpos)
     assert torch.equal(again, full)
+
+
+def test_slab_halo_exchange_emulated(oracle_mod):
+    """the halo path of bench.py --gpus N, emulated on one GPU: every 'rank' packs its two faces with htf_pack_halo,
+    receives its neighbours' buffers, bins [own | halo | halo] inside its region of interest and builds its rows.
+    The (dx,dy,dz,type) multisets must equal the rows of the global build bit for bit."""
+    from htf import synthetic, parallel
+    import htf
+    pos, lo, hi = synthetic.lattice_fluid((10, 10, 48), 0.7, seed=19)
+    n, K, r_cut = pos.shape[0], 64, 2.5
+    ctx = _ctx(n, K, r_cut, lo, hi)
+    full = ctx.build_nlist(torch.from_numpy(pos).cuda()).cpu().numpy()
+
+    def canon(nl):           # sort each row lexicographically by (dx,dy,dz,type) bit patterns
+        v = nl.view(np.uint32).astype(np.uint64)
+        key = (v[..., 0] << 32) | v[..., 1]
+        key2 = (v[..., 2] << 32) | v[..., 3]
+        order = np.lexsort((key2, key), axis=1)
+        return np.take_along_axis(nl, order[:, :, None], axis=1)
+
+    world = 4
+    shards = [parallel.row_shard(n, world, r) for r in range(world)]
+    plans = [parallel.slab_plan(pos[a:b], 2, r_cut) for a, b in shards]
+    cap = max(p_[3] for p_ in plans)
+    ctxs, sends = [], []
+    for r, (a, b) in enumerate(shards):
+        c = htf.HtfContext(b - a + 2 * cap, K, r_cut)
+        c.set_box(lo, hi)
+        c.set_roi(*parallel.roi_for_rows(pos[a:b], lo, hi, r_cut))
+        own = torch.from_numpy(pos[a:b].copy()).cuda()
+        lo_face, hi_face, width, _ = plans[r]
+        s_lo = c.pack_halo(own, 2, lo_face + width, True, torch.empty((cap, 4), device="cuda"))
+        s_hi = c.pack_halo(own, 2, hi_face - width, False, torch.empty((cap, 4), device="cuda"))
+        assert c.overflow() == 0
+        ctxs.append((c, own)); sends.append((s_lo, s_hi))
+    # stable packing: the selected particles appear in index order, the rest is sentinel
+    s_lo0 = sends[0][0].cpu().numpy()
+    a0, b0 = shards[0]
+    want = pos[a0:b0][pos[a0:b0, 2] < plans[0][0] + plans[0][2]]
+    assert np.array_equal(s_lo0[:len(want)], want) and np.all(s_lo0[len(want):, 0] > 1e29)
+    for r, (a, b) in enumerate(shards):
+        c, own = ctxs[r]
+        prev, nxt = (r - 1) % world, (r + 1) % world
+        local = torch.cat([own, sends[nxt][0], sends[prev][1]], dim=0).contiguous()
+        nl = c.build_nlist(local, 0, b - a)
+        assert c.overflow() == 0
+        assert np.array_equal(canon(nl.cpu().numpy()).view(np.uint32), canon(full[a:b]).view(np.uint32)), r
