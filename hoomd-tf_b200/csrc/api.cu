@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -122,6 +123,7 @@ int make_grid(htf_ctx *ctx)
         g.ncell *= g.n[a];
     }
     ctx->binned = false;
+    ctx->calib_valid = false;
     update_z_window(ctx);
     return ensure_cells(ctx, g.ncell);
 }
@@ -156,7 +158,6 @@ cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles)
 {
     if (ntiles <= ctx->tile_flag_cap) return cudaSuccess;
     if (ctx->d_tile_flag) cudaFree(ctx->d_tile_flag);
-    cudaFree(ctx->d_sel_cnt); cudaFree(ctx->d_sel_off); cudaFree(ctx->d_sel_sums);
     ctx->d_tile_flag = nullptr;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_tile_flag), (size_t)ntiles);
     if (e == cudaSuccess) ctx->tile_flag_cap = ntiles;
@@ -230,6 +231,7 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     for (int a = 0; a < 3; a++) ctx->grid.roi_h[a] = -1.0f;
     DeviceGuard guard(device);
     int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
+    if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 4);
     if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
     *out = ctx;
     return HTF_OK;
@@ -239,10 +241,16 @@ void htf_destroy(htf_ctx *ctx)
 {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    cudaFree(ctx->d_cell_cnt); cudaFree(ctx->d_cell_start); cudaFree(ctx->d_block_sums);
-    cudaFree(ctx->d_cell_of); cudaFree(ctx->d_sorted_idx); cudaFree(ctx->d_spos);
-    cudaFree(ctx->d_nlist_scratch); cudaFree(ctx->d_rdf_thr); cudaFree(ctx->d_tile_flag);
-    cudaFree(ctx->d_sel_cnt); cudaFree(ctx->d_sel_off); cudaFree(ctx->d_sel_sums);
+    void *ptrs[] = {ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx,
+                    ctx->d_spos, ctx->d_nlist_scratch, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
+                    ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
+        if (!ptrs[i]) continue;
+        cudaError_t e = cudaFree(ptrs[i]);
+        if (e != cudaSuccess && getenv("HTF_DEBUG"))
+            fprintf(stderr, "htf_destroy: cudaFree #%zu %p: %s\n", i, ptrs[i], cudaGetErrorString(e));
+    }
+    (void)cudaGetLastError();       // never leave a sticky error behind for the next context
     delete ctx;
 }
 
@@ -277,6 +285,7 @@ int htf_set_roi(htf_ctx *ctx, const float h_center[3], const float h_half_width[
         ctx->grid.roi_h[a] = (h_center && h_half_width) ? h_half_width[a] : -1.0f;
     }
     ctx->binned = false;
+    ctx->calib_valid = false;
     if (ctx->box_set) update_z_window(ctx);
     return HTF_OK;
 }

@@ -201,6 +201,26 @@ __global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__
     for (int s = b + lane; s < e; s += 32) spos[s] = __ldg(pos + sorted_idx[s]);
 }
 
+// ---- cell population statistics (calibrates the staging capacities of the build kernels) ----
+// stats[0] = particles binned, stats[1] = occupied cells, stats[2] = largest cell population
+__global__ void __launch_bounds__(256) cell_stats_kernel(const int *__restrict__ cell_start, int ncell,
+                                                         int *__restrict__ stats)
+{
+    int occ = 0, mx = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        const int n = cell_start[c + 1] - cell_start[c];
+        occ += n > 0;
+        mx = max(mx, n);
+    }
+    occ = __reduce_add_sync(HTF_FULL, occ);
+    mx = __reduce_max_sync(HTF_FULL, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 1, occ);
+        atomicMax(stats + 2, mx);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[0] = cell_start[ncell];
+}
+
 // ---- stable selection of the particles beyond a plane (halo packing for the slab exchange) ----
 // out[k] = k-th particle (in index order) with pos[axis] < thr (LESS) or > thr; the rest of out[0..cap)
 // is filled with a far-away sentinel that the region-of-interest test of the binning rejects.
@@ -311,4 +331,19 @@ cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n64, int 
     else select_scatter_kernel<false><<<nb, 256, 0, st>>>(pos, n, axis, thr, off, out, cap, d_overflow);
     ctx->launches += 5;
     return cudaGetLastError();
+}
+
+
+// Synchronising (one cudaMemcpy): called by the nlist launcher only when the context has no valid
+// calibration for the current box / cutoff / region of interest / particle count.
+cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(ctx->d_stats, 0, 3 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int ncell = ctx->grid.ncell;
+    cell_stats_kernel<<<min((ncell + 255) / 256, 592), 256, 0, st>>>(ctx->d_cell_start, ncell, ctx->d_stats);
+    ctx->launches += 1;
+    e = cudaMemcpyAsync(h_stats, ctx->d_stats, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
 }

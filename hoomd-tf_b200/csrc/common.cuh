@@ -45,6 +45,10 @@ struct htf_ctx {
     int *d_sorted_idx;    // [n_cap] cell-sorted slot -> particle index
     float4 *d_spos;       // [n_cap] cell-sorted positions
     int64_t n_cap;
+    int *d_stats;                 // [3] cell population statistics (see htf_cell_stats)
+    bool calib_valid;             // staging capacities calibrated for the current configuration
+    int64_t calib_n;              // n_binned at calibration time
+    double calib_cell_mean;       // particles per occupied cell
     int *d_sel_cnt, *d_sel_off, *d_sel_sums;   // halo selection scratch (per 256-particle block)
     int64_t sel_cap;
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
@@ -74,6 +78,7 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
                            unsigned long long *bins, cudaStream_t st);
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
+cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st);
 cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,
                               float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st);
 

@@ -881,7 +881,23 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     // stencil population: mean + 5 sigma (Poisson) + slack, rounded to a chunk
     const CellGrid &g = ctx->grid;
     const int stencil = min(g.n[0], 3) * min(g.n[1], 3) * min(g.n[2], 3);
-    const double cell_mean = (double)ctx->n_binned / (double)g.ncell;
+    // particles per occupied cell.  With a region of interest (sharded builds) only part of the grid is
+    // populated, so the density is measured once per configuration (one small kernel + a synchronising
+    // 12-byte copy) instead of being derived from n / ncell; unrestricted builds need no calibration.
+    double cell_mean = (double)ctx->n_binned / (double)g.ncell;
+    const bool restricted = g.roi_h[0] >= 0.f || g.roi_h[1] >= 0.f || g.roi_h[2] >= 0.f;
+    if (restricted) {
+        const double drift = ctx->calib_n > 0 ? fabs((double)ctx->n_binned - (double)ctx->calib_n) / (double)ctx->calib_n : 1.0;
+        if (!ctx->calib_valid || drift > 0.05) {
+            int st3[3] = {0, 0, 0};
+            cudaError_t ce = htf_cell_stats(ctx, st3, st);
+            if (ce != cudaSuccess) return ce;
+            ctx->calib_cell_mean = st3[1] > 0 ? (double)st3[0] / (double)st3[1] : 1.0;
+            ctx->calib_n = ctx->n_binned;
+            ctx->calib_valid = true;
+        }
+        cell_mean = ctx->calib_cell_mean;
+    }
     const double mean = (double)stencil * cell_mean;
     int cap = (int)(mean + 5.0 * sqrt(mean > 1.0 ? mean : 1.0)) + 32;
     cap = (cap + 31) / 32 * 32;
