@@ -337,9 +337,11 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
     h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
     h_f = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
-    h_v = torch.empty((rows, 9), dtype=torch.float32).pin_memory()
+    h_v = torch.empty((rows, 6), dtype=torch.float32).pin_memory()
     d_shard = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     tfc.shard = (row_lo, row_hi)
+    if world > 1:
+        tfc.ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
 
     def step(t):
         d_shard.copy_(h_pos, non_blocking=True)
@@ -349,7 +351,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
             system.positions.copy_(d_shard)
         f = tfc.compute_forces(t)
         h_f.copy_(f[row_lo:row_hi], non_blocking=True)
-        h_v.copy_(tfc._virial[row_lo:row_hi], non_blocking=True)
+        h_v.copy_(tfc.virial6((row_lo, row_hi)), non_blocking=True)       # the 6 components HOOMD keeps
 
     steps = max(3, min(args.steps, 10))
     for t in range(3):

@@ -239,6 +239,12 @@ class tfcompute:
     def get_virial_array(self):
         return self._virial.detach().cpu().numpy().astype(np.float64).reshape((-1, 9))
 
+    def virial6(self, rows=None):
+        """Device tensor [rows, 6] = xx, xy, xz, yy, yz, zz: the six components HOOMD keeps of the 3x3 virial
+        (receiveVirial, htf/TensorflowCompute.cc:285-301)."""
+        v = self._virial if rows is None else self._virial[rows[0]:rows[1]]
+        return v[:, [0, 1, 2, 4, 5, 8]]
+
     def get_log_value(self):
         """HOOMD log quantity "tensorflow": the potential energy sum (htf/TensorflowCompute.cc:377-395)."""
         return float(self._forces[:, 3].sum().item())
