@@ -417,6 +417,33 @@ int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, f
     return HTF_OK;
 }
 
+int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float r0, float *d_force_energy,
+                     float *d_virial, int virial_components, float *d_cv_row, double *d_cv_sum, int64_t *d_bins,
+                     float r_lo, float r_hi, int nbins, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (rows < 0 || k < 1 || !(r0 > 0.0f) || !d_cv_sum || (rows > 0 && (!d_nlist || !d_force_energy || !d_cv_row))) {
+        set_err(ctx, "htf_lj_cv_forces: bad arguments"); return HTF_EINVAL;
+    }
+    if (d_virial && virial_components != 6 && virial_components != 9) {
+        set_err(ctx, "htf_lj_cv_forces: virial_components must be 6 or 9"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    const float *thr = nullptr;
+    int nb = 0;
+    if (d_bins) {
+        if (nbins + 2 > 1024) { set_err(ctx, "htf_lj_cv_forces: nbins must be <= 1022"); return HTF_EINVAL; }
+        if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, (cudaStream_t)stream))) return rc;
+        thr = ctx->d_rdf_thr; nb = nbins + 2;
+    }
+    HTF_CUDA(ctx, htf_launch_lj_cv(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
+                                   reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components, r0,
+                                   reinterpret_cast<float4 *>(d_cv_row), d_cv_sum, thr, nb,
+                                   reinterpret_cast<unsigned long long *>(d_bins), (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_row_type,
                  int64_t row_type_stride, float r_lo, float r_hi, int nbins, int type_i, int type_j,
                  int64_t *d_bins, void *stream)

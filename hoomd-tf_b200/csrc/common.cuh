@@ -82,5 +82,9 @@ cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st);
 cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,
                               float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st);
 
+cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
+                             int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
+                             unsigned long long *bins, cudaStream_t st);
+
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -44,9 +44,13 @@ struct PairParams {
     long long row_type_stride;
     int type_i, type_j;
     unsigned long long *bins;
+    // smooth coordination-number collective variable: s(r) = 1 / (1 + (r/r0)^6)
+    float cv_inv_r0;
+    float4 *cv_row;            // [rows]: (sum_j ds/dd_ij (x,y,z), sum_j s(r_ij))
+    double *cv_sum;            // += sum over rows of the coordination number
 };
 
-template <int LPR, bool FORCES, bool VIRIAL, bool RDF>
+template <int LPR, bool FORCES, bool VIRIAL, bool RDF, bool CV>
 __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams p)
 {
     extern __shared__ int s_hist[];             // RDF: [warps][nb] private histograms + thr copy
@@ -60,6 +64,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
     int *my_hist = nullptr;
     float *s_thr = nullptr;
     unsigned bin0 = 0;                          // lane-private count of bin 0 (padded slots land here)
+    double cv_acc = 0.0;                        // CV: coordination numbers of the rows this lane reported
     if (RDF) {
         my_hist = s_hist + warp * p.nb;
         s_thr = reinterpret_cast<float *>(s_hist + WARPS * p.nb);
@@ -75,6 +80,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
         const float4 *rp = p.nlist + (active ? row : 0) * K;
         float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
         float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
+        float cn = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
         bool row_in_rdf = false;
         if (RDF) {
             row_in_rdf = active;
@@ -111,6 +117,14 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                             const float wx = w * dx, wy = w * dy, wz = w * dz;
                             vxx += wx * dx; vxy += wx * dy; vxz += wx * dz;
                             vyy += wy * dy; vyz += wy * dz; vzz += wz * dz;
+                        }
+                        if (CV) {
+                            // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a
+                            const float x = rt * p.cv_inv_r0, x2 = x * x, x6 = x2 * x2 * x2;
+                            const float sw = 1.0f / (1.0f + x6);
+                            cn += sw;
+                            const float cg = -6.0f * x6 * sw * sw * irt * irt;
+                            gx += cg * ax; gy += cg * ay; gz += cg * az;
                         }
                     }
                 }
@@ -149,6 +163,19 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                 }
             }
             if (active && sub == 0) p.fe[row] = make_float4(fx, fy, fz, en);
+            if (CV) {
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) {
+                    cn += __shfl_xor_sync(HTF_FULL, cn, o);
+                    gx += __shfl_xor_sync(HTF_FULL, gx, o);
+                    gy += __shfl_xor_sync(HTF_FULL, gy, o);
+                    gz += __shfl_xor_sync(HTF_FULL, gz, o);
+                }
+                if (active && sub == 0) {
+                    p.cv_row[row] = make_float4(gx, gy, gz, cn);
+                    cv_acc += (double)cn;
+                }
+            }
             if (VIRIAL && active) {
                 if (p.vcomp == 6) {
                     // xx,xy,xz,yy,yz,zz  (htf/TensorflowCompute.cc:294-299)
@@ -167,6 +194,11 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
             }
         }
     }
+    if (CV) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cv_acc += __shfl_xor_sync(HTF_FULL, cv_acc, o);
+        if (lane == 0 && cv_acc != 0.0) atomicAdd(p.cv_sum, cv_acc);
+    }
     if (RDF) {
         // bin 0 holds every padded slot: reduce it in registers, one shared atomic per warp
 #pragma unroll
@@ -182,7 +214,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
     }
 }
 
-template <bool FORCES, bool VIRIAL, bool RDF>
+template <bool FORCES, bool VIRIAL, bool RDF, bool CV = false>
 cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 {
     // lanes per row: 8 keeps every warp request on whole 128-byte lines; small K uses fewer
@@ -194,13 +226,13 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
     const long long blocks_needed = (groups + LJ_THREADS / 32 - 1) / (LJ_THREADS / 32);
     long long grid = blocks_needed;
     const long long persistent = (long long)ctx->sm_count * 8;     // 8 x 256 threads = full occupancy
-    if (RDF && grid > persistent) grid = persistent;               // fewer histogram flushes
+    if ((RDF || CV) && grid > persistent) grid = persistent;       // fewer histogram / CV flushes
     if (grid < 1) grid = 1;
     switch (lpr) {
-    case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    case 4: pair_pass_kernel<4, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    case 2: pair_pass_kernel<2, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    default: pair_pass_kernel<1, FORCES, VIRIAL, RDF><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 4: pair_pass_kernel<4, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 2: pair_pass_kernel<2, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    default: pair_pass_kernel<1, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
     }
     ctx->launches += 1;
     return cudaGetLastError();
@@ -218,6 +250,7 @@ cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
     p.row_type = row_type; p.row_type_stride = row_type_stride; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    p.cv_inv_r0 = 0.f; p.cv_row = nullptr; p.cv_sum = nullptr;
     const bool rdf = bins != nullptr;
     if (rdf && nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
     if (virial) return rdf ? launch_pair<true, true, true>(ctx, p, st) : launch_pair<true, true, false>(ctx, p, st);
@@ -235,5 +268,24 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     p.thr = thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
     p.row_type = row_type; p.row_type_stride = row_type_stride; p.type_i = type_i; p.type_j = type_j; p.bins = bins;
+    p.cv_inv_r0 = 0.f; p.cv_row = nullptr; p.cv_sum = nullptr;
     return launch_pair<false, false, true>(ctx, p, st);
+}
+
+
+// LJ forces + virial + smooth coordination CV (+ RDF) in one pass: the EDS-biased model of BASELINE config 5
+cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
+                             int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
+                             unsigned long long *bins, cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    PairParams p;
+    p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
+    p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
+    p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
+    p.row_type = nullptr; p.row_type_stride = 0; p.type_i = -1; p.type_j = -1; p.bins = bins;
+    p.cv_inv_r0 = 1.0f / r0; p.cv_row = cv_row; p.cv_sum = cv_sum;
+    if (bins && nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
+    if (virial) return bins ? launch_pair<true, true, true, true>(ctx, p, st) : launch_pair<true, true, false, true>(ctx, p, st);
+    return bins ? launch_pair<true, false, true, true>(ctx, p, st) : launch_pair<true, false, false, true>(ctx, p, st);
 }

@@ -158,6 +158,23 @@ class HtfContext:
                                             float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
 
+    def lj_cv_forces(self, nlist, r0, cv_row, cv_sum, force_out=None, virial_out=None, bins=None,
+                     r_range=(0.0, 1.0), nbins=100):
+        """LJ forces(+virial) + smooth coordination CV (+ RDF) in one pass (BASELINE config 5 model).
+        ``cv_row`` float32[rows,4] = (dCV-sum/dd x,y,z, cn_i); ``cv_sum`` float64[1] is incremented."""
+        _check_dev_f32(nlist, "nlist", 4)
+        _check_dev_f32(cv_row, "cv_row", 4)
+        if cv_sum.dtype != torch.float64 or not cv_sum.is_cuda:
+            raise ValueError("cv_sum must be a float64 CUDA tensor")
+        rows, k = nlist.shape[0], nlist.shape[1]
+        if force_out is None:
+            force_out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        vc = virial_out.shape[1] if virial_out is not None else 6
+        self._ck(self.lib.htf_lj_cv_forces(self._h, _ptr(nlist), rows, int(k), float(r0), _ptr(force_out),
+                                           _ptr(virial_out), int(vc), _ptr(cv_row), _ptr(cv_sum), _ptr(bins),
+                                           float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
+        return force_out
+
     def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None,
                  type_tensor=None):
         """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given.

@@ -206,3 +206,48 @@ class RBF(SimModel):
         r = safe_norm(nlist[:, :, :3], axis=2)
         energy = self.dense(self.rbf(r)).sum()
         return compute_nlist_forces(nlist, energy)
+
+
+class EDSCoordinationModel(SimModel):
+    """BASELINE config 5: LJ fluid with an EDS bias on the smooth coordination number
+    ``CV = mean_i sum_j 1/(1 + (r_ij/r0)^6)`` and a running RDF, all from ONE pass over the neighbor tensor.
+
+    Bias energy ``alpha * CV`` (htf/layers.py EDSLayer, examples/03): force on row i is
+    ``F_LJ,i + 2 alpha / N * sum_j ds/dd_ij`` (compute_nlist_forces convention, htf/simmodel.py:542-550); the
+    energy column carries ``e_i + alpha * cn_i / N`` so that the total is ``E_LJ + alpha * CV``.  With row shards
+    (``group`` given) the CV sum, the particle count and the histogram are all-reduced.
+    """
+
+    def setup(self, set_point, period=25, learning_rate=5.0, r0=1.3, rdf_range=None, nbins=100, group=None,
+              cv_scale=1.0):
+        self.eds_bias = EDSLayer(float(set_point), period, learning_rate, cv_scale)
+        self.r0, self.rdf_range, self.nbins, self.group = float(r0), rdf_range, nbins, group
+        self.cv_avg = Mean()
+        self.avg_rdf = MeanTensor()
+        self.last_bins = None
+
+    def compute(self, nlist, positions, box):
+        import torch.distributed as dist
+        from .simmodel import rdf_from_hist
+        fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins)
+        n = torch.tensor([float(nlist.shape[0])], dtype=torch.float64, device=fe.device)
+        if self.group is not None or (dist.is_available() and dist.is_initialized() and self.group is not False):
+            g = self.group if self.group not in (None, False) else None
+            if dist.is_initialized() and dist.get_world_size(g) > 1:
+                packed = torch.cat([cv_sum, n])
+                dist.all_reduce(packed, group=g)
+                cv_sum, n = packed[:1], packed[1:]
+                if bins is not None:
+                    dist.all_reduce(bins, group=g)
+        cv = (cv_sum / n).to(torch.float32)[0]
+        self.cv_avg.update_state(cv)
+        alpha = self.eds_bias(cv)
+        scale = (alpha / n.to(torch.float32))[0]
+        forces = fe.clone()
+        forces[:, :3] += (2.0 * scale) * cv_row[:, :3]
+        forces[:, 3] += scale * cv_row[:, 3]
+        if bins is not None:
+            self.last_bins = bins
+            rdf, _ = rdf_from_hist(bins, self.rdf_range, self.nbins)
+            self.avg_rdf.update_state(rdf)
+        return forces, alpha, cv

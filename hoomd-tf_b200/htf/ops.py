@@ -60,3 +60,23 @@ def rdf_hist(nlist, r_range, nbins=100, type_tensor=None, type_i=None, type_j=No
             tt = tt.to(torch.float32)
     return ctx.rdf_hist(nl, r_range, nbins=nbins, type_tensor=tt, type_i=type_i if tt is not None else None,
                         type_j=type_j if type_tensor is not None else None, bins=bins)
+
+
+def lj_cv_forces(nlist, r0, virial=False, rdf_range=None, nbins=100, bins=None, cv_sum=None):
+    """One pass: LJ forces (+virial [N,6]) + the smooth coordination CV of BASELINE config 5 (+ RDF histogram).
+
+    Returns ``(forces[N,4], virial6 or None, cv_row[N,4], cv_sum float64[1], bins or None)`` where
+    ``cv_row = (sum_j ds/dd_ij (x,y,z), cn_i)`` and ``cv_sum = sum_i cn_i`` (see include/htf_b200.h).
+    """
+    nl = _as_nlist(nlist)
+    ctx = default_context(nl.device)
+    rows = nl.shape[0]
+    cv_row = torch.empty((rows, 4), dtype=torch.float32, device=nl.device)
+    if cv_sum is None:
+        cv_sum = torch.zeros(1, dtype=torch.float64, device=nl.device)
+    vir = torch.empty((rows, 6), dtype=torch.float32, device=nl.device) if virial else None
+    if rdf_range is not None and bins is None:
+        bins = torch.zeros(nbins + 2, dtype=torch.int64, device=nl.device)
+    fe = ctx.lj_cv_forces(nl, r0, cv_row, cv_sum, virial_out=vir, bins=bins,
+                          r_range=rdf_range if rdf_range is not None else (0.0, 1.0), nbins=nbins)
+    return fe, vir, cv_row, cv_sum, bins

@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 7
+#define HTF_ABI_VERSION 8
 int htf_abi_version(void);
 
 /*
@@ -154,6 +154,21 @@ int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float
 int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
                       float *d_virial, int virial_components, int64_t *d_bins, float r_lo, float r_hi,
                       int nbins, void *stream);
+
+/*
+ * EDS-biased model of BASELINE config 5 in one pass over the neighbor tensor: htf_lj_forces (+ optional
+ * fused RDF histogram as in htf_lj_forces_rdf) plus a smooth coordination-number collective variable
+ *   cn_i = sum_j s(r_ij),  s(r) = (1 - (r/r0)^6) / (1 - (r/r0)^12) = 1 / (1 + (r/r0)^6),  CV = mean_i cn_i
+ * (the differentiable form of the `mean(rinv > 0)` coordination number of sphinx-docs/source/running.rst:100-105;
+ * r uses nlist_rinv's safe norm, padded slots are excluded exactly like there).
+ *   d_cv_row  float[rows][4] = (sum_j ds/dd_ij (x, y, z), cn_i): the bias force on row i is
+ *             2 * alpha / N * (x, y, z)   (compute_nlist_forces convention, htf/simmodel.py:542-550)
+ *   d_cv_sum  double[1], atomically += sum_i cn_i (caller zeroes; all-reduce it across row shards)
+ * EDSLayer (htf/layers.py:101-195) turns the CV into alpha on the host side of the ABI.
+ */
+int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float r0, float *d_force_energy,
+                     float *d_virial, int virial_components, float *d_cv_row, double *d_cv_sum, int64_t *d_bins,
+                     float r_lo, float r_hi, int nbins, void *stream);
 
 /*
  * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,

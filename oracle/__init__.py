@@ -49,6 +49,8 @@ def lib():
         L.htf_oracle_lj.argtypes = [fp, i64, i32, fp, fp, fp]
         L.htf_oracle_rdf_hist.restype = ctypes.c_int
         L.htf_oracle_rdf_hist.argtypes = [fp, i64, i32, fp, f32, f32, i32, i32, i32, lp]
+        L.htf_oracle_cv.restype = ctypes.c_int
+        L.htf_oracle_cv.argtypes = [fp, i64, i32, f32, fp, fp]
         L.htf_oracle_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -122,6 +124,18 @@ def rdf_hist(nl, r_range, nbins=100, row_type=None, type_i=None, type_j=None):
     if rc != 0:
         raise RuntimeError("oracle rdf failed: %d" % rc)
     return hist
+
+
+def coordination_cv(nl, r0):
+    """Smooth coordination numbers cn[rows] and their gradient sums grad[rows,3] (BASELINE config 5 CV)."""
+    nl = _f32(nl)
+    rows, K = nl.shape[0], nl.shape[1]
+    cn = np.empty((rows,), dtype=np.float32)
+    g = np.empty((rows, 3), dtype=np.float32)
+    rc = lib().htf_oracle_cv(_ptr(nl, ctypes.c_float), rows, K, float(r0), _ptr(cn, ctypes.c_float), _ptr(g, ctypes.c_float))
+    if rc != 0:
+        raise RuntimeError("oracle cv failed: %d" % rc)
+    return cn, g
 
 
 def rdf_from_hist(hist, r_range, nbins=100):

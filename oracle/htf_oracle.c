@@ -295,6 +295,34 @@ int htf_oracle_rdf_hist(const float *nlist, int64_t rows, int K, const float *ro
     return 0;
 }
 
+/*
+ * Smooth coordination-number CV of BASELINE config 5: cn_i = sum_j 1/(1 + (rt/r0)^6) over the
+ * non-padded slots, rt = nlist_rinv's safe norm (htf/simmodel.py:630-631); grad[i] = sum_j d s/d d_ij.
+ * The reference has no implementation of this CV: this is the specification the kernel is
+ * held to, the differentiable form of `mean(rinv > 0)` (sphinx-docs/source/running.rst:100-105).
+ */
+int htf_oracle_cv(const float *nlist, int64_t rows, int K, float r0, float *coord, float *grad)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; r++) {
+        float cn = 0.f, g[3] = { 0.f, 0.f, 0.f };
+        for (int s = 0; s < K; s++) {
+            const float *d = nlist + 4 * ((size_t)K * r + s);
+            float ax = d[0] + 1e-7f, ay = d[1] + 1e-7f, az = d[2] + 1e-7f;
+            float rt = sqrtf(ax * ax + ay * ay + az * az);
+            if (!(rt > 3e-6f)) continue;
+            float x = rt / r0, x2 = x * x, x6 = x2 * x2 * x2;
+            float sw = 1.0f / (1.0f + x6);
+            cn += sw;
+            float cg = -6.0f * x6 * sw * sw / (rt * rt);
+            g[0] += cg * ax; g[1] += cg * ay; g[2] += cg * az;
+        }
+        coord[r] = cn;
+        grad[3 * r + 0] = g[0]; grad[3 * r + 1] = g[1]; grad[3 * r + 2] = g[2];
+    }
+    return 0;
+}
+
 int htf_oracle_num_threads(void)
 {
 #ifdef _OPENMP

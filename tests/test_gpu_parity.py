@@ -377,3 +377,61 @@ def test_slab_halo_exchange_emulated(oracle_mod):
         nl = c.build_nlist(local, 0, b - a)
         assert c.overflow() == 0
         assert np.array_equal(canon(nl.cpu().numpy()).view(np.uint32), canon(full[a:b]).view(np.uint32)), r
+
+
+def test_coordination_cv_fused_pass(oracle_mod):
+    """fused LJ + coordination CV (+RDF) pass vs the oracle and vs torch autograd of the same CV (config 5 model)."""
+    from htf import synthetic
+    import htf
+    pos, lo, hi = synthetic.lattice_fluid((12, 12, 12), 0.8442, seed=5)
+    K, r_cut, r0 = 96, 2.8, 1.3
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    nl = ctx.build_nlist(torch.from_numpy(pos).cuda())
+    assert ctx.overflow() == 0
+    fe, vir, cv_row, cv_sum, bins = htf.ops.lj_cv_forces(nl, r0, virial=True, rdf_range=(0.0, r_cut), nbins=100)
+    torch.cuda.synchronize()
+    nl_h = nl.cpu().numpy()
+    cn_o, g_o = oracle_mod.coordination_cv(nl_h, r0)
+    fe_o, _, v6_o = oracle_mod.lj(nl_h)
+    assert_close_rel(cv_row.cpu().numpy()[:, 3], cn_o, what="coordination numbers")
+    assert_close_rel(cv_row.cpu().numpy()[:, :3], g_o, what="CV gradient sums")
+    assert_close_rel(fe.cpu().numpy(), fe_o, what="LJ part")
+    assert_close_rel(vir.cpu().numpy(), v6_o, what="virial")
+    assert abs(float(cv_sum) - float(cn_o.astype(np.float64).sum())) <= 1e-6 * float(cv_sum)
+    assert np.array_equal(bins.cpu().numpy(), oracle_mod.rdf_hist(nl_h, (0.0, r_cut), 100))
+    # autograd of the literal CV on the same tensor
+    t = nl.clone().requires_grad_(True)
+    rt = htf.safe_norm(t[:, :, :3], axis=2)
+    s = torch.where(rt > 3e-6, 1.0 / (1.0 + (rt / r0) ** 6), torch.zeros_like(rt))
+    s.sum().backward()
+    np.testing.assert_allclose(cv_row[:, :3].cpu().numpy(), t.grad[:, :, :3].sum(1).cpu().numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_eds_coordination_model_runs_and_biases(oracle_mod):
+    """EDSCoordinationModel through tfcompute: alpha moves towards the set point side, forces = LJ + bias."""
+    import htf
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 8), 0.8442, seed=6)
+    system = htf.sim.System(pos, lo, hi)
+    system.integrator = htf.sim.Langevin(0.002, kT=1.0, seed=3)
+    model = htf.models.EDSCoordinationModel(96, set_point=0.0, period=10, learning_rate=0.05, r0=1.3,
+                                            rdf_range=(0.0, 2.8), nbins=100)
+    tfc = htf.tfcompute(model)
+    tfc.attach(htf.sim.nlist_cell(system), r_cut=2.8, save_output_period=1)
+    system.run(1)
+    cv0 = float(tfc.outputs[1][0])
+    model.eds_bias.set_point.fill_(cv0 * 1.05)           # set point = initial CV + 5 % (SURVEY 8d, config 5)
+    system.run(60)
+    alphas, cvs = tfc.outputs[0], tfc.outputs[1]
+    assert np.all(np.isfinite(alphas)) and np.all(np.isfinite(cvs))
+    assert alphas[-1] != 0.0 and alphas[-1] < 0.0        # CV below the set point -> negative coupling pulls it up
+    assert int(model.last_bins.sum()) == pos.shape[0] * 96
+    # bias force really is 2 alpha / N * grad
+    nl = tfc._nlist_buf
+    fe, _, cv_row, cv_sum, _ = htf.ops.lj_cv_forces(nl, 1.3)
+    f = tfc._forces
+    a = float(model.eds_bias.alpha)
+    # the layer has already stepped past the alpha used for f; recompute with the alpha that was returned
+    a_used = float(alphas[-1])
+    want = fe[:, :3] + (2.0 * a_used / pos.shape[0]) * cv_row[:, :3]
+    np.testing.assert_allclose(f[:, :3].cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-4)
