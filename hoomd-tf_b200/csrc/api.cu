@@ -444,6 +444,39 @@ int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, fl
     return HTF_OK;
 }
 
+int htf_mlp_param_sizes(int *raw_count, int *packed_bytes)
+{
+    if (raw_count) *raw_count = htf_mlp_raw_count_host();
+    if (packed_bytes) *packed_bytes = htf_mlp_packed_bytes_host();
+    return HTF_OK;
+}
+
+int htf_mlp_pack(htf_ctx *ctx, const float *d_raw, void *d_packed, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_raw || !d_packed) { set_err(ctx, "htf_mlp_pack: null argument"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_mlp_pack(ctx, d_raw, reinterpret_cast<unsigned char *>(d_packed), (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const void *d_packed, float rbf_high,
+                   float *d_force_energy, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (rows < 0 || k < 1 || !(rbf_high > 0.0f) || !d_packed || (rows > 0 && (!d_nlist || !d_force_energy))) {
+        set_err(ctx, "htf_mlp_forces: bad arguments"); return HTF_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_packed) & 15) != 0) { set_err(ctx, "htf_mlp_forces: packed blob must be 16-byte aligned"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_mlp(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
+                                 reinterpret_cast<const unsigned char *>(d_packed), rbf_high,
+                                 reinterpret_cast<float4 *>(d_force_energy), (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_row_type,
                  int64_t row_type_stride, float r_lo, float r_hi, int nbins, int type_i, int type_j,
                  int64_t *d_bins, void *stream)

@@ -86,5 +86,11 @@ cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, in
                              int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
                              unsigned long long *bins, cudaStream_t st);
 
+int htf_mlp_packed_bytes_host();
+int htf_mlp_raw_count_host();
+cudaError_t htf_launch_mlp_pack(htf_ctx *ctx, const float *raw, unsigned char *packed, cudaStream_t st);
+cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const unsigned char *packed,
+                           float rbf_high, float4 *fe, cudaStream_t st);
+
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -175,6 +175,32 @@ class HtfContext:
                                            float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
 
+    def mlp_param_sizes(self):
+        """(number of fp32 values in the raw parameter blob, bytes of the packed blob)."""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self.lib.htf_mlp_param_sizes(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def mlp_pack(self, raw, packed=None):
+        """fp32 parameter blob (torch.nn.Linear layout, see include/htf_b200.h) -> packed bf16 operand layouts."""
+        n_raw, n_packed = self.mlp_param_sizes()
+        if not (raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous() and raw.numel() == n_raw):
+            raise ValueError("raw MLP parameters must be a contiguous float32 CUDA tensor of %d values" % n_raw)
+        if packed is None:
+            packed = torch.empty(n_packed, dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.htf_mlp_pack(self._h, _ptr(raw), _ptr(packed), self._stream()))
+        return packed
+
+    def mlp_forces(self, nlist, packed, rbf_high, out=None):
+        """Pairwise-MLP forces+energy [rows,4] on the tensor cores (tcgen05)."""
+        _check_dev_f32(nlist, "nlist", 4)
+        rows, k = nlist.shape[0], nlist.shape[1]
+        if out is None:
+            out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.htf_mlp_forces(self._h, _ptr(nlist), rows, int(k), _ptr(packed), float(rbf_high), _ptr(out),
+                                         self._stream()))
+        return out
+
     def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None,
                  type_tensor=None):
         """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given.

@@ -251,3 +251,44 @@ class EDSCoordinationModel(SimModel):
             rdf, _ = rdf_from_hist(bins, self.rdf_range, self.nbins)
             self.avg_rdf.update_state(rdf)
         return forces, alpha, cv
+
+
+class PairwiseMLPModel(SimModel):
+    """BASELINE config 3: per-pair neural force field, 32 radial basis features -> 3 x Dense(64, tanh) -> Dense(1),
+    ``e_i = 1/2 sum_j u(r_ij)`` over the non-padded slots (the per-pair form of the reference's `RBF` / `NlistNN`
+    models, htf/test-py/build_examples.py:199-241).  Inference runs the fused tcgen05 kernel (bf16 operands, fp32
+    accumulation); ``fused=False`` or ``training=True`` evaluates the same network with torch autograd in fp32 --
+    the reference the tensor-core result is validated against, and the path online training uses."""
+
+    def setup(self, r_cut, seed=3, fused=True):
+        self.r_cut, self.fused = float(r_cut), fused
+        self.rbf = RBFExpansion(0.0, float(r_cut), 32)
+        self.dense1 = torch.nn.Linear(32, 64)
+        self.dense2 = torch.nn.Linear(64, 64)
+        self.dense3 = torch.nn.Linear(64, 64)
+        self.last = torch.nn.Linear(64, 1)
+        g = torch.Generator().manual_seed(int(seed))
+        with torch.no_grad():
+            for lin in (self.dense1, self.dense2, self.dense3, self.last):
+                lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) / lin.in_features ** 0.5)   # N(0, 1/fan_in)
+                lin.bias.copy_(0.1 * torch.randn(lin.bias.shape, generator=g))
+
+    def raw_parameters(self):
+        """fp32 blob in the layout of include/htf_b200.h (htf_mlp_pack)."""
+        return torch.cat([self.dense1.weight.reshape(-1), self.dense1.bias, self.dense2.weight.reshape(-1),
+                          self.dense2.bias, self.dense3.weight.reshape(-1), self.dense3.bias,
+                          self.last.weight.reshape(-1), self.last.bias]).detach().to(torch.float32).contiguous()
+
+    def pair_energy(self, nlist):
+        r = safe_norm(nlist[:, :, :3], axis=2)
+        x = torch.tanh(self.dense1(self.rbf(r)))
+        x = torch.tanh(self.dense2(x))
+        x = torch.tanh(self.dense3(x))
+        u = self.last(x)[..., 0]
+        return torch.where(r > 3e-6, u, torch.zeros_like(u))
+
+    def compute(self, nlist, positions, training):
+        if self.fused and not training and nlist.is_cuda:
+            return ops.mlp_forces(nlist, self.raw_parameters(), self.r_cut)
+        energy = 0.5 * self.pair_energy(nlist).sum(dim=1)
+        return compute_nlist_forces(nlist, energy)

@@ -80,3 +80,11 @@ def lj_cv_forces(nlist, r0, virial=False, rdf_range=None, nbins=100, bins=None, 
     fe = ctx.lj_cv_forces(nl, r0, cv_row, cv_sum, virial_out=vir, bins=bins,
                           r_range=rdf_range if rdf_range is not None else (0.0, 1.0), nbins=nbins)
     return fe, vir, cv_row, cv_sum, bins
+
+
+def mlp_forces(nlist, raw_params, rbf_high, packed=None):
+    """Pairwise-MLP forces+energy [N,4] from the raw fp32 parameter blob (packed to bf16 operands on the fly)."""
+    nl = _as_nlist(nlist)
+    ctx = default_context(nl.device)
+    packed = ctx.mlp_pack(raw_params.detach().to(torch.float32).contiguous(), packed)
+    return ctx.mlp_forces(nl, packed, rbf_high)

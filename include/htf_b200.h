@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 8
+#define HTF_ABI_VERSION 9
 int htf_abi_version(void);
 
 /*
@@ -169,6 +169,23 @@ int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, f
 int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float r0, float *d_force_energy,
                      float *d_virial, int virial_components, float *d_cv_row, double *d_cv_sum, int64_t *d_bins,
                      float r_lo, float r_hi, int nbins, void *stream);
+
+/*
+ * Pairwise-MLP neural force field over the neighbor tensor (BASELINE config 3): the per-pair analogue of the
+ * reference's learned models (`RBF`, htf/test-py/build_examples.py:231-241 with RBFExpansion htf/layers.py:7-49, and
+ * the Dense stack of examples/08): r -> 32 radial basis features (centres linspace(0, rbf_high, 32)) ->
+ * 3 x Dense(64, tanh) -> Dense(1); e_i = 1/2 sum_j u_ij over the non-padded slots; forces by
+ * compute_nlist_forces' rule (htf/simmodel.py:542-550).  Forward and input gradient are six GEMMs per 128 pairs
+ * on the tensor cores (tcgen05, bf16 operands, fp32 accumulate in TMEM); replaces Keras Dense + tf.gradients.
+ *   htf_mlp_param_sizes  number of fp32 values of the raw parameter blob / bytes of the packed blob
+ *   htf_mlp_pack         raw blob, torch.nn.Linear layout  W1[64][32] b1[64] W2[64][64] b2[64] W3[64][64] b3[64]
+ *                        w4[64] b4[1]  ->  packed bf16 operand layouts (call again whenever the weights change)
+ *   htf_mlp_forces       d_force_energy float[rows][4] = (Fx, Fy, Fz, e_i), overwritten
+ */
+int htf_mlp_param_sizes(int *raw_count, int *packed_bytes);
+int htf_mlp_pack(htf_ctx *ctx, const float *d_raw, void *d_packed, void *stream);
+int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const void *d_packed, float rbf_high,
+                   float *d_force_energy, void *stream);
 
 /*
  * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,

@@ -435,3 +435,43 @@ def test_eds_coordination_model_runs_and_biases(oracle_mod):
     a_used = float(alphas[-1])
     want = fe[:, :3] + (2.0 * a_used / pos.shape[0]) * cv_row[:, :3]
     np.testing.assert_allclose(f[:, :3].cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+# bf16 operands (2^-8 relative) + tanh.approx through three 64-wide layers and three gradient GEMMs, summed over
+# ~40 neighbours: errors relative to the RMS force/energy of the fp32 run.
+MLP_TOL_MAX = 1e-1     # worst component of any particle
+MLP_TOL_RMS = 2e-2     # root-mean-square over all particles
+
+
+def test_pairwise_mlp_tensor_core_vs_fp32():
+    """tcgen05 pairwise-MLP kernel vs the fp32 torch evaluation of the same network (north star: 'a stated
+    bf16 tolerance for the tensor-core MLP, validated against an fp32 run')."""
+    import htf
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((16, 16, 16), 0.7, seed=3)
+    K, r_cut = 64, 2.5
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    nl = ctx.build_nlist(torch.from_numpy(pos).cuda())
+    model = htf.models.PairwiseMLPModel(K, r_cut=r_cut, seed=3).cuda()
+    fused = model([nl, None], False)[0]
+    ref = model([nl, None], True)[0].detach()           # training=True -> autograd fp32 path
+    torch.cuda.synchronize()
+    f, g = fused.cpu().numpy().astype(np.float64), ref.cpu().numpy().astype(np.float64)
+    scale_f = np.sqrt(np.mean(g[:, :3] ** 2)); scale_e = np.sqrt(np.mean(g[:, 3] ** 2))
+    err_f = np.abs(f[:, :3] - g[:, :3]).max() / scale_f
+    err_e = np.abs(f[:, 3] - g[:, 3]).max() / scale_e
+    print("pairwise MLP: max |dF|/rms(F) = %.3e, max |de|/rms(e) = %.3e (rms F %.3g, rms e %.3g)" % (err_f, err_e, scale_f, scale_e))
+    assert scale_f > 1e-3 and np.isfinite(f).all()
+    rms_f = np.sqrt(np.mean((f[:, :3] - g[:, :3]) ** 2)) / scale_f
+    print("pairwise MLP: rms dF / rms F = %.3e" % rms_f)
+    assert err_f < MLP_TOL_MAX and err_e < MLP_TOL_MAX and rms_f < MLP_TOL_RMS
+    # other K (generic row reduction path) and a ragged tile count
+    ctx2 = _ctx(pos.shape[0], 40, 2.0, lo, hi)
+    nl2 = ctx2.build_nlist(torch.from_numpy(pos).cuda())[:1001].contiguous()
+    m2 = htf.models.PairwiseMLPModel(40, r_cut=2.0, seed=5).cuda()
+    a = m2([nl2, None], False)[0].cpu().numpy(); b = m2([nl2, None], True)[0].detach().cpu().numpy()
+    s = np.sqrt(np.mean(b[:, :3] ** 2))
+    print("pairwise MLP K=40: max %.3e rms %.3e" % (np.abs(a[:, :3] - b[:, :3]).max() / s, np.sqrt(np.mean((a[:, :3] - b[:, :3]) ** 2)) / s))
+    assert np.abs(a[:, :3] - b[:, :3]).max() / s < MLP_TOL_MAX
+    assert np.sqrt(np.mean((a[:, :3] - b[:, :3]) ** 2)) / s < MLP_TOL_RMS
+    assert np.abs(a[:, 3] - b[:, 3]).max() / np.sqrt(np.mean(b[:, 3] ** 2)) < MLP_TOL_MAX
