@@ -1,5 +1,5 @@
-// Pairwise-MLP neural force field over the neighbor tensor, fused forward + input-gradient on the
-// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a.
+// Pairwise-MLP neural force field over the neighbor tensor: energy and its radial derivative in ONE forward
+// sweep on the 5th-generation tensor cores (tcgen05.mma, operands and accumulators in TMEM), sm_100a.
 //
 // Model (BASELINE config 3; the per-pair analogue of /root/reference htf/test-py/build_examples.py:231-241
 // `RBF` + examples/08's Dense stack):
@@ -9,14 +9,27 @@
 //   e_i = 1/2 sum_j u_ij over the non-padded slots;  F_i = sum_j 2 d(sum e)/d d_ij = sum_j du/dr (d+1e-7)/r
 //   (compute_nlist_forces convention, htf/simmodel.py:542-550).
 //
-// One CTA (128 threads) walks tiles of 128 pairs.  Thread t owns pair t of the tile = TMEM lane t.
-// Six GEMMs per tile, M = 128: three forward (K = 32, 64, 64 -> N = 64) and three for the input
-// gradient (K = 64 -> N = 64, 64, 32).  Activations live on chip for the whole chain: the A operand of
-// every GEMM is written by the epilogue of the previous one into shared memory (bf16, UMMA canonical
-// K-major layout, no swizzle), the weights (both W and W^T, 40 KB bf16) stay resident in shared memory,
-// accumulators are read back from TMEM with tcgen05.ld.  tanh runs as tanh.approx.bf16x2 (two per MUFU).
-// HBM traffic is the 16*K bytes/row read + 16 bytes/row written, the tensor pipe and the SIMT epilogue
-// are the bound.
+// The network input is the scalar r, so du/dr is propagated FORWARD next to the activations (tangent mode):
+//   h' = (1 - h^2) (W h'_prev),  phi'_c = -2 (r - mu_c)/gap phi_c,  du/dr = w4 . h3'
+// Every layer is two M=128 UMMA chains against the same weight tile: Z = [H | 1] [W | b]^T (the bias rides on a
+// constant "ones" K-block, split hi+lo bf16) and Z' = H' W^T.  The last Dense(1) is one more N=16 UMMA pair, so no
+// dot product is left on the SIMT side: u and du/dr are one TMEM column each.
+//
+// One CTA per SM, 512 threads, two tile slots of 128 pairs.  Everything between the UMMAs lives in TMEM: a slot
+// owns 192 columns (Z 64 | Z' 64 fp32 accumulators, H 32 | H' 32 = the next layer's bf16 A operands) and the
+// tensor core reads A straight from TMEM (tcgen05.mma [d], [a], b-desc): activations never touch shared memory
+// or HBM, the only shared-memory operand traffic is the resident weight tiles (29 KB bf16).  A slot is served by
+// two warpgroups that split the columns (TMEM lane = pair, warps w and w+4 reach the same lanes): 32 of the 64
+// outputs each per layer, and the lower / upper 16 radial basis centres.  The pairs arrive by TMA bulk copies
+// (cp.async.bulk + mbarrier, double buffered, one tile ahead).  The epilogues of the two slots alternate through
+// a named-barrier token, so one slot's UMMA round trip (~400 cycles for 9 UMMAs) hides under the other's epilogue;
+// the MUFU pipe (192 MUFU.TANH per pair at 16 lanes/clk/SM) is the bound.  The radial basis is a multiplicative
+// recurrence outwards from the middle centres (8 MUFU.EX2 per pair instead of 32), the tangent update is bf16x2
+// HFMA2/HMUL2.  HBM traffic is the 16 B/pair read + 16 B/row accumulated.
+//
+// Measured on B200 (tools/micro/umma_bench.cu): a UMMA M=128 K=16 with A in TMEM costs 36 cycles at N=64 and 13 at
+// N=16, but only when the issuing lane is chosen with elect.sync -- behind a `threadIdx.x == 0` branch ptxas wraps
+// every UTCHMMA in an ELECT/BRA loop and the issue rate drops to one per ~47 cycles.
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -26,20 +39,23 @@ namespace {
 constexpr int MLP_F = 32;       // radial basis features
 constexpr int MLP_H = 64;       // hidden width
 constexpr int MLP_TM = 128;     // pairs per tile = UMMA M
-constexpr int MLP_THREADS = 128;
+constexpr int MLP_SLOTS = 2;    // tile slots per CTA, two warpgroups (column halves) each
+constexpr int MLP_THREADS = MLP_SLOTS * 2 * MLP_TM;
+// TMEM columns: per slot Z | Z' (fp32 accumulators) and H | H' (bf16 pairs, A operands); one shared ones block
+constexpr int TM_Z = 0, TM_ZP = 64, TM_H = 128, TM_HP = 160, TM_SLOT = 192, TM_ONES = MLP_SLOTS * TM_SLOT;
 
 // ---- packed parameter blob (device), built by mlp_pack_kernel ----
 // bf16 canonical layouts: element (row, k) of an [R x Kt] K-major operand sits at
 //   (k/8) * (R/8)*128 + (row/8) * 128 + (row%8) * 16 + (k%8) * 2      [bytes]
 // i.e. 8x8 core matrices, row groups contiguous (SBO = 128 B), K groups LBO = R*16 B apart.
-constexpr int OFF_B1 = 0;                         // W1   : N=64 x K=32   (forward  layer 1)
-constexpr int OFF_B2 = OFF_B1 + 64 * 32 * 2;      // W2   : 64 x 64
-constexpr int OFF_B3 = OFF_B2 + 64 * 64 * 2;      // W3   : 64 x 64
-constexpr int OFF_B4 = OFF_B3 + 64 * 64 * 2;      // W3^T : 64 x 64       (gradient through layer 3)
-constexpr int OFF_B5 = OFF_B4 + 64 * 64 * 2;      // W2^T : 64 x 64
-constexpr int OFF_B6 = OFF_B5 + 64 * 64 * 2;      // W1^T : N=32 x K=64
-constexpr int OFF_FP = OFF_B6 + 32 * 64 * 2;      // fp32: b1[64] b2[64] b3[64] w4[64] b4 (+3 pad)
-constexpr int MLP_PACKED_BYTES = OFF_FP + (4 * 64 + 4) * 4;
+// Every weight tile carries 16 extra K columns: column Kt = bf16(bias), Kt+1 = bf16(bias - bf16(bias)), rest 0.
+constexpr int OFF_B1 = 0;                               // [W1 | b1] : N=64 x K=32+16   (K order: rbf_centre_of_k)
+constexpr int OFF_B2 = OFF_B1 + 64 * (32 + 16) * 2;     // [W2 | b2] : 64 x 64+16
+constexpr int OFF_B3 = OFF_B2 + 64 * (64 + 16) * 2;     // [W3 | b3] : 64 x 64+16
+constexpr int OFF_B4 = OFF_B3 + 64 * (64 + 16) * 2;     // [w4 | b4] : N=16 x 64+16, rows 1..15 zero
+constexpr int MLP_PACKED_BYTES = OFF_B4 + 16 * (64 + 16) * 2;
+// K order of layer 1: the kernel emits the centres below 16 from the middle outwards, (14,15), (12,13), ...
+__host__ __device__ constexpr int rbf_centre_of_k(int k) { return k < 16 ? 14 - 2 * (k / 2) + (k % 2) : k; }
 
 // raw fp32 parameter blob (torch.nn.Linear layout, [out][in]):
 //   W1[64][32] b1[64] W2[64][64] b2[64] W3[64][64] b3[64] w4[64] b4[1]
@@ -47,49 +63,38 @@ constexpr int RAW_W1 = 0, RAW_B1 = RAW_W1 + 64 * 32, RAW_W2 = RAW_B1 + 64, RAW_B
               RAW_W3 = RAW_B2 + 64, RAW_B3 = RAW_W3 + 64 * 64, RAW_W4 = RAW_B3 + 64, RAW_B4 = RAW_W4 + 64,
               RAW_COUNT = RAW_B4 + 1;
 
-__host__ __device__ constexpr int canon_off(int row, int k, int rows)
+// value of element (row, k) of a [W | b] tile with Kt weight columns
+__device__ __forceinline__ float wb_value(const float *w, const float *b, int row, int k, int Kt)
 {
-    return (k / 8) * (rows / 8) * 128 + (row / 8) * 128 + (row % 8) * 16 + (k % 8) * 2;
+    if (k < Kt) return w[row * Kt + (Kt == MLP_F ? rbf_centre_of_k(k) : k)];
+    const float bv = b[row];
+    const float hi = __bfloat162float(__float2bfloat16(bv));
+    return k == Kt ? hi : (k == Kt + 1 ? bv - hi : 0.f);
 }
 
 __global__ void mlp_pack_kernel(const float *__restrict__ raw, unsigned char *__restrict__ packed)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    auto put = [&](int off, int row, int k, int rows, float v) {
-        *reinterpret_cast<__nv_bfloat16 *>(packed + off + canon_off(row, k, rows)) = __float2bfloat16(v);
-    };
-    if (t < 64 * 32) {                      // W1[o][i]: forward B1 (N=o, K=i); gradient B6 (N=i, K=o)
-        const int o = t / 32, i = t % 32;
-        const float v = raw[RAW_W1 + t];
-        put(OFF_B1, o, i, 64, v);
-        put(OFF_B6, i, o, 32, v);
-    }
-    if (t < 64 * 64) {
-        const int o = t / 64, i = t % 64;
-        const float v2 = raw[RAW_W2 + t], v3 = raw[RAW_W3 + t];
-        put(OFF_B2, o, i, 64, v2);
-        put(OFF_B5, i, o, 64, v2);
-        put(OFF_B3, o, i, 64, v3);
-        put(OFF_B4, i, o, 64, v3);
-    }
-    float *fp = reinterpret_cast<float *>(packed + OFF_FP);
-    if (t < 64) {
-        fp[t] = raw[RAW_B1 + t];
-        fp[64 + t] = raw[RAW_B2 + t];
-        fp[128 + t] = raw[RAW_B3 + t];
-        fp[192 + t] = raw[RAW_W4 + t];
-    }
-    if (t == 0) fp[256] = raw[RAW_B4];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // one bf16 element of the blob: invert the layout
+    if (e >= MLP_PACKED_BYTES / 2) return;
+    const int off = e * 2;
+    const int base = off < OFF_B2 ? OFF_B1 : (off < OFF_B3 ? OFF_B2 : (off < OFF_B4 ? OFF_B3 : OFF_B4));
+    const int rows = base == OFF_B4 ? 16 : 64;
+    const int rel = off - base;
+    const int kg = rel / (rows * 16), rem = rel % (rows * 16);
+    const int row = (rem / 128) * 8 + (rem % 128) / 16, k = kg * 8 + (rem % 16) / 2;
+    float v;
+    if (base == OFF_B1) v = wb_value(raw + RAW_W1, raw + RAW_B1, row, k, 32);
+    else if (base == OFF_B2) v = wb_value(raw + RAW_W2, raw + RAW_B2, row, k, 64);
+    else if (base == OFF_B3) v = wb_value(raw + RAW_W3, raw + RAW_B3, row, k, 64);
+    else v = row == 0 ? wb_value(raw + RAW_W4, raw + RAW_B4, 0, k, 64) : 0.f;
+    reinterpret_cast<__nv_bfloat16 *>(packed)[e] = __float2bfloat16(v);
 }
 
-// ---- shared memory map of the main kernel (dynamic, 1024-aligned base) ----
-constexpr int SM_W = 0;                                   // packed parameters (MLP_PACKED_BYTES)
-constexpr int SM_A0 = (MLP_PACKED_BYTES + 127) / 128 * 128;   // Phi      [128 x 32] bf16   8 KB
-constexpr int SM_A1 = SM_A0 + 128 * 32 * 2;               // H1       [128 x 64] bf16  16 KB
-constexpr int SM_A2 = SM_A1 + 128 * 64 * 2;               // H2       [128 x 64]
-constexpr int SM_A3 = SM_A2 + 128 * 64 * 2;               // Delta    [128 x 64] (reused for delta3, delta2, delta1)
-constexpr int SM_BAR = SM_A3 + 128 * 64 * 2;              // mbarrier (8 B) + tmem base (4 B)
-constexpr int MLP_SMEM = SM_BAR + 16;
+// ---- shared memory map of the main kernel (dynamic) ----
+constexpr int SM_W = 0;                                       // packed parameters (MLP_PACKED_BYTES)
+constexpr int SM_PAIR = (MLP_PACKED_BYTES + 127) / 128 * 128; // float4[MLP_SLOTS][2][128]: TMA-staged pairs, double buffered
+constexpr int SM_BAR = SM_PAIR + MLP_SLOTS * 2 * MLP_TM * 16; // mbarriers: UMMA[MLP_SLOTS], pairs[MLP_SLOTS][2]; tmem base
+constexpr int MLP_SMEM = SM_BAR + 64;
 
 // ---- PTX wrappers ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -111,12 +116,13 @@ __device__ __forceinline__ unsigned make_idesc(int M, int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate)
+// D[128 x N] (TMEM) (+)= A[128 x 16] (TMEM, lane = row, 8 columns of bf16 pairs) * B[N x 16]^T (shared memory)
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc, unsigned idesc,
+                                          unsigned accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(unsigned bar_s)
@@ -131,12 +137,54 @@ __device__ __forceinline__ void mbar_wait(unsigned bar_s, unsigned parity)
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar_s), "r"(parity) : "memory");
 }
 
+// one lane of a converged warp.  A leader chosen this way lets ptxas issue tcgen05.mma back to back; a plain
+// `threadIdx.x == 0` branch wraps every UTCHMMA in an ELECT/BRA loop (~47 cycles per instruction, measured).
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load(unsigned dst_s, const void *src, unsigned bytes, unsigned bar_s)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar_s)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+}
+
+// slot-local barrier: the 256 threads (two warpgroups) of one slot, named barrier 1 + slot
+__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
+// epilogue token: named barriers 3 + slot, 512 participants = the waiting slot (bar.sync) + the releasing slot (bar.arrive)
+__device__ __forceinline__ void token_wait(int slot) { asm volatile("bar.sync %0, 512;" ::"r"(slot + 3) : "memory"); }
+__device__ __forceinline__ void token_arrive(int slot) { asm volatile("bar.arrive %0, 512;" ::"r"(slot + 3) : "memory"); }
+
 #define TMEM_LD16(taddr, v, o)                                                                              \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                  : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),    \
                    "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),  \
                    "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                  \
-                 : "r"((taddr) + (o)))
+                 : "r"(taddr))
+#define TMEM_ST16(taddr, v, o)                                                                              \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+                 ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),  \
+                   "r"(v[o + 6]), "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]),           \
+                   "r"(v[o + 12]), "r"(v[o + 13]), "r"(v[o + 14]), "r"(v[o + 15]) : "memory")
+#define TMEM_ST8(taddr, v)                                                                                  \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                   \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory")
+
+__device__ __forceinline__ unsigned tmem_ld1(unsigned taddr)
+{
+    unsigned r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    return r;
+}
 
 __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi)
 {
@@ -144,25 +192,40 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi)
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));     // first source -> upper half
     return r;
 }
-__device__ __forceinline__ unsigned tanh_bf16x2(unsigned x)
+__device__ __forceinline__ float tanh_approx(float x)
 {
-    unsigned r;
-    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float bf16_lo(unsigned v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(unsigned v) { return __uint_as_float(v & 0xffff0000u); }
-
-// 16-byte store of 8 bf16 of this thread's row into a [128 x Kt] canonical A tile: K group kg
-__device__ __forceinline__ void st_row8(unsigned tile_s, int t, int kg, unsigned a, unsigned b, unsigned c, unsigned d)
+// (1 - h*h) * g on bf16 pairs, given -g: one HFMA2 (exact h^2 - 1, rounded once) and one HMUL2
+__device__ __forceinline__ unsigned tangent_bf16x2(unsigned h, unsigned neg_g)
 {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (unsigned)kg * 2048u + (unsigned)t * 16u),
-                 "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    unsigned d, r;
+    const unsigned minus_one = 0xBF80BF80u;
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(h), "r"(h), "r"(minus_one));
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(d), "r"(neg_g));
+    return r;
 }
-__device__ __forceinline__ void ld_row8(unsigned tile_s, int t, int kg, unsigned &a, unsigned &b, unsigned &c, unsigned &d)
+
+// packed fp32 pairs (FMUL2 on sm_100a)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 {
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
-                 : "r"(tile_s + (unsigned)kg * 2048u + (unsigned)t * 16u) : "memory");
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned bf16x2_of(unsigned long long v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return pack_bf16x2(lo, hi);
 }
 
 struct MlpParams {
@@ -171,195 +234,196 @@ struct MlpParams {
     int K;
     const unsigned char *packed;
     float gap, inv_gap;    // RBF centre spacing
+    float kk;              // exp(-8 gap): ratio of successive stride-2 feature ratios
     float4 *fe;            // [rows]: += (Fx, Fy, Fz, e)   (zeroed by the launcher)
 };
 
-// one GEMM of the chain: D[128 x N] (TMEM) = A[128 x Kt] (smem) * B[N x Kt]^T (smem); issued by one thread
-__device__ __forceinline__ void issue_gemm(unsigned tmem_d, unsigned a_s, unsigned b_s, int N, int Kt, unsigned bar_s)
+// One layer of the chain for one slot, issued by one elected lane (tz = the slot's first TMEM column):
+//   Z  [128 x N] = [H | ones] [W | b]^T     (ksteps K-steps of 16 + the bias step)
+//   Z' [128 x N] =  H' W^T
+__device__ __forceinline__ void issue_layer(unsigned tz, unsigned ones_t, unsigned b_s, int N, int ksteps, unsigned bar_s)
 {
     const unsigned idesc = make_idesc(MLP_TM, N);
-    const unsigned a_lbo = MLP_TM * 16, b_lbo = (unsigned)N * 16;
-    for (int k = 0; k < Kt / 16; k++) {
-        const unsigned long long ad = make_desc(a_s + (unsigned)k * 2u * a_lbo, a_lbo, 128);
+    const unsigned b_lbo = (unsigned)N * 16;
+#pragma unroll 1
+    for (int k = 0; k < ksteps; k++) {
         const unsigned long long bd = make_desc(b_s + (unsigned)k * 2u * b_lbo, b_lbo, 128);
-        umma_bf16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+        umma_bf16(tz + TM_Z, tz + TM_H + 8u * k, bd, idesc, k > 0 ? 1u : 0u);
+        umma_bf16(tz + TM_ZP, tz + TM_HP + 8u * k, bd, idesc, k > 0 ? 1u : 0u);
     }
+    umma_bf16(tz + TM_Z, ones_t, make_desc(b_s + (unsigned)ksteps * 2u * b_lbo, b_lbo, 128), idesc, 1u);
     umma_commit(bar_s);
 }
 
-__global__ void __launch_bounds__(MLP_THREADS, 2) mlp_force_kernel(const MlpParams p)
+// row sums of a finished tile: pair force from (u, du/dr), warp reduction when a warp's 32 pairs share a row
+__device__ __forceinline__ void finish_tile(const MlpParams &p, long long tile, int lt, float ax, float ay, float az, float r,
+                                            float uval, float dudr)
+{
+    const int lane = lt & 31;
+    const long long pair = tile * MLP_TM + lt;
+    const bool inb = pair < p.npairs, valid = inb && r > 3e-6f;
+    const float coef = valid ? dudr / r : 0.f;
+    float fx = coef * ax, fy = coef * ay, fz = coef * az, en = valid ? 0.5f * uval : 0.f;
+    if ((p.K & 31) == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(HTF_FULL, fx, o);
+            fy += __shfl_xor_sync(HTF_FULL, fy, o);
+            fz += __shfl_xor_sync(HTF_FULL, fz, o);
+            en += __shfl_xor_sync(HTF_FULL, en, o);
+        }
+        const long long first = pair - lane;
+        if (lane == 0 && first < p.npairs) {
+            float *dst = reinterpret_cast<float *>(p.fe + first / p.K);
+            atomicAdd(dst + 0, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz); atomicAdd(dst + 3, en);
+        }
+    } else if (inb) {
+        float *dst = reinterpret_cast<float *>(p.fe + pair / p.K);
+        atomicAdd(dst + 0, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz); atomicAdd(dst + 3, en);
+    }
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_force_kernel(const MlpParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x;
+    const int slot = t >> 8, half = (t >> 7) & 1, lt = t & 127, lw = lt >> 5;
+    const bool slot_warp0 = (t & 255) < 32;                 // issues this slot's UMMAs and TMA copies
     const unsigned sbase = smem_u32(smem);
-    const unsigned bar_s = sbase + SM_BAR;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + SM_BAR + 8);
+    const unsigned bar_s = sbase + SM_BAR + 8u * slot;                     // UMMA completion
+    const unsigned ldbar_s = sbase + SM_BAR + 8u * MLP_SLOTS + 16u * slot; // pair buffers 0, 1
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + SM_BAR + 8 * MLP_SLOTS * 3);
 
     // parameters -> shared memory (resident for the whole kernel)
     for (int i = t; i < MLP_PACKED_BYTES / 16; i += MLP_THREADS)
         reinterpret_cast<uint4 *>(smem + SM_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.packed) + i);
     if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        for (int s = 0; s < MLP_SLOTS * 3; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + SM_BAR + 8u * s));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {                    // TMEM: 64 fp32 columns x 128 lanes for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)));
+    if (t < 32) {                       // the whole TMEM (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // parameter stores visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem_d = *tmem_slot;
-    const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16);   // this warp's 32 lanes
-    const float *fp = reinterpret_cast<const float *>(smem + SM_W + OFF_FP);
-    unsigned phase = 0;
-
-    const long long ntiles = (p.npairs + MLP_TM - 1) / MLP_TM;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- pair -> features ----
-        const long long pair = tile * MLP_TM + t;
-        const bool inb = pair < p.npairs;
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb) d = __ldg(p.nlist + pair);
-        const float ax = d.x + 1e-7f, ay = d.y + 1e-7f, az = d.z + 1e-7f;
-        const float r2 = ax * ax + ay * ay + az * az;
-        const float r = sqrtf(r2);
-        const bool valid = inb && r > 3e-6f;
-        {
-            unsigned w[4];
-#pragma unroll
-            for (int kg = 0; kg < MLP_F / 8; kg++) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int c = kg * 8 + 2 * q;
-                    const float u0 = r - (float)c * p.gap, u1 = r - (float)(c + 1) * p.gap;
-                    w[q] = pack_bf16x2(__expf(-u0 * u0 * p.inv_gap), __expf(-u1 * u1 * p.inv_gap));
-                }
-                st_row8(sbase + SM_A0, t, kg, w[0], w[1], w[2], w[3]);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-
-        unsigned v[64];
-        float uval = 0.f;
-        // ================= forward =================
-#pragma unroll 1
-        for (int layer = 0; layer < 3; layer++) {
-            if (t == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned a_s = sbase + (layer == 0 ? SM_A0 : (layer == 1 ? SM_A1 : SM_A2));
-                const unsigned b_s = sbase + SM_W + (layer == 0 ? OFF_B1 : (layer == 1 ? OFF_B2 : OFF_B3));
-                issue_gemm(tmem_d, a_s, b_s, MLP_H, layer == 0 ? MLP_F : MLP_H, bar_s);
-            }
-            mbar_wait(bar_s, phase);
-            phase ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            TMEM_LD16(taddr, v, 0); TMEM_LD16(taddr, v, 16); TMEM_LD16(taddr, v, 32); TMEM_LD16(taddr, v, 48);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float *bias = fp + layer * 64;
-            const unsigned out_s = sbase + (layer == 0 ? SM_A1 : (layer == 1 ? SM_A2 : SM_A3));
-#pragma unroll
-            for (int kg = 0; kg < 8; kg++) {
-                unsigned h[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int c = kg * 8 + 2 * q;
-                    h[q] = tanh_bf16x2(pack_bf16x2(__uint_as_float(v[c]) + bias[c], __uint_as_float(v[c + 1]) + bias[c + 1]));
-                }
-                if (layer < 2) {
-                    st_row8(out_s, t, kg, h[0], h[1], h[2], h[3]);
-                } else {
-                    // last hidden layer: u = w4 . h3 + b4 and delta3 = (1 - h3^2) w4 (A operand of the first gradient GEMM)
-                    unsigned dl[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int c = kg * 8 + 2 * q;
-                        const float h0 = bf16_lo(h[q]), h1 = bf16_hi(h[q]);
-                        const float w0 = fp[192 + c], w1 = fp[192 + c + 1];
-                        uval += h0 * w0 + h1 * w1;
-                        dl[q] = pack_bf16x2((1.f - h0 * h0) * w0, (1.f - h1 * h1) * w1);
-                    }
-                    st_row8(out_s, t, kg, dl[0], dl[1], dl[2], dl[3]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-        }
-        uval += fp[256];
-
-        // ================= gradient w.r.t. the features =================
-#pragma unroll 1
-        for (int layer = 0; layer < 3; layer++) {
-            const int N = layer == 2 ? MLP_F : MLP_H;
-            if (t == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned b_s = sbase + SM_W + (layer == 0 ? OFF_B4 : (layer == 1 ? OFF_B5 : OFF_B6));
-                issue_gemm(tmem_d, sbase + SM_A3, b_s, N, MLP_H, bar_s);
-            }
-            mbar_wait(bar_s, phase);
-            phase ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            TMEM_LD16(taddr, v, 0); TMEM_LD16(taddr, v, 16);
-            if (layer < 2) { TMEM_LD16(taddr, v, 32); TMEM_LD16(taddr, v, 48); }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (layer < 2) {
-                // delta_l = (1 - h_l^2) * g_l, h_l read back from the forward A tile of the next layer
-                const unsigned h_s = sbase + (layer == 0 ? SM_A2 : SM_A1);
-#pragma unroll
-                for (int kg = 0; kg < 8; kg++) {
-                    unsigned h[4], dl[4];
-                    ld_row8(h_s, t, kg, h[0], h[1], h[2], h[3]);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int c = kg * 8 + 2 * q;
-                        const float h0 = bf16_lo(h[q]), h1 = bf16_hi(h[q]);
-                        dl[q] = pack_bf16x2((1.f - h0 * h0) * __uint_as_float(v[c]), (1.f - h1 * h1) * __uint_as_float(v[c + 1]));
-                    }
-                    st_row8(sbase + SM_A3, t, kg, dl[0], dl[1], dl[2], dl[3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-        }
-
-        // ---- du/dr = sum_c g_c dphi_c/dr, pair force, row sums ----
-        float dudr = 0.f;
-#pragma unroll
-        for (int c = 0; c < MLP_F; c++) {
-            const float uu = r - (float)c * p.gap;
-            const float phi = __expf(-uu * uu * p.inv_gap);
-            dudr += __uint_as_float(v[c]) * (-2.f * uu * p.inv_gap) * phi;
-        }
-        const float coef = valid ? dudr / r : 0.f;
-        float fx = coef * ax, fy = coef * ay, fz = coef * az, en = valid ? 0.5f * uval : 0.f;
-        if ((p.K & 31) == 0) {
-            // the 32 pairs of a warp belong to one row: warp reduction, one atomic per component
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                fx += __shfl_xor_sync(HTF_FULL, fx, o);
-                fy += __shfl_xor_sync(HTF_FULL, fy, o);
-                fz += __shfl_xor_sync(HTF_FULL, fz, o);
-                en += __shfl_xor_sync(HTF_FULL, en, o);
-            }
-            const long long first = tile * MLP_TM + warp * 32;
-            if (lane == 0 && first < p.npairs) {
-                float *dst = reinterpret_cast<float *>(p.fe + first / p.K);
-                atomicAdd(dst + 0, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz); atomicAdd(dst + 3, en);
-            }
-        } else if (inb) {
-            float *dst = reinterpret_cast<float *>(p.fe + pair / p.K);
-            atomicAdd(dst + 0, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz); atomicAdd(dst + 3, en);
-        }
+    const unsigned tmem_base = *tmem_slot;
+    const unsigned lane_off = (unsigned)(lw * 32) << 16;                   // this warp's 32 TMEM lanes
+    const unsigned tz = tmem_base + (unsigned)slot * TM_SLOT;              // this slot's columns
+    const unsigned w_s = sbase + SM_W;
+    if (t < MLP_TM) {                   // ones block: K columns 0,1 = 1 (bias hi + lo), the other 14 zero
+        unsigned one[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        TMEM_ST8(tmem_base + TM_ONES + lane_off, one);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const long long ntiles = (p.npairs + MLP_TM - 1) / MLP_TM;
+    const long long stride = (long long)gridDim.x * MLP_SLOTS;
+    long long tile = (long long)blockIdx.x * MLP_SLOTS + slot;
+    const unsigned pair_s = sbase + SM_PAIR + (unsigned)slot * (2 * MLP_TM * 16);
+    // one elected lane per slot stages the pairs of a tile (whole tile, or the ragged last one, or nothing)
+    auto stage_pairs = [&](long long tl, int buf) {
+        long long n = p.npairs - tl * MLP_TM;
+        n = n < 0 ? 0 : (n > MLP_TM ? MLP_TM : n);
+        if (n > 0) tma_load(pair_s + (unsigned)buf * (MLP_TM * 16), p.nlist + tl * MLP_TM, (unsigned)n * 16u, ldbar_s + 8u * buf);
+        else mbar_arrive(ldbar_s + 8u * buf);
+    };
+    if (slot_warp0 && elect_one()) stage_pairs(tile, 0);
+    if (slot == 1) token_arrive(0);     // slot 0 owns the MUFU pipe first
+    unsigned phase = 0;
+    // the lower half finishes tile i while the first UMMAs of tile i+1 run: its pair and (u, du/dr) wait here
+    long long pend_tile = -1;
+    float pend_ax = 0.f, pend_ay = 0.f, pend_az = 0.f, pend_r = 1.f, pend_u = 0.f, pend_du = 0.f;
+    // both slots run the same number of rounds (a slot past the end works on an all-padding tile): the epilogue
+    // token alternates strictly between them
+    int round = 0;
+    for (long long tile0 = (long long)blockIdx.x * MLP_SLOTS; tile0 < ntiles; tile0 += stride, tile += stride, round++) {
+        const int buf = round & 1;
+        if (slot_warp0) {
+            if (elect_one()) stage_pairs(tile + stride, buf ^ 1);         // next round's pairs
+            __syncwarp();
+        }
+        mbar_wait(ldbar_s + 8u * buf, (unsigned)(round >> 1) & 1u);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile * MLP_TM + lt < p.npairs) d = *reinterpret_cast<const float4 *>(smem + SM_PAIR + ((size_t)(slot * 2 + buf) * MLP_TM + lt) * 16);
+        const float ax = d.x + 1e-7f, ay = d.y + 1e-7f, az = d.z + 1e-7f;
+        const float r = sqrtf(ax * ax + ay * ay + az * az);
+
+        // ---- radial basis and its derivative: this half's 16 centres by recurrence away from the middle.
+        //      upper half: (16,17), (18,19), ...   lower half: (14,15), (12,13), ...   (K order: rbf_centre_of_k)
+        {
+            const float g = p.gap, s = p.inv_gap;
+            const float sgn = half ? 1.f : -1.f, c0 = half ? 16.f : 14.f;
+            const float ua = r - c0 * g, ub = ua - g;
+            unsigned long long ph = pk2(__expf(-ua * ua * s), __expf(-ub * ub * s));
+            unsigned long long ratio = pk2(__expf(sgn * 4.f * ua - 4.f * g), __expf(sgn * 4.f * ub - 4.f * g));   // phi_{c+-2}/phi_c
+            const unsigned long long kk2 = pk2(p.kk, p.kk);
+            const float wbase = 2.f * c0 - 2.f * s * r, sgn4 = 4.f * sgn;  // phi'_c = (2c - 2 r/gap) phi_c
+            unsigned f[8], fd[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float wa = fmaf(sgn4, (float)i, wbase);
+                f[i] = bf16x2_of(ph);
+                fd[i] = bf16x2_of(mul2(ph, pk2(wa, wa + 2.f)));
+                if (i < 7) { ph = mul2(ph, ratio); ratio = mul2(ratio, kk2); }
+            }
+            TMEM_ST8(tz + TM_H + 8u * half + lane_off, f);
+            TMEM_ST8(tz + TM_HP + 8u * half + lane_off, fd);
+        }
+
+        // ---- three hidden layers and Dense(1): UMMA pair -> epilogue back into the A columns ----
+#pragma unroll 1
+        for (int layer = 0; layer < 4; layer++) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            slot_sync(slot);
+            if (slot_warp0) {
+                if (elect_one()) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned b_s = w_s + (layer == 0 ? OFF_B1 : (layer == 1 ? OFF_B2 : (layer == 2 ? OFF_B3 : OFF_B4)));
+                    issue_layer(tz, tmem_base + TM_ONES, b_s, layer == 3 ? 16 : MLP_H, layer == 0 ? MLP_F / 16 : MLP_H / 16, bar_s);
+                }
+                __syncwarp();
+            }
+            if (layer == 0 && half == 0 && pend_tile >= 0)                // previous tile's row sums, under this tile's UMMAs
+                finish_tile(p, pend_tile, lt, pend_ax, pend_ay, pend_az, pend_r, pend_u, pend_du);
+            mbar_wait(bar_s, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (layer == 3) break;
+            token_wait(slot);           // one slot's epilogue at a time: the other one is inside its UMMA round trip
+            unsigned z[32], zp[32], h[16], hp[16];
+            const unsigned zc = tz + lane_off + 32u * half;               // this half's 32 output columns
+            TMEM_LD16(zc + TM_Z, z, 0); TMEM_LD16(zc + TM_Z + 16, z, 16);
+            TMEM_LD16(zc + TM_ZP, zp, 0); TMEM_LD16(zc + TM_ZP + 16, zp, 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                h[q] = pack_bf16x2(tanh_approx(__uint_as_float(z[2 * q])), tanh_approx(__uint_as_float(z[2 * q + 1])));
+                hp[q] = tangent_bf16x2(h[q], pack_bf16x2(-__uint_as_float(zp[2 * q]), -__uint_as_float(zp[2 * q + 1])));
+            }
+            TMEM_ST16(tz + TM_H + 16u * half + lane_off, h, 0);
+            TMEM_ST16(tz + TM_HP + 16u * half + lane_off, hp, 0);
+            token_arrive(1 - slot);
+        }
+        if (half == 0) {
+            pend_u = __uint_as_float(tmem_ld1(tz + TM_Z + lane_off));     // u     = w4 . h3 + b4
+            pend_du = __uint_as_float(tmem_ld1(tz + TM_ZP + lane_off));   // du/dr = w4 . h3'
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            pend_tile = tile; pend_ax = ax; pend_ay = ay; pend_az = az; pend_r = r;
+        }
+    }
+    if (half == 0 && pend_tile >= 0) finish_tile(p, pend_tile, lt, pend_ax, pend_ay, pend_az, pend_r, pend_u, pend_du);
+    // drain the pair copy staged for the round that never ran, then release the TMEM
+    mbar_wait(ldbar_s + 8u * (round & 1), (unsigned)(round >> 1) & 1u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 }  // namespace
@@ -369,7 +433,7 @@ int htf_mlp_raw_count_host() { return RAW_COUNT; }
 
 cudaError_t htf_launch_mlp_pack(htf_ctx *ctx, const float *raw, unsigned char *packed, cudaStream_t st)
 {
-    mlp_pack_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(raw, packed);
+    mlp_pack_kernel<<<(MLP_PACKED_BYTES / 2 + 255) / 256, 256, 0, st>>>(raw, packed);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -388,10 +452,10 @@ cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     }
     MlpParams p;
     p.nlist = nlist; p.npairs = (long long)rows * K; p.K = K; p.packed = packed;
-    p.gap = rbf_high / (float)(MLP_F - 1); p.inv_gap = 1.0f / p.gap; p.fe = fe;
+    p.gap = rbf_high / (float)(MLP_F - 1); p.inv_gap = 1.0f / p.gap; p.kk = expf(-8.0f * p.gap); p.fe = fe;
     const long long ntiles = (p.npairs + MLP_TM - 1) / MLP_TM;
-    long long grid = 2LL * ctx->sm_count;
-    if (grid > ntiles) grid = ntiles;
+    long long grid = ctx->sm_count;
+    if (grid > (ntiles + MLP_SLOTS - 1) / MLP_SLOTS) grid = (ntiles + MLP_SLOTS - 1) / MLP_SLOTS;
     mlp_force_kernel<<<(unsigned)grid, MLP_THREADS, MLP_SMEM, st>>>(p);
     ctx->launches += 1;
     return cudaGetLastError();
