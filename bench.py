@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--model", default="lj", choices=["lj", "mlp"],
+                    help="lj: closed-form LJ + virial (the headline path); mlp: BASELINE config 3's pairwise-MLP force "
+                         "field on the tensor cores (forces + energy)")
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
                     help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
@@ -52,6 +55,17 @@ def peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+MLP_FLOP_PER_PAIR = 2 * 2 * (32 * 64 + 64 * 64 + 64 * 64 + 64)     # value and tangent chains, multiply+add
+
+
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1500.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
 
 
 def ncu_traffic():
@@ -149,8 +163,15 @@ def run_reference(args):
     rows = min(n, 262144)                  # bounded sample: a row slab of the same system
     a0 = (n - rows) // 2
 
+    if args.model == "mlp":
+        rows = min(n, 32768)               # the numpy MLP is ~50x slower per row than the LJ closed form
+        a0 = (n - rows) // 2
+        raw = mlp_raw_parameters()
+
     def step():
         nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
+        if args.model == "mlp":
+            return oracle.pairwise_mlp(nl, raw, r_cut)
         fe, _, v6 = oracle.lj(nl, virial=True)
         if args.rdf:
             oracle.rdf_hist(nl, (0.0, r_cut), 100)
@@ -178,10 +199,22 @@ def run_reference(args):
     return 0
 
 
+def mlp_raw_parameters(seed=3):
+    """Random-init weights of the config-3 architecture (N(0, 1/fan_in), biases 0.1 N(0,1)) as the raw blob."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    parts = []
+    for fan_out, fan_in in ((64, 32), (64, 64), (64, 64), (1, 64)):
+        parts.append((rng.standard_normal((fan_out, fan_in)) / np.sqrt(fan_in)).astype(np.float32).ravel())
+        parts.append((0.1 * rng.standard_normal(fan_out)).astype(np.float32))
+    return np.concatenate(parts)
+
+
 def cfg_dict(args, n, K, r_cut, world):
-    return {"workload": "lj_fluid_%s%s" % (args.workload, "+rdf100" if args.rdf else ""),
+    return {"workload": "lj_fluid_%s%s%s" % (args.workload, "+rdf100" if args.rdf else "", "+pairwise_mlp" if args.model == "mlp" else ""),
             "particles": n, "particles_per_gpu": n // world, "nneighbor_cutoff": K, "r_cut": r_cut,
-            "model": "LJ (nlist_rinv closed form) + 6-component virial",
+            "model": ("pairwise MLP: RBF(32) -> 3 x Dense(64, tanh) -> Dense(1), bf16 operands / fp32 accumulation (tcgen05)"
+                      if args.model == "mlp" else "LJ (nlist_rinv closed form) + 6-component virial"),
             "sharding": ("particle rows (z-slabs), %s per step" % ("halo exchange of the two slab faces"
                          if args.exchange == "halo" else "all-gather of all positions")) if world > 1 else "single GPU",
             "l2": "per-GPU working set %.0f MiB/step > 126 MB L2, no flush needed" % (n // world * K * 16 / 2 ** 20)}
@@ -234,6 +267,9 @@ def run_b200(args):
     fe = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     vir = torch.empty((rows, 6), dtype=torch.float32, device=dev)
     bins = torch.zeros(102, dtype=torch.int64, device=dev) if args.rdf else None
+    packed = None
+    if args.model == "mlp":
+        packed = ctx.mlp_pack(torch.from_numpy(mlp_raw_parameters()).to(dev))
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):
@@ -247,7 +283,9 @@ def run_b200(args):
         ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
         if marks is not None:
             marks[1].record()
-        if bins is not None:
+        if packed is not None:
+            ctx.mlp_forces(nl, packed, r_cut, out=fe)
+        elif bins is not None:
             bins.zero_()
             ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
             if world > 1:
@@ -317,6 +355,18 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": e2e,
         }
+        if args.model == "mlp":
+            # the dominant kernel of this workload is the tensor-core MLP: report it against the measured bf16 peak
+            tpeak, tsrc = tensor_peak()
+            flop = rows * K * MLP_FLOP_PER_PAIR
+            tf = flop / (force_ms * 1e-3) / 1e12
+            line["dtype"] = "bf16"
+            line["roofline"] = {"bound": "tensor", "kernel": "mlp_force_kernel (tcgen05, operands in TMEM)", "achieved": tf,
+                                "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
+                                "algorithmic_flop_per_launch": flop, "kernel_ms": force_ms, "traffic": None,
+                                "note": "41,216 useful flop per pair (value + tangent through 32-64-64-64-1); the kernel's own "
+                                        "bound is the MUFU pipe (200 MUFU per pair at 16 lanes/clk/SM), see DESIGN.md",
+                                "nlist_build_ms": build_ms, "nlist_build_frac": achieved / peak}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pos, lo, hi, r_cut, K)
         print(json.dumps(line))
@@ -332,7 +382,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     n = pos.shape[0]
     rows = row_hi - row_lo
     system = htf.sim.System(pos, lo, hi, device=dev)
-    model = htf.models.LJVirialModel(K, virial=True)
+    model = htf.models.PairwiseMLPModel(K, r_cut=r_cut).to(dev) if args.model == "mlp" else htf.models.LJVirialModel(K, virial=True)
     tfc = htf.tfcompute(model)
     tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
     h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
@@ -351,7 +401,8 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
             system.positions.copy_(d_shard)
         f = tfc.compute_forces(t)
         h_f.copy_(f[row_lo:row_hi], non_blocking=True)
-        h_v.copy_(tfc.virial6((row_lo, row_hi)), non_blocking=True)       # the 6 components HOOMD keeps
+        if args.model != "mlp":
+            h_v.copy_(tfc.virial6((row_lo, row_hi)), non_blocking=True)   # the 6 components HOOMD keeps
 
     steps = max(3, min(args.steps, 10))
     for t in range(3):
@@ -372,8 +423,9 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4),
-            "d2h_bytes_per_step": int(h_f.numel() * 4 + h_v.numel() * 4), "steps": steps,
-            "api": "htf.tfcompute(LJVirialModel).compute_forces with pinned host positions in, forces+virial out"}
+            "d2h_bytes_per_step": int(h_f.numel() * 4 + (0 if args.model == "mlp" else h_v.numel() * 4)), "steps": steps,
+            "api": "htf.tfcompute(%s).compute_forces with pinned host positions in, forces%s out"
+                   % (("PairwiseMLPModel", "+energy") if args.model == "mlp" else ("LJVirialModel", "+virial"))}
 
 
 def cpu_baseline(args, pos, lo, hi, r_cut, K):
@@ -381,13 +433,17 @@ def cpu_baseline(args, pos, lo, hi, r_cut, K):
     import oracle
     oracle.build()
     n = pos.shape[0]
-    rows = min(n, 262144)
+    rows = min(n, 32768 if args.model == "mlp" else 262144)
     a0 = (n - rows) // 2
+    raw = mlp_raw_parameters() if args.model == "mlp" else None
     reps, t_tot = 0, 0.0
     while t_tot < 8.0 and reps < 6:
         t0 = time.perf_counter()
         nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
-        oracle.lj(nl, virial=True)
+        if raw is not None:
+            oracle.pairwise_mlp(nl, raw, r_cut)
+        else:
+            oracle.lj(nl, virial=True)
         if args.rdf:
             oracle.rdf_hist(nl, (0.0, r_cut), 100)
         t_tot += time.perf_counter() - t0

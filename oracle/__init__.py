@@ -147,6 +147,46 @@ def rdf_from_hist(hist, r_range, nbins=100):
     return (hist[1:-1].astype(np.float32) / vols).astype(np.float32), vis
 
 
+def pairwise_mlp(nl, raw, rbf_high):
+    """fp32 numpy restatement of the pairwise-MLP force field (BASELINE config 3): RBFExpansion(0, rbf_high, 32)
+    (htf/layers.py:27-49) -> 3 x Dense(64, tanh) -> Dense(1), e_i = 1/2 sum_j u(r_ij) over the non-padded slots,
+    forces by compute_nlist_forces' convention (htf/simmodel.py:542-550) with the analytic du/dr.
+    ``raw`` is the parameter blob of include/htf_b200.h (torch.nn.Linear layout).  Returns [rows,4] (F, e).
+    PARITY UNPINNED against the reference (it has no such model with fixed weights); it is pinned against the
+    torch autograd evaluation of the same network in tests/."""
+    f = np.float32
+    nl = _f32(nl)
+    raw = _f32(raw)
+    o = 0
+    def take(n, shape):
+        nonlocal o
+        a = raw[o:o + n].reshape(shape); o += n
+        return a
+    W1, b1 = take(64 * 32, (64, 32)), take(64, (64,))
+    W2, b2 = take(64 * 64, (64, 64)), take(64, (64,))
+    W3, b3 = take(64 * 64, (64, 64)), take(64, (64,))
+    w4, b4 = take(64, (64,)), take(1, (1,))
+    d = nl[..., :3] + f(1e-7)
+    r = np.sqrt((d * d).sum(-1, dtype=f))
+    mu = np.linspace(0.0, rbf_high, 32, dtype=f)
+    gap = f(mu[1] - mu[0])
+    u_c = r[..., None] - mu
+    phi = np.exp(-(u_c * u_c) / gap).astype(f)
+    dphi = (f(-2.0) * u_c / gap * phi).astype(f)
+    h, hp = phi, dphi
+    for W, b in ((W1, b1), (W2, b2), (W3, b3)):
+        z, zp = h @ W.T + b, hp @ W.T
+        h = np.tanh(z).astype(f)
+        hp = ((f(1.0) - h * h) * zp).astype(f)
+    u, du = h @ w4 + b4[0], hp @ w4
+    mask = r > f(3e-6)
+    coef = np.where(mask, du / r, f(0)).astype(f)
+    out = np.empty(nl.shape[:1] + (4,), dtype=f)
+    out[:, :3] = (coef[..., None] * d).sum(1, dtype=f)
+    out[:, 3] = (f(0.5) * np.where(mask, u, f(0))).sum(1, dtype=f)
+    return out
+
+
 class EDSLayer:
     """Scalar restatement of htf/layers.py:142-195 (EDSLayer.call) with tf.compat.v1 Adam
     (beta1 .9, beta2 .999, eps 1e-8, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)); fp32 state.

@@ -182,3 +182,18 @@ def test_two_rank_row_sharding_gloo(oracle_mod):
     bins = oracle_mod.rdf_hist(nl, (0.0, 2.5), 100)
     assert np.array_equal(res[0][4], bins) and np.array_equal(res[1][4], bins)
     assert abs(res[0][5] - float((nl[:, :, :3].astype(np.float64) ** 2).sum())) < 1e-3 * res[0][5]
+
+
+def test_oracle_pairwise_mlp_matches_torch_autograd():
+    """The numpy restatement of the config-3 network (analytic du/dr) against torch autograd of the same network."""
+    import oracle
+    import htf
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((6, 6, 6), 0.7, seed=1)
+    nl, _, _ = oracle.nlist(pos, lo, hi, 2.5, 64)
+    m = htf.models.PairwiseMLPModel(64, r_cut=2.5, seed=3)
+    ref = m([torch.from_numpy(nl), None], True)[0].detach().numpy()
+    out = oracle.pairwise_mlp(nl, m.raw_parameters().numpy(), 2.5)
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() < 1e-5 * scale          # fp32 tolerance of the north star
+    assert np.abs(ref[:, :3]).max() > 0.1
