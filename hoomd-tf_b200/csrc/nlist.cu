@@ -638,6 +638,11 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
         if (lane >= o) incl += t;
     }
     if (lane == 31 && warp < 4) wtot[warp] = incl;              // totals of pieces [32w, 32w+32)
+    const unsigned stage_bar = (unsigned)__cvta_generic_to_shared(wtot + 4);   // mbarrier of the bulk copies (8-byte aligned)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stage_bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     for (int w = 0; w < warp && w < 4; w++) incl += wtot[w];
     if (tid < NPMAX) {
@@ -670,19 +675,28 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
         if (!__syncthreads_or(any)) return;
     }
 
-    // ---- stage the whole neighbourhood once (asynchronous copies, one wait) ----
-    // warp w copies pieces w, w+TILE, ...: a piece is one cell (a dozen particles), one lane each
-    for (int q = warp; q < npieces; q += TILE) {
-        const int qend = ptab_end[q], qadj = ptab_adj[q];
-        const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
-        for (int t = qbeg + lane; t < qend; t += 32) {
-            cp_async16(cand_s + (unsigned)t * 16u, p.spos + (t + qadj));
-            if (WITH_IDX) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
+    // ---- stage the whole neighbourhood once: one TMA bulk copy per piece (a piece = one stencil cell = one
+    //      contiguous run of the cell-sorted positions), issued by the thread that owns the piece's table entry;
+    //      completion is counted in bytes on one mbarrier ----
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stage_bar), "r"((unsigned)mblock * 16u) : "memory");
+    if (tid < npieces && pl > 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(cand_s + (unsigned)(incl - pl) * 16u), "l"(p.spos + pb), "r"((unsigned)pl * 16u), "r"(stage_bar) : "memory");
+    if (WITH_IDX) {
+        // original indices ride along as 4-byte cp.async (bulk copies need 16-byte granules): warp w takes pieces w, w+TILE, ...
+        for (int q = warp; q < npieces; q += TILE) {
+            const int qend = ptab_end[q], qadj = ptab_adj[q];
+            const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
+            for (int t = qbeg + lane; t < qend; t += 32) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     // 32 sentinels behind the staged data: the last chunk of the last window may read past its end
     if (warp == 0) cand[mblock + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(stage_bar) : "memory");
     __syncthreads();
 
     // ---- one warp per cell of the tile ----
