@@ -231,7 +231,9 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     for (int a = 0; a < 3; a++) ctx->grid.roi_h[a] = -1.0f;
     DeviceGuard guard(device);
     int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
-    if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 4);
+    if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 8);          // [0..2] cell statistics, [4..5] flagged-tile counters
+    if (!rc && cudaMemset(ctx->d_stats, 0, 8 * sizeof(int)) != cudaSuccess) rc = HTF_ECUDA;
+    if (!rc) ctx->d_flag_count = ctx->d_stats + 4;
     if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
     *out = ctx;
     return HTF_OK;

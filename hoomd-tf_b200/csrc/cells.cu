@@ -164,21 +164,16 @@ __global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__
     const int n = e - b;
     if (n == 0) return;
     if (n <= 32) {
-        int v = (lane < n) ? sorted_idx[b + lane] : 0x7fffffff;
+        const int v = (lane < n) ? sorted_idx[b + lane] : 0x7fffffff;
+        int dst = lane;
         if (SORT && n > 1) {
-#pragma unroll
-            for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    const int o = __shfl_xor_sync(HTF_FULL, v, j);
-                    const bool up = ((lane & k) == 0);          // ascending block?
-                    const bool lower = ((lane & j) == 0);       // this lane keeps the smaller one?
-                    v = (lower == up) ? min(v, o) : max(v, o);
-                }
-            }
-            if (lane < n) sorted_idx[b + lane] = v;
+            // rank by counting (indices are distinct): n shuffles instead of a 15-stage bitonic network
+            __syncwarp();                                       // every lane holds its index before any lane overwrites the run
+            dst = 0;
+            for (int j = 0; j < n; j++) dst += (__shfl_sync(HTF_FULL, v, j) < v) ? 1 : 0;
+            if (lane < n) sorted_idx[b + dst] = v;
         }
-        if (lane < n) spos[b + lane] = __ldg(pos + v);
+        if (lane < n) spos[b + dst] = __ldg(pos + v);
         return;
     }
     // crowded cell (> 32 particles): serial insertion sort by one lane, then a strided gather

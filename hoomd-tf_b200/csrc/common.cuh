@@ -53,6 +53,8 @@ struct htf_ctx {
     int64_t sel_cap;
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
     int tile_flag_cap;
+    int *d_flag_count;            // two counters (inside d_stats) of tiles the tile kernel flagged, used in turn
+    int flag_parity;
     float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
     int64_t nlist_scratch_elems;
     // RDF threshold table (device) and the key it was built for

@@ -31,6 +31,10 @@
 #include "common.cuh"
 
 #include <math_constants.h>
+#ifdef HTF_DEBUG_FLAGS
+#include <cstdio>
+#include <vector>
+#endif
 
 namespace {
 
@@ -55,6 +59,8 @@ struct NlistParams {
     int cap;             // per-warp window capacity (candidates), multiple of 32, <= 32768
     int cap_tile;        // tile kernel: candidates staged per block
     unsigned char *tile_flag;   // [tiles]: 1 = the tile kernel left this tile to the per-cell kernel
+    int *flag_count;            // tiles flagged by this launch's tile kernel (nullptr: unknown, always scan)
+    int *flag_count_next;       // the other parity's counter, zeroed by the per-cell kernel for the next launch
     int use_flags;       // per-cell kernel: process only cells of flagged tiles
     float4 *out;
     int *idx_out;
@@ -141,6 +147,18 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
+}
+
+// same accesses without the compiler barrier, for read-only staged data / write-only lists inside one phase
+__device__ __forceinline__ float4 lds_f4_ro(unsigned addr)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16_nb(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
 }
 
 struct RowState {
@@ -311,7 +329,11 @@ __device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_w
 }
 
 constexpr int TILE = HTF_TILE;    // cells per block along x in the tile kernel (= warps per block)
+#ifdef HTF_EXP_ROWS
+constexpr int NPMAX = 192;        // piece table capacity: (TILE + 2) * 9 <= NPMAX; rows kernel: (cells + 2) * 9 <= NPMAX
+#else
 constexpr int NPMAX = 128;        // piece table capacity: (TILE + 2) * 9 <= NPMAX  ->  TILE <= 12
+#endif
 constexpr int TILE_HDR = (2 * NPMAX + 32) * 4;   // bytes: piece table end[NPMAX] + adj[NPMAX] + colstart[24] + warp totals[8]
 static_assert((TILE + 2) * 9 <= NPMAX && TILE * 32 >= (TILE + 2) * 9 && TILE + 3 <= 24, "tile size");
 
@@ -565,6 +587,12 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
         }
         return;
     }
+    if (p.flag_count) {
+        // nothing flagged by the tile kernel (the usual case): leave at once
+        const int nflag = *reinterpret_cast<volatile const int *>(p.flag_count);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *p.flag_count_next = 0;
+        if (nflag == 0) return;
+    }
     const int nx = p.g.n[0], tiles_x = (nx + TILE - 1) / TILE;
     const int per_layer = tiles_x * p.g.n[1];
     const int ntiles_win = per_layer * p.g.zcount;                  // tiles of the z-window only
@@ -658,7 +686,10 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
         const int wl = xs ? colstart[w + 3] - colstart[w] : mblock;
         fits = fits && wl <= capW;
     }
-    if (tid == 0) p.tile_flag[bid] = fits ? 0 : 1;
+    if (tid == 0) {
+        p.tile_flag[bid] = fits ? 0 : 1;
+        if (!fits && p.flag_count) atomicAdd(p.flag_count, 1);
+    }
     if (!fits) return;                                          // block-uniform
     const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
     if (!full) {
@@ -827,6 +858,351 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-per-lane kernel -- an evaluated alternative, compiled only with -DHTF_EXP_ROWS (parity-green, but
+// 0.59 ms against the tile kernel's 0.43 ms at 1M x 64: 324 instead of 388 warp-instructions per row, yet the
+// per-block staging chain and 30 KB of shared memory per 64 rows hold it at 12 warps per SM and IPC 2.1).  A block builds up to 32*ROWS_NW CONSECUTIVE rows of the cell-sorted
+// order, all from one x-row of cells; a lane owns one row.  The stencil of the cells the block touches is staged
+// once (column-major, TMA bulk copies, as in the tile kernel), so a lane's 27-cell stencil is one contiguous
+// window of the shared buffer:
+//   test : every lane walks ITS window candidate by candidate (one LDS.128 per lane and candidate; lanes of
+//          the same cell read the same address) and appends the window-relative index of each hit to its own
+//          row list -- the list IS the row in slot order, so there is no ballot, no scan and no slot map;
+//   emit : the warp then writes its rows one after the other, lane s deriving (d, type) for slots s, s+32, ...
+//          from the row's list: contiguous coalesced 16-byte stores, zero padding included.
+// Row lists are [slot][33] u16 (stride 33 keeps both the lane-wise appends and the slot-wise reads free of
+// bank conflicts).  A list saturates at K entries; rows that reach K, segments whose stencil does not fit the
+// buffer and x-rows with more rows than the grid has segments flag their tiles and are rebuilt exactly (modulo-K
+// rule included) by the per-cell kernel, like tiles the tile kernel gives up on.
+#ifndef HTF_ROWS_NW
+#define HTF_ROWS_NW 2
+#endif
+constexpr int ROWS_NW = HTF_ROWS_NW;
+constexpr int ROWS_PB = 32 * ROWS_NW;              // rows per block
+constexpr int ROWS_MAXCELLS = NPMAX / 9 - 2;       // cells a segment may span: (cells + 2) * 9 pieces <= NPMAX
+constexpr int ROWS_SLACK = 128;                    // readable sentinels behind the staged data: lanes run to the warp's longest window
+constexpr int ROWS_HDR = (2 * NPMAX + 24 + 8 + 24) * 4;   // piece table | colstart[24] | misc[8] (mbarrier at +4) | cs[24]
+static_assert(ROWS_MAXCELLS + 3 <= 24 && ROWS_HDR % 16 == 0 && NPMAX % 32 == 0, "rows kernel header");
+
+__device__ __forceinline__ size_t rows_list_bytes(int K) { return (((size_t)(K + 1) * 66) + 15) & ~(size_t)15; }
+
+// one candidate against this lane's row; appends to the lane's list on a hit
+template <bool WRAP, bool MAPPED>
+__device__ __forceinline__ void rows_test_one(const NlistParams &p, const float4 &q, int c, int wlen, int self_rel,
+                                              const float4 &pi, f32x2 pxy, unsigned &ha, unsigned ha_dump)
+{
+    const f32x2 dxy = sub2(pack2(q.x, q.y), pxy);
+    float dz = __fsub_rn(q.z, pi.z);
+    float xx, yy, zz;
+    if (WRAP) {
+        float dx, dy;
+        unpack2(dxy, dx, dy);
+        dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
+        dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+        dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
+        xx = __fmul_rn(dx, dx); yy = __fmul_rn(dy, dy);
+    } else {
+        unpack2(mul2(dxy, dxy), xx, yy);
+    }
+    zz = __fmul_rn(dz, dz);
+    const float rsq = __fadd_rn(__fadd_rn(xx, yy), zz);
+    bool hit = (rsq <= p.rc2) & (c != self_rel) & (c < wlen);
+    if (MAPPED) hit = hit && (((int)q.w >= p.map_type_start) == ((int)pi.w >= p.map_type_start));
+    if (hit) {
+        sts_u16_nb(ha, (unsigned)c);
+        ha = min(ha + 66u, ha_dump);
+    }
+}
+
+// The window walk, four candidates per step.  ptxas cannot move a shared load above an earlier shared store (it has
+// no alias information), so the next group's loads are issued by hand before this group's list appends.
+template <bool WRAP, bool MAPPED>
+__device__ __forceinline__ unsigned rows_test(const NlistParams &p, unsigned cbase, int maxlen, int wlen, int self_rel,
+                                              const float4 &pi, unsigned ha, unsigned ha_dump)
+{
+    const f32x2 pxy = pack2_pinned(pi.x, pi.y);
+    constexpr int G = 4;
+    float4 q[G], n[G];
+#pragma unroll
+    for (int u = 0; u < G; u++) q[u] = lds_f4_ro(cbase + (unsigned)u * 16u);        // sentinels make any over-read harmless
+#pragma unroll 1
+    for (int c = 0; c < maxlen; c += G) {
+#pragma unroll
+        for (int u = 0; u < G; u++) n[u] = lds_f4_ro(cbase + (unsigned)(c + G + u) * 16u);
+#pragma unroll
+        for (int u = 0; u < G; u++) rows_test_one<WRAP, MAPPED>(p, q[u], c + u, wlen, self_rel, pi, pxy, ha, ha_dump);
+#pragma unroll
+        for (int u = 0; u < G; u++) q[u] = n[u];
+    }
+    return ha;
+}
+
+template <bool WITH_IDX, bool MAPPED>
+__global__ void __launch_bounds__(ROWS_PB) nlist_rows_kernel(const NlistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, capB = p.cap_tile;
+    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [NPMAX] inclusive prefix of piece lengths
+    int *ptab_adj = ptab_end + NPMAX;                           // [NPMAX] source slot - staged index
+    int *colstart = ptab_adj + NPMAX;                           // [<= ROWS_MAXCELLS + 3] staged offset of each column
+    int *misc = colstart + 24;                                  // [0] first cell, [1] last cell, [2] fits, [4..5] mbarrier
+    int *cs = misc + 8;                                         // [<= ROWS_MAXCELLS + 1] sorted-order start of the segment's cells
+    float4 *cand = reinterpret_cast<float4 *>(smem_raw + ROWS_HDR);
+    int *candidx = reinterpret_cast<int *>(cand + capB + ROWS_SLACK);
+    unsigned char *lists = WITH_IDX ? reinterpret_cast<unsigned char *>(candidx + capB + ROWS_SLACK)
+                                    : reinterpret_cast<unsigned char *>(candidx);
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
+    const unsigned hl_s = (unsigned)__cvta_generic_to_shared(lists) + (unsigned)(rows_list_bytes(K) * warp);
+    const unsigned stage_bar = (unsigned)__cvta_generic_to_shared(misc + 4);
+
+    const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
+    const int tiles_x = (nx + TILE - 1) / TILE;                 // flags use the tile kernel's tiling
+    const int cy = blockIdx.y, cz = (p.g.z0 + (int)blockIdx.z) % nz;
+    const int c_base = (cz * ny + cy) * nx;
+    unsigned char *flag_row = p.tile_flag + (size_t)(cz * ny + cy) * tiles_x;
+    const int R0 = __ldg(p.cell_start + c_base), R1 = __ldg(p.cell_start + c_base + nx);
+    const int nrows = R1 - R0;
+    if (nrows == 0) return;
+    const int nseg = (nrows + ROWS_PB - 1) / ROWS_PB;
+    if (nseg > (int)gridDim.x) {                                // denser than the launch was sized for: whole x-row to the fallback
+#ifdef HTF_DEBUG_FLAGS
+        if (tid == 0 && blockIdx.x == 0 && cy < 2) printf("flag A: nseg %d grid %d nrows %d cy %d cz %d\n", nseg, gridDim.x, nrows, cy, cz);
+#endif
+        if (blockIdx.x == 0)
+            for (int t = tid; t < tiles_x; t += ROWS_PB) flag_row[t] = 1;
+        return;
+    }
+    const int seg = blockIdx.x;
+    if (seg >= nseg) return;
+    const int rb = R0 + (int)((long long)seg * nrows / nseg), re = R0 + (int)((long long)(seg + 1) * nrows / nseg);
+
+    if (!(p.row_lo == 0 && p.row_hi == p.n_all)) {
+        // sharded build: skip the segment (before staging anything) when none of its rows is local
+        bool any = false;
+        for (int r = rb + tid; r < re; r += ROWS_PB) {
+            const int o = __ldg(p.sorted_idx + r);
+            any |= (o >= p.row_lo && o < p.row_hi);
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+
+    // ---- which cells does the segment touch ----
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stage_bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < nx; c += ROWS_PB) {
+        const int a = __ldg(p.cell_start + c_base + c), b = __ldg(p.cell_start + c_base + c + 1);
+        if (a <= rb && rb < b) misc[0] = c;
+        if (a < re && re <= b) misc[1] = c;
+    }
+    __syncthreads();
+    const int cx_first = misc[0], cx_last = misc[1];
+    const int ncs = cx_last - cx_first + 1;
+    if (ncs > ROWS_MAXCELLS) {                                  // sparse x-row: too many cells for the piece table
+#ifdef HTF_DEBUG_FLAGS
+        if (tid == 0 && cy < 2) printf("flag B: ncs %d first %d last %d rb %d re %d\n", ncs, cx_first, cx_last, rb, re);
+#endif
+        for (int t = cx_first / TILE + tid; t <= cx_last / TILE; t += ROWS_PB) flag_row[t] = 1;
+        return;
+    }
+    const int nly = min(ny, 3), nlz = min(nz, 3), nyz = nly * nlz;
+    const int ncol = ncs + 2, npieces = ncol * nyz;
+    if (tid <= ncs) cs[tid] = __ldg(p.cell_start + c_base + cx_first + tid);
+
+    // ---- warp 0: piece table (piece (col, j) = one stencil cell), fit check, one TMA bulk copy per piece ----
+    if (warp == 0) {
+        int pl[NPMAX / 32], pb[NPMAX / 32], incl[NPMAX / 32];
+        int carry = 0;
+#pragma unroll
+        for (int k = 0; k < NPMAX / 32; k++) {
+            const int q = lane + 32 * k;
+            pl[k] = 0; pb[k] = 0;
+            if (q < npieces) {
+                const int col = q / nyz, j = q - col * nyz, jy = j % nly, jz = j / nly;
+                int sx = cx_first - 1 + col;
+                sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
+                int sy = ny <= 3 ? jy : cy + jy - 1;
+                sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
+                int sz = nz <= 3 ? jz : cz + jz - 1;
+                sz = sz < 0 ? sz + nz : (sz >= nz ? sz - nz : sz);
+                const int c0 = (sz * ny + sy) * nx + sx;
+                pb[k] = __ldg(p.cell_start + c0);
+                pl[k] = __ldg(p.cell_start + c0 + 1) - pb[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NPMAX / 32; k++) {
+            const int q = lane + 32 * k;
+            int v = pl[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(HTF_FULL, v, o);
+                if (lane >= o) v += t;
+            }
+            v += carry;
+            incl[k] = v;
+            carry = __shfl_sync(HTF_FULL, v, 31);
+            ptab_end[q] = v;
+            ptab_adj[q] = pb[k] - (v - pl[k]);
+            if (q < npieces && q % nyz == 0) colstart[q / nyz] = v - pl[k];
+        }
+        const int mblock = carry;
+        const bool fits = mblock <= capB;
+        if (lane == 0) { colstart[ncol] = mblock; misc[2] = fits ? 1 : 0; }
+        if (fits) {
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stage_bar), "r"((unsigned)mblock * 16u) : "memory");
+#pragma unroll
+            for (int k = 0; k < NPMAX / 32; k++)
+                if (pl[k] > 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(cand_s + (unsigned)(incl[k] - pl[k]) * 16u), "l"(p.spos + pb[k]), "r"((unsigned)pl[k] * 16u),
+                                   "r"(stage_bar) : "memory");
+        }
+    }
+    __syncthreads();
+    if (!misc[2]) {                                             // stencil larger than the buffer: dense cluster -> fallback
+#ifdef HTF_DEBUG_FLAGS
+        if (tid == 0 && cy < 2) printf("flag C: mblock %d capB %d ncs %d\n", colstart[ncol], capB, ncs);
+#endif
+        for (int t = cx_first / TILE + tid; t <= cx_last / TILE; t += ROWS_PB) flag_row[t] = 1;
+        return;
+    }
+    const int mblock = colstart[ncol];
+    if (WITH_IDX) {
+        for (int q = warp; q < npieces; q += ROWS_NW) {
+            const int qend = ptab_end[q], qadj = ptab_adj[q];
+            const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
+            for (int t = qbeg + lane; t < qend; t += 32) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    for (int t = tid; t < ROWS_SLACK; t += ROWS_PB) cand[mblock + t] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+
+    // ---- this lane's row, its cell and its window (overlaps the TMA latency) ----
+    const int row = rb + warp * 32 + lane;
+    bool active = row < re;
+    int orig = -1;
+    if (active) {
+        orig = __ldg(p.sorted_idx + row);
+        active = orig >= p.row_lo && orig < p.row_hi;
+    }
+    int w = -1;
+    for (int j = 0; j < ncs; j++) w += (row >= cs[j]) ? 1 : 0;
+    w = max(0, min(w, ncs - 1));
+    const int ws = colstart[w], wlen = colstart[w + 3] - ws;
+    const int ps = (w + 1) * nyz + (nz <= 3 ? cz : 1) * nly + (ny <= 3 ? cy : 1);      // the row's own cell: piece (w + 1, centre)
+    const int self_rel = active ? ptab_end[ps - 1] + (row - cs[w]) - ws : -1;
+    const int cx = cx_first + w;
+    const bool wrapflag = !((nx >= 5 && cx >= 1 && cx <= nx - 2) && (ny >= 5 && cy >= 1 && cy <= ny - 2) &&
+                            (nz >= 5 && cz >= 1 && cz <= nz - 2));
+    int maxlen = active ? wlen : 0, maxend = active ? ws + wlen : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(HTF_FULL, maxlen, o));
+    maxend = active ? ws + maxlen : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxend = max(maxend, __shfl_xor_sync(HTF_FULL, maxend, o));
+    const bool anywrap = __any_sync(HTF_FULL, active && wrapflag);
+
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(stage_bar) : "memory");
+    __syncthreads();
+    if (maxlen == 0) return;                                    // no row of this warp belongs to the shard
+    if (maxend + 8 > mblock + ROWS_SLACK) {                     // a lane would read past the sentinels (wildly uneven cells)
+#ifdef HTF_DEBUG_FLAGS
+        if (lane == 0 && cy < 2) printf("flag D: maxend %d mblock %d maxlen %d\n", maxend, mblock, maxlen);
+#endif
+        if (active) flag_row[cx / TILE] = 1;
+        return;
+    }
+
+    // ---- test ----
+    const unsigned cbase = cand_s + (unsigned)ws * 16u;
+    float4 pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);                   // inactive lanes never hit
+    if (active) pi = lds_f4(cbase + (unsigned)self_rel * 16u);
+    const unsigned ha0 = hl_s + (unsigned)lane * 2u, ha_dump = ha0 + (unsigned)K * 66u;
+    unsigned ha;
+    if (!anywrap) ha = rows_test<false, MAPPED>(p, cbase, maxlen, wlen, self_rel, pi, ha0, ha_dump);
+    else ha = rows_test<true, MAPPED>(p, cbase, maxlen, wlen, self_rel, pi, ha0, ha_dump);
+    const int cnt = (int)((ha - ha0) / 66u);
+#ifdef HTF_DEBUG_FLAGS
+    if (active && cnt >= K && cy < 2) printf("flag E: cnt %d row %d w %d ws %d wlen %d self %d cx %d cy %d cz %d ncs %d\n", cnt, row, w, ws, wlen, self_rel, cx, cy, cz, ncs);
+#endif
+    if (active && cnt >= K) {                                   // full or overflowing row: exact modulo-K rule in the fallback
+        flag_row[cx / TILE] = 1;
+        active = false;
+    }
+    if (active && p.count_out) p.count_out[orig - p.row_lo] = cnt;
+    __syncwarp();
+
+    // ---- emit: one row after the other, lanes = slots ----
+    unsigned todo = __ballot_sync(HTF_FULL, active);
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int cnt_r = __shfl_sync(HTF_FULL, cnt, r);
+        const unsigned cb_r = __shfl_sync(HTF_FULL, cbase, r);
+        const int self_r = __shfl_sync(HTF_FULL, self_rel, r);
+        const int orig_r = __shfl_sync(HTF_FULL, orig, r);
+        const bool wrap_r = __shfl_sync(HTF_FULL, wrapflag ? 1 : 0, r) != 0;
+        const float4 pr = lds_f4(cb_r + (unsigned)self_r * 16u);
+        const size_t orow = (size_t)(orig_r - p.row_lo);
+        float4 *dst = p.out + orow * K + lane;
+        unsigned la = hl_s + (unsigned)r * 2u + (unsigned)lane * 66u;
+        // two slots per step, both index loads and both candidate loads issued before either is used
+        for (int sl = lane; sl < K; sl += 64, dst += 64, la += 64u * 66u) {
+            const bool v0 = sl < cnt_r, v1 = sl + 32 < cnt_r, in1 = sl + 32 < K;
+            const unsigned c0 = v0 ? lds_u16(la) : 0u;
+            const unsigned c1 = v1 ? lds_u16(la + 32u * 66u) : 0u;
+            const float4 q0 = lds_f4(cb_r + c0 * 16u);
+            const float4 q1 = lds_f4(cb_r + c1 * 16u);
+            float dx0 = __fsub_rn(q0.x, pr.x), dy0 = __fsub_rn(q0.y, pr.y), dz0 = __fsub_rn(q0.z, pr.z);
+            float dx1 = __fsub_rn(q1.x, pr.x), dy1 = __fsub_rn(q1.y, pr.y), dz1 = __fsub_rn(q1.z, pr.z);
+            if (wrap_r) {
+                dz0 = wrap_axis(dz0, -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy0 = wrap_axis(dy0, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx0 = wrap_axis(dx0, -p.g.half[0], p.g.half[0], p.g.L[0]);
+                dz1 = wrap_axis(dz1, -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy1 = wrap_axis(dy1, -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx1 = wrap_axis(dx1, -p.g.half[0], p.g.half[0], p.g.L[0]);
+            }
+            dst[0] = v0 ? make_float4(dx0, dy0, dz0, q0.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in1) dst[32] = v1 ? make_float4(dx1, dy1, dz1, q1.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (WITH_IDX) {
+                const int *ci = candidx + (cb_r - cand_s) / 16u;
+                p.idx_out[orow * K + sl] = v0 ? ci[c0] : -1;
+                if (in1) p.idx_out[orow * K + sl + 32] = v1 ? ci[c1] : -1;
+            }
+        }
+    }
+}
+
+template <bool WITH_IDX, bool MAPPED>
+cudaError_t launch_rows_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nlist_rows_kernel<WITH_IDX, MAPPED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    nlist_rows_kernel<WITH_IDX, MAPPED><<<grid, ROWS_PB, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+size_t rows_block_bytes(int capB, int K, bool with_idx)
+{
+    size_t b = ROWS_HDR + (size_t)(capB + ROWS_SLACK) * 16;
+    if (with_idx) b += (size_t)(capB + ROWS_SLACK) * 4;
+    b += (size_t)ROWS_NW * ((((size_t)(K + 1) * 66) + 15) & ~(size_t)15);
+    return b;
+}
+
 template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_tile_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
@@ -920,13 +1296,58 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     const bool mapped = ctx->map_type_start >= 0;
     cudaError_t e;
 
-    // ---- pass 1: tile kernel (TILE cells per block share one staged neighbourhood) ----
+    // ---- pass 1: row-per-lane kernel (grids with >= 4 cells in x), else the tile kernel ----
     const int tiles_x = (g.n[0] + TILE - 1) / TILE;
     const int ntiles = tiles_x * g.n[1] * g.n[2];
     p.use_flags = 0;
     p.tile_flag = nullptr;
+    p.flag_count = nullptr;
+    p.flag_count_next = nullptr;
     bool tiled = false;
-    {
+#ifdef HTF_EXP_ROWS
+    if (g.n[0] >= 4 && g.n[1] <= 65535 && g.n[2] <= 65535 && cap <= 32768) {
+        const int nyz = min(g.n[1], 3) * min(g.n[2], 3);
+        const double cm = cell_mean > 0.05 ? cell_mean : 0.05;
+        int ncells = (int)ceil((double)ROWS_PB / cm) + 2;                       // cells a full segment can span (two partial ones)
+        if (ncells > ROWS_MAXCELLS) ncells = ROWS_MAXCELLS;
+        const double bmean = (double)(ncells + 2) * nyz * cm;
+        int capB = (int)(bmean + 5.0 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
+        capB = (capB + 31) / 32 * 32;
+        // rows per x-row of cells: a lattice-like fluid puts 2x2 or 3x3 lattice lines into a cell row, so allow twice
+        // the mean (blocks beyond an x-row's own segment count exit at once; a denser x-row goes to the fallback)
+        const double xrow = 2.0 * (double)g.n[0] * cm;
+        const int segs = (int)((xrow + 5.0 * sqrt(xrow > 1.0 ? xrow : 1.0)) / ROWS_PB) + 1;
+        const size_t bytes = rows_block_bytes(capB, p.K, with_idx);
+        if (capB <= 32768 && bytes <= 100 * 1024 && segs <= 65535) {
+            if ((e = htf_ensure_tile_flags(ctx, ntiles)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(ctx->d_tile_flag, 0, (size_t)ntiles, st)) != cudaSuccess) return e;
+            p.cap = cap;
+            p.cap_tile = capB;
+            p.tile_flag = ctx->d_tile_flag;
+            ctx->launches += 1;
+            const dim3 rg((unsigned)segs, (unsigned)g.n[1], (unsigned)g.zcount);
+            e = with_idx ? (mapped ? launch_rows_variant<true, true>(p, rg, bytes, st)
+                                   : launch_rows_variant<true, false>(p, rg, bytes, st))
+                         : (mapped ? launch_rows_variant<false, true>(p, rg, bytes, st)
+                                   : launch_rows_variant<false, false>(p, rg, bytes, st));
+            if (e != cudaSuccess) return e;
+            tiled = true;
+#ifdef HTF_DEBUG_FLAGS
+            {
+                std::vector<unsigned char> h(ntiles);
+                cudaMemcpyAsync(h.data(), ctx->d_tile_flag, ntiles, cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                int nf = 0, firstf = -1;
+                for (int i = 0; i < ntiles; i++) if (h[i]) { nf++; if (firstf < 0) firstf = i; }
+                static int printed = 0;
+                if (printed++ < 3) printf("[rows] flagged tiles %d of %d (first %d: tx %d cy %d cz %d) capB %d segs %d\n", nf, ntiles, firstf,
+                                          firstf % tiles_x, (firstf / tiles_x) % g.n[1], firstf / tiles_x / g.n[1], capB, segs);
+            }
+#endif
+        }
+    }
+#endif
+    if (!tiled) {
         const int ncol = g.n[0] >= 3 ? min(TILE, g.n[0]) + 2 : g.n[0];
         const double bmean = (double)ncol * min(g.n[1], 3) * min(g.n[2], 3) * cell_mean;
         int capB = (int)(bmean + 5.0 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
@@ -937,6 +1358,10 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             p.cap = cap;
             p.cap_tile = capB;
             p.tile_flag = ctx->d_tile_flag;
+            // two counters in turn: this launch counts into one, its per-cell pass zeroes the other for the next launch
+            p.flag_count = ctx->d_flag_count + (ctx->flag_parity & 1);
+            p.flag_count_next = ctx->d_flag_count + ((ctx->flag_parity + 1) & 1);
+            ctx->flag_parity ^= 1;
             ctx->launches += 1;
             const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)g.zcount);
             e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, tg, bytes, st)
