@@ -315,6 +315,30 @@ int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float t
     return HTF_OK;
 }
 
+int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold_lo, float threshold_hi,
+                       float *d_out_lo, float *d_out_hi, int64_t capacity, int32_t *d_counts, int32_t *d_overflow,
+                       void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n < 0 || n > 1000000000LL || capacity < 1 || capacity > 2000000000LL || axis < 0 || axis > 2 || !d_out_lo ||
+        !d_out_hi || (n > 0 && !d_pos)) {
+        set_err(ctx, "htf_pack_halo_pair: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    const int64_t need = 2 * ((n + 255) / 256) + 2;
+    if (need > ctx->sel_cap) {
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_cnt, (size_t)need))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_off, (size_t)need))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_sel_sums, (size_t)need / 1024 + 4))) return rc;
+        ctx->sel_cap = need;
+    }
+    HTF_CUDA(ctx, htf_launch_select_pair(ctx, reinterpret_cast<const float4 *>(d_pos), n, axis, threshold_lo, threshold_hi,
+                                         reinterpret_cast<float4 *>(d_out_lo), reinterpret_cast<float4 *>(d_out_hi),
+                                         (int)capacity, d_counts, d_overflow, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_set_mapped_nlist(htf_ctx *ctx, int map_type_start)
 {
     int rc = check_ctx(ctx);

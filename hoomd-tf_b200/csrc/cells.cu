@@ -267,6 +267,66 @@ __global__ void __launch_bounds__(256) select_scatter_kernel(const float4 *__res
     }
 }
 
+// ---- both slab faces in one pass: block_cnt[b] = particles of block b below thr_lo, block_cnt[nb + b] = above thr_hi ----
+__global__ void __launch_bounds__(256) select_count2_kernel(const float4 *__restrict__ pos, int n, int axis, float thr_lo,
+                                                            float thr_hi, int nb, int *__restrict__ block_cnt)
+{
+    __shared__ int wsum[16];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) p = __ldg(pos + i);
+    const unsigned ml = __ballot_sync(HTF_FULL, i < n && beyond<true>(p, axis, thr_lo));
+    const unsigned mh = __ballot_sync(HTF_FULL, i < n && beyond<false>(p, axis, thr_hi));
+    if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = __popc(ml); wsum[8 + (threadIdx.x >> 5)] = __popc(mh); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += wsum[8 * threadIdx.x + w];
+        block_cnt[threadIdx.x * nb + blockIdx.x] = t;
+    }
+}
+
+// block_off = exclusive scan of block_cnt[2 nb]; *total = its grand total.  Threads past n only pad: every entry of
+// the two buffers beyond its face's count gets the sentinel, so no separate fill pass is needed.
+__global__ void __launch_bounds__(256) select_scatter2_kernel(const float4 *__restrict__ pos, int n, int axis, float thr_lo,
+                                                              float thr_hi, int nb, const int *__restrict__ block_off,
+                                                              const int *__restrict__ total, float4 *__restrict__ out_lo,
+                                                              float4 *__restrict__ out_hi, int cap, int *__restrict__ counts,
+                                                              int *__restrict__ overflow)
+{
+    __shared__ int wsum[16];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int tot_lo = block_off[nb], tot_hi = *total - tot_lo;
+    if (i == 0 && counts) { counts[0] = tot_lo; counts[1] = tot_hi; }
+    if (i < cap) {
+        const float4 far = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        if (i >= tot_lo) out_lo[i] = far;
+        if (i >= tot_hi) out_hi[i] = far;
+    }
+    if (blockIdx.x >= nb) return;                               // padding-only blocks (cap > n)
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) p = __ldg(pos + i);
+    const bool sl = i < n && beyond<true>(p, axis, thr_lo), sh = i < n && beyond<false>(p, axis, thr_hi);
+    const unsigned ml = __ballot_sync(HTF_FULL, sl), mh = __ballot_sync(HTF_FULL, sh);
+    if (lane == 0) { wsum[w] = __popc(ml); wsum[8 + w] = __popc(mh); }
+    __syncthreads();
+    int bl = block_off[blockIdx.x], bh = block_off[nb + blockIdx.x] - tot_lo;
+    for (int q = 0; q < w; q++) { bl += wsum[q]; bh += wsum[8 + q]; }
+    const unsigned below = (1u << lane) - 1u;
+    if (sl) {
+        const int k = bl + __popc(ml & below);
+        if (k < cap) out_lo[k] = p;
+        else if (overflow) atomicMax(overflow, k + 1);
+    }
+    if (sh) {
+        const int k = bh + __popc(mh & below);
+        if (k < cap) out_hi[k] = p;
+        else if (overflow) atomicMax(overflow, k + 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_sentinel_kernel(float4 *__restrict__ out, int cap)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -328,6 +388,28 @@ cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n64, int 
     return cudaGetLastError();
 }
 
+
+cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64, int axis, float thr_lo, float thr_hi,
+                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st)
+{
+    const int n = (int)n64;
+    const int nb = (n + 255) / 256;
+    int *cnt = ctx->d_sel_cnt, *off = ctx->d_sel_off, *sums = ctx->d_sel_sums;
+    if (nb > 0) select_count2_kernel<<<nb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, cnt);
+    const int m = 2 * nb + 1;                                   // one extra (zero) entry so that off[2 nb] exists
+    cudaError_t e = cudaMemsetAsync(cnt + 2 * nb, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    int *total = sums + ntiles + 1;
+    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, ntiles, total);
+    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums, off);
+    const int gb = max(nb, (cap + 255) / 256);
+    select_scatter2_kernel<<<gb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, off, total, out_lo, out_hi, cap, d_counts,
+                                               d_overflow);
+    ctx->launches += 5;
+    return cudaGetLastError();
+}
 
 // Synchronising (one cudaMemcpy): called by the nlist launcher only when the context has no valid
 // calibration for the current box / cutoff / region of interest / particle count.

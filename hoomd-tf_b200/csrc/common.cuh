@@ -81,6 +81,8 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
 cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st);
+cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr_lo, float thr_hi,
+                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st);
 cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,
                               float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st);
 

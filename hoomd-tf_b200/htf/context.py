@@ -87,6 +87,18 @@ class HtfContext:
                                         _ptr(out), out.shape[0], _ptr(count), _ptr(self._overflow), self._stream()))
         return out
 
+    def pack_halo_pair(self, pos, axis, threshold_lo, threshold_hi, out_lo, out_hi, counts=None):
+        """Both slab faces in one pass: ``pos[axis] < threshold_lo`` -> out_lo, ``> threshold_hi`` -> out_hi."""
+        _check_dev_f32(pos, "positions", 4)
+        _check_dev_f32(out_lo, "halo buffer", 4)
+        _check_dev_f32(out_hi, "halo buffer", 4)
+        if out_lo.shape[0] != out_hi.shape[0]:
+            raise ValueError("the two halo buffers must have the same capacity")
+        self._ck(self.lib.htf_pack_halo_pair(self._h, _ptr(pos), pos.shape[0], int(axis), float(threshold_lo),
+                                             float(threshold_hi), _ptr(out_lo), _ptr(out_hi), out_lo.shape[0],
+                                             _ptr(counts), _ptr(self._overflow), self._stream()))
+        return out_lo, out_hi
+
     def set_mapped_nlist(self, map_type_start):
         self._ck(self.lib.htf_set_mapped_nlist(self._h, -1 if map_type_start is None else int(map_type_start)))
 

@@ -106,8 +106,7 @@ class SlabExchange:
         if self.world == 1:
             return self.local
         own = self.own
-        self.ctx.pack_halo(own, self.axis, self.lo_thr, True, self.send_lo)
-        self.ctx.pack_halo(own, self.axis, self.hi_thr, False, self.send_hi)
+        self.ctx.pack_halo_pair(own, self.axis, self.lo_thr, self.hi_thr, self.send_lo, self.send_hi)
         prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         a = self.local[self.n_local:self.n_local + self.cap]
         b = self.local[self.n_local + self.cap:]

@@ -364,6 +364,13 @@ def test_slab_halo_exchange_emulated(oracle_mod):
         s_lo = c.pack_halo(own, 2, lo_face + width, True, torch.empty((cap, 4), device="cuda"))
         s_hi = c.pack_halo(own, 2, hi_face - width, False, torch.empty((cap, 4), device="cuda"))
         assert c.overflow() == 0
+        # the one-pass two-face packer (what SlabExchange uses) must produce the same two buffers, bit for bit
+        counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+        p_lo, p_hi = c.pack_halo_pair(own, 2, lo_face + width, hi_face - width, torch.empty((cap, 4), device="cuda"),
+                                      torch.empty((cap, 4), device="cuda"), counts)
+        assert torch.equal(p_lo, s_lo) and torch.equal(p_hi, s_hi) and c.overflow() == 0
+        z = pos[a:b, 2]
+        assert counts.cpu().tolist() == [int((z < np.float32(lo_face + width)).sum()), int((z > np.float32(hi_face - width)).sum())]
         ctxs.append((c, own)); sends.append((s_lo, s_hi))
     # stable packing: the selected particles appear in index order, the rest is sentinel
     s_lo0 = sends[0][0].cpu().numpy()
