@@ -41,6 +41,13 @@ def parse():
     ap.add_argument("--model", default="lj", choices=["lj", "mlp"],
                     help="lj: closed-form LJ + virial (the headline path); mlp: BASELINE config 3's pairwise-MLP force "
                          "field on the tensor cores (forces + energy)")
+    ap.add_argument("--skin", type=float, default=0.0,
+                    help="> 0: buffered neighbor lists like HOOMD's r_buff (the reference's own split): search with "
+                         "r_cut + skin every --rebuild-every steps, distance filter every step; the particles then "
+                         "move ballistically each step (|v| dt = --step-length) so that rebuilds are really needed")
+    ap.add_argument("--rebuild-every", type=int, default=10)
+    ap.add_argument("--step-length", type=float, default=0.0087,
+                    help="displacement per step in the --skin workload (LJ liquid at T*=1, dt=0.005: 0.005*sqrt(3))")
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
                     help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
@@ -272,7 +279,50 @@ def run_b200(args):
         packed = ctx.mlp_pack(torch.from_numpy(mlp_raw_parameters()).to(dev))
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    skin = args.skin > 0.0
+    if skin:
+        if world > 1:
+            raise SystemExit("--skin is single-GPU in this round (the halo layout changes every step)")
+        ctx.skin_configure(args.skin)
+        g = torch.Generator(device="cpu").manual_seed(7)
+        v = torch.randn((n, 4), generator=g)
+        v[:, 3] = 0.0
+        v[:, :3] *= args.step_length / v[:, :3].norm(dim=1, keepdim=True)
+        d_vel = v.to(dev)
+        d_lo = torch.tensor(list(lo) + [0.0], dtype=torch.float32, device=dev)
+        d_L = torch.tensor([hi[a] - lo[a] for a in range(3)] + [1.0], dtype=torch.float32, device=dev)
+        skin_state = {"t": 0, "rebuilds": 0}
+
+    def skin_step(marks):
+        # the particles move (ballistic, |v| dt = --step-length); every --rebuild-every steps they are wrapped back
+        # into the box and the candidate lists (r_cut + skin) are rebuilt; the distance filter runs every step
+        d_pos_all.add_(d_vel)
+        if skin_state["t"] % args.rebuild_every == 0:
+            wrapped = torch.remainder(d_pos_all - d_lo, d_L) + d_lo
+            wrapped[:, 3] = d_pos_all[:, 3]
+            d_pos_all.copy_(wrapped)
+            ctx.skin_rebuild(d_pos_all)
+            skin_state["rebuilds"] += 1
+        skin_state["t"] += 1
+        if marks is not None:
+            marks[0].record()
+        ctx.skin_nlist(d_pos_all, out=nl)
+        if marks is not None:
+            marks[1].record()
+
     def step(marks=None):
+        if skin:
+            skin_step(marks)
+            if packed is not None:
+                ctx.mlp_forces(nl, packed, r_cut, out=fe)
+            elif bins is not None:
+                bins.zero_()
+                ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
+            else:
+                ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
+            if marks is not None:
+                marks[2].record()
+            return
         if halo:
             xch.exchange()                                            # the path's one exchange step (2 faces)
         elif world > 1:
@@ -309,6 +359,7 @@ def run_b200(args):
 
     # ---- timed region: exactly --steps steps, device timed, clocks sampled meanwhile ----
     marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    skin_t0 = skin_state["t"] if skin else 0
     line0 = sampler.lines() if sampler else 0
     launches0 = ctx.launches
     e0, e1 = ev(), ev()
@@ -320,6 +371,9 @@ def run_b200(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
+    assert ctx.overflow() == 0, "neighbor list overflowed K: the run is void"
+    if skin:
+        assert ctx.skin_status() == (0, 0), "a buffered list was used past skin/2 or overflowed: the run is void"
     clocks = sampler.stop(line0) if sampler else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -355,6 +409,15 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": e2e,
         }
+        if skin:
+            cfg = line["config"]
+            cfg["workload"] += "+skin"
+            cfg["skin"] = {"r_buff": args.skin, "rebuild_every": args.rebuild_every, "step_length": args.step_length,
+                           "rebuilds_in_timed_region": sum(1 for i in range(args.steps)
+                                                           if (skin_t0 + i) % args.rebuild_every == 0),
+                           "note": "HOOMD-style buffered list: search (r_cut + r_buff) amortised, prepareNeighbors-style "
+                                   "distance filter every step; particles move ballistically every step"}
+            line["roofline"]["kernel"] = "nlist_filter_kernel (per-step pass; the search is amortised inside build_ms)"
         if args.model == "mlp":
             # the dominant kernel of this workload is the tensor-core MLP: report it against the measured bf16 peak
             tpeak, tsrc = tensor_peak()

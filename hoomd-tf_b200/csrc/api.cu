@@ -243,7 +243,8 @@ void htf_destroy(htf_ctx *ctx)
 {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    void *ptrs[] = {ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx,
+    if (ctx->skin_ctx) { htf_destroy(ctx->skin_ctx); ctx->skin_ctx = nullptr; }
+    void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx,
                     ctx->d_spos, ctx->d_nlist_scratch, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
                     ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
@@ -336,6 +337,97 @@ int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, fl
     HTF_CUDA(ctx, htf_launch_select_pair(ctx, reinterpret_cast<const float4 *>(d_pos), n, axis, threshold_lo, threshold_hi,
                                          reinterpret_cast<float4 *>(d_out_lo), reinterpret_cast<float4 *>(d_out_hi),
                                          (int)capacity, d_counts, d_overflow, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_skin_configure(htf_ctx *ctx, float skin, int k_candidates)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!(skin > 0.0f) || k_candidates < 0) { set_err(ctx, "htf_skin_configure: need skin > 0"); return HTF_EINVAL; }
+    if (ctx->K < 32) { set_err(ctx, "htf_skin_configure: buffered lists need nneighbor_cutoff >= 32"); return HTF_EINVAL; }
+    if (k_candidates == 0) {
+        const double g = (double)(ctx->r_cut + skin) / (double)ctx->r_cut;
+        k_candidates = ((int)ceil(ctx->K * g * g * g) + 31) / 32 * 32;
+    }
+    if (k_candidates < ctx->K) k_candidates = ctx->K;
+    DeviceGuard guard(ctx->device);
+    if (ctx->skin_ctx) { htf_destroy(ctx->skin_ctx); ctx->skin_ctx = nullptr; }
+    ctx->skin = skin; ctx->skin_kc = k_candidates;
+    ctx->skin_row_lo = ctx->skin_row_hi = ctx->skin_n = -1;
+    rc = htf_create(&ctx->skin_ctx, ctx->device, ctx->n_max, k_candidates, ctx->r_cut + skin, ctx->flags);
+    if (rc) { set_err(ctx, "htf_skin_configure: %s", htf_last_error(nullptr)); return rc; }
+    return HTF_OK;
+}
+
+int htf_skin_rebuild(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->skin_ctx) { set_err(ctx, "htf_skin_rebuild: call htf_skin_configure first"); return HTF_ESTATE; }
+    if (!ctx->box_set) { set_err(ctx, "htf_skin_rebuild: call htf_set_box first"); return HTF_ESTATE; }
+    if (n_all < 0 || row_lo < 0 || row_hi > n_all || row_lo > row_hi || (n_all > 0 && !d_pos_all)) {
+        set_err(ctx, "htf_skin_rebuild: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    htf_ctx *sk = ctx->skin_ctx;
+    // same box, mapped rule and region of interest (widened by the skin) as the outer context
+    if (!sk->box_set || memcmp(sk->grid.lo, ctx->grid.lo, sizeof(float) * 3) || memcmp(sk->grid.hi, ctx->grid.hi, sizeof(float) * 3)) {
+        const float tilt[3] = {0.f, 0.f, 0.f};
+        if ((rc = htf_set_box(sk, ctx->grid.lo, ctx->grid.hi, tilt))) { set_err(ctx, "htf_skin_rebuild: %s", htf_last_error(sk)); return rc; }
+    }
+    {
+        float hw[3];
+        for (int a = 0; a < 3; a++) hw[a] = ctx->grid.roi_h[a] >= 0.f ? ctx->grid.roi_h[a] + ctx->skin : -1.0f;
+        if (memcmp(hw, sk->grid.roi_h, sizeof(hw)) || memcmp(ctx->grid.roi_c, sk->grid.roi_c, sizeof(float) * 3))
+            if ((rc = htf_set_roi(sk, ctx->grid.roi_c, hw))) { set_err(ctx, "htf_skin_rebuild: %s", htf_last_error(sk)); return rc; }
+    }
+    sk->map_type_start = ctx->map_type_start;
+    const int64_t rows = row_hi - row_lo;
+    if (rows > ctx->skin_rows_cap) {
+        if ((rc = dev_realloc(ctx, &ctx->d_skin_cand, (size_t)rows * ctx->skin_kc))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_skin_count, (size_t)rows))) return rc;
+        ctx->skin_rows_cap = rows;
+    }
+    if (n_all > ctx->skin_n_cap) {
+        if ((rc = dev_realloc(ctx, &ctx->d_skin_ref, (size_t)n_all))) return rc;
+        ctx->skin_n_cap = n_all;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = htf_bin_particles(sk, d_pos_all, n_all, stream))) { set_err(ctx, "htf_skin_rebuild: %s", htf_last_error(sk)); return rc; }
+    HTF_CUDA(ctx, htf_launch_nlist(sk, row_lo, row_hi, nullptr, ctx->d_skin_cand, ctx->d_skin_count, nullptr, st));
+    HTF_CUDA(ctx, cudaMemcpyAsync(ctx->d_skin_ref, d_pos_all, sizeof(float4) * (size_t)n_all, cudaMemcpyDeviceToDevice, st));
+    ctx->launches += sk->launches; sk->launches = 0;
+    ctx->skin_row_lo = row_lo; ctx->skin_row_hi = row_hi; ctx->skin_n = n_all;
+    return HTF_OK;
+}
+
+int htf_skin_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                   float *d_nlist_out, int32_t *d_idx_out, int32_t *d_count_out, int32_t *d_overflow, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->skin_ctx || ctx->skin_n != n_all || ctx->skin_row_lo != row_lo || ctx->skin_row_hi != row_hi) {
+        set_err(ctx, "htf_skin_nlist: no candidate lists for these rows (call htf_skin_rebuild first)"); return HTF_ESTATE;
+    }
+    if (row_hi > row_lo && (!d_nlist_out || !d_pos_all)) { set_err(ctx, "htf_skin_nlist: null argument"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_skin_filter(ctx, reinterpret_cast<const float4 *>(d_pos_all), row_lo, row_hi,
+                                         reinterpret_cast<float4 *>(d_nlist_out), d_idx_out, d_count_out, d_overflow,
+                                         (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_skin_status(htf_ctx *ctx, int32_t h_status[2], int reset, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!h_status) return HTF_EINVAL;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    HTF_CUDA(ctx, cudaMemcpyAsync(h_status, ctx->d_stats + 6, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HTF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (reset) HTF_CUDA(ctx, cudaMemsetAsync(ctx->d_stats + 6, 0, 2 * sizeof(int), st));
     return HTF_OK;
 }
 

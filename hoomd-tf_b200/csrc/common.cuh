@@ -55,6 +55,14 @@ struct htf_ctx {
     int tile_flag_cap;
     int *d_flag_count;            // two counters (inside d_stats) of tiles the tile kernel flagged, used in turn
     int flag_parity;
+    // buffered ("skin") lists: candidates within r_cut + skin, rebuilt by htf_skin_rebuild, filtered every step
+    float skin;
+    int skin_kc;                  // candidate capacity per row
+    htf_ctx *skin_ctx;            // inner context with cutoff r_cut + skin and K = skin_kc
+    int *d_skin_cand, *d_skin_count;
+    float4 *d_skin_ref;           // positions at the last rebuild
+    int64_t skin_rows_cap, skin_n_cap;
+    int64_t skin_row_lo, skin_row_hi, skin_n;   // what the current lists cover (-1: none)
     float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
     int64_t nlist_scratch_elems;
     // RDF threshold table (device) and the key it was built for
@@ -81,6 +89,8 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
 cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st);
+cudaError_t htf_launch_skin_filter(htf_ctx *ctx, const float4 *pos, int64_t row_lo, int64_t row_hi, float4 *out,
+                                   int32_t *idx_out, int32_t *count_out, int32_t *overflow, cudaStream_t st);
 cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr_lo, float thr_hi,
                                    float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st);
 cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,

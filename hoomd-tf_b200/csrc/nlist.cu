@@ -272,7 +272,7 @@ __device__ HTF_EMIT_INLINE void emit_single_window(const NlistParams &p, unsigne
             v = make_float4(dx, dy, dz, cd.w);
             if (WITH_IDX) vi = candidx[ci];
         }
-        grow[sl] = v;
+        if (!WITH_IDX || p.out) grow[sl] = v;                   // idx-only builds (candidate lists) pass out == nullptr
         if (WITH_IDX) p.idx_out[row * K + sl] = vi;
     }
     if (lane == 0) {
@@ -307,7 +307,7 @@ __device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_w
                 dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
                 dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
             }
-            dst[32 * i] = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!WITH_IDX || p.out) dst[32 * i] = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (WITH_IDX) idst[32 * i] = valid ? candidx_w[ci] : -1;
         }
     } else {
@@ -322,7 +322,7 @@ __device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_w
                 dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
                 dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
             }
-            *dst = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!WITH_IDX || p.out) *dst = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (WITH_IDX) { *idst = valid ? candidx_w[ci] : -1; idst += 32; }
         }
     }
@@ -555,7 +555,7 @@ __device__ __forceinline__ void build_cell(const NlistParams &p, const int cell,
                     __syncwarp();
                     if (last) {
                         for (int sl = lane; sl < K; sl += 32) {
-                            grow[sl] = rowstage[sl];
+                            if (!WITH_IDX || p.out) grow[sl] = rowstage[sl];
                             if (WITH_IDX) p.idx_out[row * K + sl] = idxstage[sl];
                         }
                     }

@@ -99,6 +99,38 @@ class HtfContext:
                                              _ptr(counts), _ptr(self._overflow), self._stream()))
         return out_lo, out_hi
 
+    # ---- buffered ("skin") lists: search every few steps, distance filter every step ----
+    def skin_configure(self, skin, k_candidates=0):
+        self._ck(self.lib.htf_skin_configure(self._h, float(skin), int(k_candidates)))
+
+    def skin_rebuild(self, pos, row_lo=0, row_hi=None):
+        _check_dev_f32(pos, "positions", 4)
+        n = pos.shape[0]
+        self._ck(self.lib.htf_skin_rebuild(self._h, _ptr(pos), n, int(row_lo), n if row_hi is None else int(row_hi),
+                                           self._stream()))
+
+    def skin_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False):
+        """The per-step pass: neighbor tensor of the rows from the candidate lists of the last ``skin_rebuild``."""
+        _check_dev_f32(pos, "positions", 4)
+        n = pos.shape[0]
+        row_hi = n if row_hi is None else int(row_hi)
+        rows = row_hi - int(row_lo)
+        if out is None:
+            out = torch.empty((rows, self.K, 4), dtype=torch.float32, device=self.device)
+        idx = torch.empty((rows, self.K), dtype=torch.int32, device=self.device) if want_idx else None
+        cnt = torch.empty((rows,), dtype=torch.int32, device=self.device) if want_count else None
+        self._ck(self.lib.htf_skin_nlist(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(out), _ptr(idx), _ptr(cnt),
+                                         _ptr(self._overflow), self._stream()))
+        if want_idx or want_count:
+            return out, idx, cnt
+        return out
+
+    def skin_status(self, reset=True):
+        """(rows used with a particle displaced by more than skin/2, rows whose candidate list overflowed); syncs."""
+        h = (ctypes.c_int32 * 2)()
+        self._ck(self.lib.htf_skin_status(self._h, h, int(bool(reset)), self._stream()))
+        return int(h[0]), int(h[1])
+
     def set_mapped_nlist(self, map_type_start):
         self._ck(self.lib.htf_set_mapped_nlist(self._h, -1 if map_type_start is None else int(map_type_start)))
 

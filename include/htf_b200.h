@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 10
+#define HTF_ABI_VERSION 11
 int htf_abi_version(void);
 
 /*
@@ -113,6 +113,25 @@ int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float t
 int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold_lo, float threshold_hi,
                        float *d_out_lo, float *d_out_hi, int64_t capacity, int32_t *d_counts, int32_t *d_overflow,
                        void *stream);
+
+/*
+ * Buffered ("skin") neighbor lists -- the reference's own split of the work: HOOMD's NeighborList::compute searches
+ * within r_cut + r_buff and runs only when particles have moved more than r_buff/2 (htf/TensorflowCompute.cc:163),
+ * prepareNeighbors (htf/TensorflowCompute.cc:304-374) filters the candidates by r_cut EVERY step.
+ *   htf_skin_configure : enable with a skin (HOOMD's r_buff) and a candidate capacity per row (0 = derived from K).
+ *   htf_skin_rebuild   : the search.  Bins the particles with cell edge >= r_cut + skin, stores the candidate indices
+ *                        of rows [row_lo,row_hi) and the positions they were built from.
+ *   htf_skin_nlist     : the per-step pass.  Same output and arithmetic as htf_build_nlist (neighbor sets, values and
+ *                        the modulo-K rule; slot order = candidate order), valid while no particle has moved more than
+ *                        skin/2 since the rebuild; particle order and count must not change between rebuilds.
+ *   htf_skin_status    : synchronising.  h_status[0] = rows whose particle had moved more than skin/2 when a list was
+ *                        used, h_status[1] = rows whose candidate list overflowed its capacity; both must be 0.
+ */
+int htf_skin_configure(htf_ctx *ctx, float skin, int k_candidates);
+int htf_skin_rebuild(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi, void *stream);
+int htf_skin_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                   float *d_nlist_out, int32_t *d_idx_out, int32_t *d_count_out, int32_t *d_overflow, void *stream);
+int htf_skin_status(htf_ctx *ctx, int32_t h_status[2], int reset, void *stream);
 
 /*
  * Replaces HOOMD's NeighborList::compute (called at htf/TensorflowCompute.cc:163) for this

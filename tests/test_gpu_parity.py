@@ -482,3 +482,50 @@ def test_pairwise_mlp_tensor_core_vs_fp32():
     assert np.abs(a[:, :3] - b[:, :3]).max() / s < MLP_TOL_MAX
     assert np.sqrt(np.mean((a[:, :3] - b[:, :3]) ** 2)) / s < MLP_TOL_RMS
     assert np.abs(a[:, 3] - b[:, 3]).max() / np.sqrt(np.mean(b[:, 3] ** 2)) < MLP_TOL_MAX
+
+
+def test_skin_lists_match_oracle_between_rebuilds(oracle_mod):
+    """Buffered lists (HOOMD's r_buff): one search with r_cut + skin, then the per-step distance filter on MOVED
+    positions without a rebuild must give the oracle's neighbor sets and values bit for bit."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((14, 14, 14), 0.7, seed=11)
+    n, K, r_cut, skin = pos.shape[0], 64, 2.5, 0.4
+    ctx = _ctx(n, K, r_cut, lo, hi)
+    ctx.skin_configure(skin)
+    dpos = torch.from_numpy(pos).cuda()
+    ctx.skin_rebuild(dpos)
+    rng = np.random.default_rng(5)
+    L = (np.asarray(hi) - np.asarray(lo)).astype(np.float64)
+    cur = pos.copy()
+    for step in range(3):
+        if step:                                                # each particle moves < 0.08 * sqrt(3) = 0.139 < skin/2 in total
+            cur[:, :3] = (cur[:, :3].astype(np.float64) + rng.uniform(-0.04, 0.04, (n, 3))).astype(np.float32)
+            cur[:, :3] = (((cur[:, :3] - lo) % L) + lo).astype(np.float32)
+        d = torch.from_numpy(cur).cuda()
+        nl, idx, cnt = ctx.skin_nlist(d, want_idx=True, want_count=True)
+        assert ctx.overflow() == 0
+        nl_o, idx_o, cnt_o = oracle_mod.nlist(cur, lo, hi, r_cut, K)
+        assert np.array_equal(cnt.cpu().numpy(), cnt_o)
+        a, ai = sort_rows(nl.cpu().numpy(), idx.cpu().numpy())
+        b, bi = sort_rows(nl_o, idx_o)
+        assert np.array_equal(ai, bi) and np.array_equal(a.view(np.uint32), b.view(np.uint32)), step
+    assert ctx.skin_status() == (0, 0)
+    # the full build on the same positions agrees too (same sets; slot order differs)
+    nl2, idx2, _ = gpu_nlist(ctx, cur)
+    a2, ai2 = sort_rows(nl2.cpu().numpy(), idx2)
+    assert np.array_equal(ai2, bi) and np.array_equal(a2.view(np.uint32), b.view(np.uint32))
+    # a particle that moved more than skin/2 is reported
+    far = cur.copy(); far[7, 0] += 0.5
+    ctx.skin_nlist(torch.from_numpy(far).cuda())
+    moved, over = ctx.skin_status()
+    assert moved >= 1 and over == 0
+    # a row shard, after a rebuild for that shard
+    ctx.skin_rebuild(d, 1000, 1800)
+    nl3, idx3, _ = ctx.skin_nlist(d, 1000, 1800, want_idx=True, want_count=True)
+    a3, ai3 = sort_rows(nl3.cpu().numpy(), idx3.cpu().numpy())
+    assert np.array_equal(ai3, bi[1000:1800]) and np.array_equal(a3.view(np.uint32), b[1000:1800].view(np.uint32))
+    # too small a candidate capacity is reported, never silently truncated
+    ctx.skin_configure(skin, 64)
+    ctx.skin_rebuild(d)
+    ctx.skin_nlist(d)
+    assert ctx.skin_status()[1] > 0
