@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--step-length", type=float, default=0.0087,
                     help="displacement per step in the --skin workload (LJ liquid at T*=1, dt=0.005: 0.005*sqrt(3))")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="single GPU: launch every kernel from the host instead of replaying the three CUDA graphs "
+                         "(binning | build | forces) the step is captured into")
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
                     help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
@@ -345,6 +348,54 @@ def run_b200(args):
         if marks is not None:
             marks[2].record()
 
+    # ---- single GPU: capture the step's three phases into CUDA graphs (same kernels, same stream order; the
+    #      events between the phases stay live).  Binning alone is six dependent launches of a few microseconds. ----
+    graphs = None
+    launches_per_step = None
+    if world == 1 and not skin and not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()                                          # warm-up on the capture stream (allocations, func attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        def phase_bin():
+            ctx.bin_particles(d_pos_all)
+
+        def phase_build():
+            ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
+
+        def phase_force():
+            if packed is not None:
+                ctx.mlp_forces(nl, packed, r_cut, out=fe)
+            elif bins is not None:
+                bins.zero_()
+                ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
+            else:
+                ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
+
+        graphs = []
+        l0 = ctx.launches
+        for fn in (phase_bin, phase_build, phase_force):
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=side):
+                fn()
+            graphs.append(g_)
+        launches_per_step = ctx.launches - l0
+
+        def step(marks=None):                                   # noqa: F811 -- the graph replay of the same step
+            graphs[0].replay()
+            if marks is not None:
+                marks[0].record()
+            graphs[1].replay()
+            if marks is not None:
+                marks[1].record()
+            graphs[2].replay()
+            if marks is not None:
+                marks[2].record()
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -370,7 +421,7 @@ def run_b200(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
+    launches = ctx.launches - launches0 if graphs is None else launches_per_step * args.steps
     assert ctx.overflow() == 0, "neighbor list overflowed K: the run is void"
     if skin:
         assert ctx.skin_status() == (0, 0), "a buffered list was used past skin/2 or overflowed: the run is void"
@@ -409,6 +460,8 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": e2e,
         }
+        line["config"]["launch"] = ("3 CUDA graphs per step (binning | build | forces), %d kernels" % launches_per_step
+                                    if graphs is not None else "stream launches from the host")
         if skin:
             cfg = line["config"]
             cfg["workload"] += "+skin"

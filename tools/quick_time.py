@@ -41,3 +41,18 @@ print("lj       med %.3f ms min %.3f" % t_ljnv)
 print("rdf      med %.3f ms min %.3f" % t_rdf)
 print("step     med %.3f ms min %.3f  -> %.0f GB/s, %.3e particle-steps/s" % (t_step + (gb(n * (32 * K + 56), t_step[0]), n / t_step[0] * 1e3)))
 print("step+rdf med %.3f ms min %.3f" % t_step_rdf)
+
+# ---- the same step replayed from a CUDA graph (launch-bound small systems) ----
+try:
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir, bins=bins, r_range=(0, r_cut), nbins=100)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir, bins=bins, r_range=(0, r_cut), nbins=100)
+    t_graph = timeit(lambda: g.replay())
+    print("step+rdf (CUDA graph replay) med %.3f ms min %.3f  -> %.3e particle-steps/s" % (t_graph + (n / t_graph[0] * 1e3,)))
+except Exception as ex:
+    print("graph capture failed:", repr(ex)[:300])
