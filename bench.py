@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--step-length", type=float, default=0.0087,
                     help="displacement per step in the --skin workload (LJ liquid at T*=1, dt=0.005: 0.005*sqrt(3))")
     ap.add_argument("--no-graph", action="store_true",
-                    help="single GPU: launch every kernel from the host instead of replaying the three CUDA graphs "
+                    help="launch every kernel from the host instead of replaying the three CUDA graphs "
                          "(binning | build | forces) the step is captured into")
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
@@ -352,7 +352,7 @@ def run_b200(args):
     #      events between the phases stay live).  Binning alone is six dependent launches of a few microseconds. ----
     graphs = None
     launches_per_step = None
-    if world == 1 and not skin and not args.no_graph:
+    if not skin and not args.no_graph and (world == 1 or halo):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -378,6 +378,11 @@ def run_b200(args):
 
         graphs = []
         l0 = ctx.launches
+        pack_graph = None
+        if halo:                                                # the device half of the exchange; NCCL send/recv stays eager
+            pack_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(pack_graph, stream=side):
+                xch.pack()
         for fn in (phase_bin, phase_build, phase_force):
             g_ = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_, stream=side):
@@ -386,6 +391,9 @@ def run_b200(args):
         launches_per_step = ctx.launches - l0
 
         def step(marks=None):                                   # noqa: F811 -- the graph replay of the same step
+            if pack_graph is not None:
+                pack_graph.replay()
+                xch.swap()
             graphs[0].replay()
             if marks is not None:
                 marks[0].record()
@@ -460,7 +468,8 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": e2e,
         }
-        line["config"]["launch"] = ("3 CUDA graphs per step (binning | build | forces), %d kernels" % launches_per_step
+        line["config"]["launch"] = ("%d CUDA graphs per step (%sbinning | build | forces), %d kernels"
+                                    % (4 if halo else 3, "halo packing | " if halo else "", launches_per_step)
                                     if graphs is not None else "stream launches from the host")
         if skin:
             cfg = line["config"]

@@ -101,12 +101,20 @@ class SlabExchange:
         """View of this rank's rows inside the local array (write the shard's positions here)."""
         return self.local[:self.n_local]
 
+    def pack(self):
+        """Device-side half of the exchange (graph-capturable): both faces into the two send buffers."""
+        if self.world > 1:
+            self.ctx.pack_halo_pair(self.own, self.axis, self.lo_thr, self.hi_thr, self.send_lo, self.send_hi)
+
     def exchange(self):
         """Pack both faces, swap with the neighbours, return the local array ``[own | halo | halo]``."""
+        self.pack()
+        return self.swap()
+
+    def swap(self):
+        """NCCL half of the exchange: send the packed faces to the two neighbours, receive theirs."""
         if self.world == 1:
             return self.local
-        own = self.own
-        self.ctx.pack_halo_pair(own, self.axis, self.lo_thr, self.hi_thr, self.send_lo, self.send_hi)
         prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         a = self.local[self.n_local:self.n_local + self.cap]
         b = self.local[self.n_local + self.cap:]
