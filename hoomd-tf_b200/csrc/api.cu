@@ -340,6 +340,23 @@ int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, fl
     return HTF_OK;
 }
 
+int htf_integrate_half(htf_ctx *ctx, int half, float *d_pos, float *d_vel, const float *d_force, int64_t n, float dt,
+                       float gamma, float kT, int flat, uint64_t seed, uint64_t timestep, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->box_set) { set_err(ctx, "htf_integrate_half: call htf_set_box first"); return HTF_ESTATE; }
+    if (n < 0 || n > 2000000000LL || (half != 0 && half != 1) || !(dt > 0.f) || gamma < 0.f || kT < 0.f ||
+        (n > 0 && (!d_vel || !d_force || (half == 0 && !d_pos)))) {
+        set_err(ctx, "htf_integrate_half: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_integrate(ctx, half, reinterpret_cast<float4 *>(d_pos), d_vel,
+                                       reinterpret_cast<const float4 *>(d_force), n, dt, gamma, kT, flat,
+                                       (unsigned long long)seed, (unsigned long long)timestep, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_skin_configure(htf_ctx *ctx, float skin, int k_candidates)
 {
     int rc = check_ctx(ctx);

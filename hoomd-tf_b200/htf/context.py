@@ -99,6 +99,16 @@ class HtfContext:
                                              _ptr(counts), _ptr(self._overflow), self._stream()))
         return out_lo, out_hi
 
+    def integrate_half(self, half, pos, vel, force, dt, gamma=0.0, kT=0.0, flat=False, seed=0, timestep=0):
+        """Velocity-Verlet half step on the device (half 0: kick + drift + wrap, half 1: kick); see include/htf_b200.h."""
+        _check_dev_f32(pos, "positions", 4)
+        _check_dev_f32(force, "forces", 4)
+        if not (vel.is_cuda and vel.dtype == torch.float32 and vel.is_contiguous() and vel.shape == (pos.shape[0], 3)):
+            raise ValueError("velocities must be a contiguous float32 CUDA tensor [N,3]")
+        self._ck(self.lib.htf_integrate_half(self._h, int(half), _ptr(pos), _ptr(vel), _ptr(force), pos.shape[0], float(dt),
+                                             float(gamma), float(kT), int(bool(flat)), int(seed), int(timestep),
+                                             self._stream()))
+
     # ---- buffered ("skin") lists: search every few steps, distance filter every step ----
     def skin_configure(self, skin, k_candidates=0):
         self._ck(self.lib.htf_skin_configure(self._h, float(skin), int(k_candidates)))

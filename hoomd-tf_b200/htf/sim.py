@@ -170,12 +170,41 @@ def nlist_cell(system, check_period=1):
 
 
 class _Integrator:
-    def __init__(self, dt):
+    """Velocity Verlet around the force computes.  On the GPU both half steps are libhtf_b200 kernels
+    (htf_integrate_half: kick + drift + wrap, kick) so a trajectory never leaves the device; ``fused=False`` (and
+    CPU tensors) use the same formulas written with torch ops -- the reference the kernels are tested against."""
+
+    def __init__(self, dt, fused=True):
         self.dt = float(dt)
+        self.fused = bool(fused)
         self._have_force = False
+        self._ctx = None
 
     def _forces(self, system):
         return system.compute_net_force()[:, :3]
+
+    def _kernel_ctx(self, system):
+        if not (self.fused and system.positions.is_cuda):
+            return None
+        if self._ctx is None:
+            from .context import HtfContext
+            self._ctx = HtfContext(system.N, 1, 1.0, device=system.device)
+            self._ctx.set_box(system.box.lo, system.box.hi)
+        return self._ctx
+
+    def _fused_step(self, system, ctx, gamma=0.0, kT=0.0, seed=0):
+        if not self._have_force:
+            self._f4 = system.compute_net_force().contiguous()
+            self._have_force = True
+        if not system.velocities.is_contiguous():
+            system.velocities = system.velocities.contiguous()
+        ctx.integrate_half(0, system.positions, system.velocities, self._f4, self.dt, gamma, kT, system.dim == 2, seed,
+                           system.timestep)
+        for h in system.half_step_hooks:
+            h.half_step(system.timestep)
+        self._f4 = system.compute_net_force().contiguous()
+        ctx.integrate_half(1, system.positions, system.velocities, self._f4, self.dt, gamma, kT, system.dim == 2, seed,
+                           system.timestep)
 
 
 class NVE(_Integrator):
@@ -183,6 +212,9 @@ class NVE(_Integrator):
 
     def step(self, system):
         dt = self.dt
+        ctx = self._kernel_ctx(system)
+        if ctx is not None:
+            return self._fused_step(system, ctx)
         if not self._have_force:
             self._f = self._forces(system)
             self._have_force = True
@@ -198,25 +230,33 @@ class NVE(_Integrator):
 
 
 class Langevin(_Integrator):
-    """BAOAB-free simple Langevin step (hoomd.md.integrate.langevin): velocity Verlet + friction + noise."""
+    """Simple Langevin step (hoomd.md.integrate.langevin): velocity Verlet whose two half kicks each carry friction
+    and an independent random impulse sized for dt/2, so that <v^2> relaxes to kT."""
 
-    def __init__(self, dt, kT, seed, gamma=1.0):
-        super().__init__(dt)
+    def __init__(self, dt, kT, seed, gamma=1.0, fused=True):
+        super().__init__(dt, fused)
         self.kT, self.gamma = float(kT), float(gamma)
         self._gen = None
         self._seed = int(seed)
 
     def step(self, system):
         dt = self.dt
+        ctx = self._kernel_ctx(system)
+        if ctx is not None:
+            return self._fused_step(system, ctx, self.gamma, self.kT, self._seed)
         if self._gen is None:
             self._gen = torch.Generator(device=system.device).manual_seed(self._seed)
         if not self._have_force:
             self._f = self._forces(system)
             self._have_force = True
-        noise = torch.randn((system.N, 3), generator=self._gen, device=system.device, dtype=torch.float32)
-        if system.dim == 2:
-            noise[:, 2] = 0.0
-        fr = self._f - self.gamma * system.velocities + math.sqrt(2.0 * self.gamma * self.kT / dt) * noise
+        sigma = math.sqrt(4.0 * self.gamma * self.kT / dt)       # each half kick lasts dt/2 and has its own impulse
+
+        def noise():
+            z = torch.randn((system.N, 3), generator=self._gen, device=system.device, dtype=torch.float32)
+            if system.dim == 2:
+                z[:, 2] = 0.0
+            return sigma * z
+        fr = self._f - self.gamma * system.velocities + noise()
         system.velocities = system.velocities + 0.5 * dt * fr
         system.positions[:, :3] += dt * system.velocities
         if system.dim == 2:
@@ -225,7 +265,7 @@ class Langevin(_Integrator):
         for h in system.half_step_hooks:
             h.half_step(system.timestep)
         self._f = self._forces(system)
-        system.velocities = system.velocities + 0.5 * dt * (self._f - self.gamma * system.velocities)
+        system.velocities = system.velocities + 0.5 * dt * (self._f - self.gamma * system.velocities + noise())
 
 
 class ReferenceLJ:

@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 11
+#define HTF_ABI_VERSION 12
 int htf_abi_version(void);
 
 /*
@@ -113,6 +113,18 @@ int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float t
 int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold_lo, float threshold_hi,
                        float *d_out_lo, float *d_out_hi, int64_t capacity, int32_t *d_counts, int32_t *d_overflow,
                        void *stream);
+
+/*
+ * The step either side of the path (what HOOMD's integrator does around the reference's compute:
+ * hoomd.md.integrate.nve / langevin, htf/test-py/benchmark.py:39-48), unit mass, so that a trajectory stays on the GPU:
+ *   half == 0 : v += dt/2 a;  x += dt v;  x wrapped into the box of htf_set_box;  flat != 0 keeps z = 0 (2-D systems)
+ *   half == 1 : v += dt/2 a
+ *   a = F, or F - gamma v + sqrt(2 gamma kT / (dt/2)) N(0,1) when gamma > 0 and kT > 0: every half kick carries its own
+ *   random impulse (Philox, keyed by (seed, particle, timestep, half)), so that <v^2> relaxes to kT.
+ * d_pos float[n][4] (w untouched), d_vel float[n][3], d_force float[n][4] (w = energy, ignored).
+ */
+int htf_integrate_half(htf_ctx *ctx, int half, float *d_pos, float *d_vel, const float *d_force, int64_t n, float dt,
+                       float gamma, float kT, int flat, uint64_t seed, uint64_t timestep, void *stream);
 
 /*
  * Buffered ("skin") neighbor lists -- the reference's own split of the work: HOOMD's NeighborList::compute searches

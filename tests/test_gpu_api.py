@@ -275,3 +275,41 @@ def test_eds_bias_converges():
     system.run(1000)
     assert np.isfinite(np.mean(tfc.outputs[0]))
     assert (float(model.cv_avg.result()) - 4) ** 2 < 0.5
+
+
+@pytest.mark.gpu
+def test_device_integrators_match_torch_formulas_and_conserve_energy():
+    """htf_integrate_half (velocity Verlet kick+drift+wrap / kick) against the same step written with torch ops, then
+    energy conservation over a config-1 style LJ run that never leaves the GPU, then the Langevin thermostat."""
+    import htf
+    from htf import sim, synthetic
+    pos, lo, hi = synthetic.lattice_fluid((4, 8, 8), 0.10, seed=1)
+    def make(fused):
+        s = sim.System(pos, lo, hi).randomize_velocities(2.0, seed=3)
+        model = htf.models.LJModel(32)
+        tfc = htf.tfcompute(model)
+        tfc.attach(sim.nlist_cell(s), r_cut=3.0)
+        s.forces.append(tfc)
+        s.integrator = sim.NVE(0.005, fused=fused)
+        return s
+    a, b = make(True), make(False)
+    a.run(5); b.run(5)
+    assert torch.allclose(a.positions, b.positions, atol=2e-6) and torch.allclose(a.velocities, b.velocities, atol=2e-6)
+    def energy(s):
+        return float(0.5 * (s.velocities.double() ** 2).sum() + s.net_force[:, 3].double().sum())
+    e0 = energy(a)
+    a.run(400)
+    # plain truncation at r_cut (no shift): every pair crossing the cutoff moves the total by 5.5e-3, so only drift matters
+    assert abs(energy(a) - e0) < 0.01 * abs(e0), (e0, energy(a))
+    assert bool(((a.positions[:, :3] >= torch.tensor(lo, device="cuda")) & (a.positions[:, :3] < torch.tensor(hi, device="cuda"))).all())
+    # Langevin on an ideal gas: the velocity variance relaxes to kT
+    class NoForce:
+        def compute_forces(self, t):
+            return torch.zeros((g.N, 4), device="cuda")
+    p2, lo2, hi2 = synthetic.lattice_fluid((16, 16, 16), 0.5, seed=2)
+    g = sim.System(p2, lo2, hi2)
+    g.forces.append(NoForce())
+    g.integrator = sim.Langevin(0.01, kT=1.5, seed=9, gamma=2.0)
+    g.run(400)
+    T = float((g.velocities.double() ** 2).mean())
+    assert abs(T - 1.5) < 0.1, T
