@@ -37,7 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "refbench"],
+                    help="cfg1..cfg5: BASELINE.json configs (default cfg3 = 1M particles, K=64, the size the target is "
+                         "quoted on); refbench: the reference's own pytest-benchmark (htf/test-py/benchmark.py: N=256 2-D "
+                         "lattice, NN=64, r_cut=3, Langevin, 4000 + 1000 steps, whole simulation) through the public API")
     ap.add_argument("--model", default="lj", choices=["lj", "mlp"],
                     help="lj: closed-form LJ + virial (the headline path); mlp: BASELINE config 3's pairwise-MLP force "
                          "field on the tensor cores (forces + energy)")
@@ -578,6 +581,50 @@ def cpu_baseline(args, pos, lo, hi, r_cut, K):
             "host_cores": os.cpu_count()}
 
 
+def run_refbench(args):
+    """The reference's one published benchmark, end to end through the kept API (/root/reference htf/test-py/benchmark.py:
+    25-48): 256 particles on a 2-D square lattice a=2.0, HOOMD-side LJ pair force + the LJ SimModel through tfcompute
+    (NN=64, r_cut=3.0), Langevin kT=1 dt=0.005, 4000 equilibration steps, then 1000 timed steps, 5 rounds (median).
+    Published: median 2.007 s per 1000 steps = 1.28e5 particle-timesteps/s on a Xeon Gold 6130."""
+    import numpy as np
+    import torch
+    import htf
+    from htf import sim
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback")
+    published = 256 * 1000 / 2.007
+    system = sim.create_lattice(sim.sq(2.0), [16, 16])
+    nlist = sim.nlist_cell(system, check_period=1)
+    system.forces.append(sim.ReferenceLJ(system, 3.0))            # hoomd.md.pair.lj stays attached in the reference run
+    system.integrator = sim.Langevin(0.005, kT=1.0, seed=42)
+    system.run(4000)
+    tfc = htf.tfcompute(htf.models.LJModel(64))
+    tfc.attach(nlist, r_cut=3.0)
+    system.forces.append(tfc)
+    system.run(50)
+    torch.cuda.synchronize()
+    rounds = []
+    l0 = tfc.ctx.launches
+    for _ in range(5):
+        t0 = time.perf_counter()
+        system.run(1000)
+        torch.cuda.synchronize()
+        rounds.append(time.perf_counter() - t0)
+    med = float(np.median(rounds))
+    value = 256 * 1000 / med
+    print(json.dumps({
+        "metric": "particle-timesteps/s (whole simulation, the reference's test_lj_benchmark)", "value": value,
+        "unit": UNIT, "n_gpus": 1, "steps": 1000, "warmup": 4050, "ms_per_step": med, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": value / published, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "refbench: N=256 2-D sq lattice a=2.0, NN=64, r_cut=3.0, Langevin kT=1 dt=0.005, "
+                               "1000 steps x 5 rounds (median), wall clock incl. the Python driver loop",
+                   "published": {"value": published, "where": "Xeon Gold 6130, HOOMD+TensorFlow, BASELINE.md section 1"}},
+        "rounds_s": rounds, "gpu_launches": tfc.ctx.launches - l0}))
+    return 0
+
+
 if __name__ == "__main__":
     a = parse()
+    if a.workload == "refbench" and a.impl != "reference":
+        sys.exit(run_refbench(a))
     sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))
