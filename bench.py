@@ -257,6 +257,7 @@ def run_b200(args):
     per = n // world
     row_lo, row_hi = rank * per, (rank + 1) * per if rank < world - 1 else n
     rows = row_hi - row_lo
+    g_lo, g_hi = row_lo, row_hi                      # this rank's rows in the global numbering
 
     ctx = htf.HtfContext(n, K, r_cut, device=dev)
     ctx.set_box(lo, hi)
@@ -448,7 +449,7 @@ def run_b200(args):
     # ---- end to end through the public API with host buffers (tfcompute + built-in LJ virial model) ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi)
+        e2e = run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, g_lo, g_hi)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -507,30 +508,49 @@ def run_b200(args):
 def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi):
     """Same metric through tfcompute (the user-facing call) with HOST buffers: every step copies the
     rank's positions from pinned host memory and reads forces+virial back into pinned host memory."""
+    import numpy as np
     n = pos.shape[0]
     rows = row_hi - row_lo
-    system = htf.sim.System(pos, lo, hi, device=dev)
+    halo = world > 1 and args.exchange == "halo"
     model = htf.models.PairwiseMLPModel(K, r_cut=r_cut).to(dev) if args.model == "mlp" else htf.models.LJVirialModel(K, virial=True)
     tfc = htf.tfcompute(model)
-    tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
     h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
     h_f = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
     h_v = torch.empty((rows, 6), dtype=torch.float32).pin_memory()
-    d_shard = torch.empty((rows, 4), dtype=torch.float32, device=dev)
-    tfc.shard = (row_lo, row_hi)
+    if halo:
+        # like the device-resident leg: the rank's system is [own rows | halo from below | halo from above]
+        lo_face, hi_face, width, cap_h = htf.parallel.slab_plan(pos[row_lo:row_hi], 2, r_cut)
+        t_ = torch.tensor([cap_h], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        cap_h = int(t_.item())
+        local0 = np.concatenate([pos[row_lo:row_hi], np.full((2 * cap_h, 4), 1e30, dtype=np.float32)])
+        system = htf.sim.System(local0, lo, hi, device=dev)
+        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
+        xch = htf.parallel.SlabExchange(tfc.ctx, rows, 2, lo_face, hi_face, width, cap_h)
+        system.positions = xch.local
+        d_shard = xch.own
+        out_lo, out_hi = 0, rows
+    else:
+        system = htf.sim.System(pos, lo, hi, device=dev)
+        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
+        d_shard = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        out_lo, out_hi = row_lo, row_hi
+    tfc.shard = (out_lo, out_hi)
     if world > 1:
         tfc.ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
 
     def step(t):
         d_shard.copy_(h_pos, non_blocking=True)
-        if world > 1:
+        if halo:
+            xch.exchange()
+        elif world > 1:
             dist.all_gather_into_tensor(system.positions, d_shard)
         else:
             system.positions.copy_(d_shard)
         f = tfc.compute_forces(t)
-        h_f.copy_(f[row_lo:row_hi], non_blocking=True)
+        h_f.copy_(f[out_lo:out_hi], non_blocking=True)
         if args.model != "mlp":
-            h_v.copy_(tfc.virial6((row_lo, row_hi)), non_blocking=True)   # the 6 components HOOMD keeps
+            h_v.copy_(tfc.virial6((out_lo, out_hi)), non_blocking=True)   # the 6 components HOOMD keeps
 
     steps = max(3, min(args.steps, 10))
     for t in range(3):
