@@ -41,9 +41,10 @@ def parse():
                     help="cfg1..cfg5: BASELINE.json configs (default cfg3 = 1M particles, K=64, the size the target is "
                          "quoted on); refbench: the reference's own pytest-benchmark (htf/test-py/benchmark.py: N=256 2-D "
                          "lattice, NN=64, r_cut=3, Langevin, 4000 + 1000 steps, whole simulation) through the public API")
-    ap.add_argument("--model", default="lj", choices=["lj", "mlp"],
+    ap.add_argument("--model", default="lj", choices=["lj", "mlp", "eds"],
                     help="lj: closed-form LJ + virial (the headline path); mlp: BASELINE config 3's pairwise-MLP force "
-                         "field on the tensor cores (forces + energy)")
+                         "field on the tensor cores (forces + energy); eds: BASELINE config 5's EDS bias on the smooth "
+                         "coordination-number CV + 100-bin RDF + LJ in one fused pass (use with --workload cfg5)")
     ap.add_argument("--skin", type=float, default=0.0,
                     help="> 0: buffered neighbor lists like HOOMD's r_buff (the reference's own split): search with "
                          "r_cut + skin every --rebuild-every steps, distance filter every step; the particles then "
@@ -227,7 +228,9 @@ def cfg_dict(args, n, K, r_cut, world):
     return {"workload": "lj_fluid_%s%s%s" % (args.workload, "+rdf100" if args.rdf else "", "+pairwise_mlp" if args.model == "mlp" else ""),
             "particles": n, "particles_per_gpu": n // world, "nneighbor_cutoff": K, "r_cut": r_cut,
             "model": ("pairwise MLP: RBF(32) -> 3 x Dense(64, tanh) -> Dense(1), bf16 operands / fp32 accumulation (tcgen05)"
-                      if args.model == "mlp" else "LJ (nlist_rinv closed form) + 6-component virial"),
+                      if args.model == "mlp" else
+                      "LJ + EDS bias (period 25, lr 5.0) on the smooth coordination CV (r0 1.3) + 100-bin RDF, one fused pass"
+                      if args.model == "eds" else "LJ (nlist_rinv closed form) + 6-component virial"),
             "sharding": ("particle rows (z-slabs), %s per step" % ("halo exchange of the two slab faces"
                          if args.exchange == "halo" else "all-gather of all positions")) if world > 1 else "single GPU",
             "l2": "per-GPU working set %.0f MiB/step > 126 MB L2, no flush needed" % (n // world * K * 16 / 2 ** 20)}
@@ -284,6 +287,11 @@ def run_b200(args):
     packed = None
     if args.model == "mlp":
         packed = ctx.mlp_pack(torch.from_numpy(mlp_raw_parameters()).to(dev))
+    eds_model = None
+    if args.model == "eds":
+        # EDS period 25, learning rate 5.0 as examples/03; the set point becomes the initial CV + 5 % below
+        eds_model = htf.models.EDSCoordinationModel(K, set_point=1.0, period=25, learning_rate=5.0, r0=1.3,
+                                                    rdf_range=(0.0, r_cut), nbins=100)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     skin = args.skin > 0.0
@@ -340,7 +348,9 @@ def run_b200(args):
         ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
         if marks is not None:
             marks[1].record()
-        if packed is not None:
+        if eds_model is not None:
+            eds_model.compute(nl, None, None)                         # fused LJ + CV + RDF pass, all-reduces, EDS update, bias
+        elif packed is not None:
             ctx.mlp_forces(nl, packed, r_cut, out=fe)
         elif bins is not None:
             bins.zero_()
@@ -351,6 +361,11 @@ def run_b200(args):
             ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
         if marks is not None:
             marks[2].record()
+
+    if eds_model is not None:
+        step()                                                        # one pass to measure the initial CV
+        eds_model.eds_bias.set_point.fill_(float(eds_model.cv_avg.result()) * 1.05)
+        eds_model.cv_avg.reset()
 
     # ---- single GPU: capture the step's three phases into CUDA graphs (same kernels, same stream order; the
     #      events between the phases stay live).  Binning alone is six dependent launches of a few microseconds. ----
@@ -372,6 +387,8 @@ def run_b200(args):
             ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
 
         def phase_force():
+            if eds_model is not None:
+                return                                          # host-side all-reduce and metric updates: runs eagerly
             if packed is not None:
                 ctx.mlp_forces(nl, packed, r_cut, out=fe)
             elif bins is not None:
@@ -404,7 +421,10 @@ def run_b200(args):
             graphs[1].replay()
             if marks is not None:
                 marks[1].record()
-            graphs[2].replay()
+            if eds_model is not None:
+                eds_model.compute(nl, None, None)
+            else:
+                graphs[2].replay()
             if marks is not None:
                 marks[2].record()
 
@@ -512,7 +532,13 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     n = pos.shape[0]
     rows = row_hi - row_lo
     halo = world > 1 and args.exchange == "halo"
-    model = htf.models.PairwiseMLPModel(K, r_cut=r_cut).to(dev) if args.model == "mlp" else htf.models.LJVirialModel(K, virial=True)
+    if args.model == "mlp":
+        model = htf.models.PairwiseMLPModel(K, r_cut=r_cut).to(dev)
+    elif args.model == "eds":
+        model = htf.models.EDSCoordinationModel(K, set_point=30.0, period=25, learning_rate=5.0, r0=1.3,
+                                                rdf_range=(0.0, r_cut), nbins=100)
+    else:
+        model = htf.models.LJVirialModel(K, virial=True)
     tfc = htf.tfcompute(model)
     h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
     h_f = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
@@ -549,7 +575,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
             system.positions.copy_(d_shard)
         f = tfc.compute_forces(t)
         h_f.copy_(f[out_lo:out_hi], non_blocking=True)
-        if args.model != "mlp":
+        if args.model == "lj":
             h_v.copy_(tfc.virial6((out_lo, out_hi)), non_blocking=True)   # the 6 components HOOMD keeps
 
     steps = max(3, min(args.steps, 10))
@@ -571,9 +597,10 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4),
-            "d2h_bytes_per_step": int(h_f.numel() * 4 + (0 if args.model == "mlp" else h_v.numel() * 4)), "steps": steps,
+            "d2h_bytes_per_step": int(h_f.numel() * 4 + (h_v.numel() * 4 if args.model == "lj" else 0)), "steps": steps,
             "api": "htf.tfcompute(%s).compute_forces with pinned host positions in, forces%s out"
-                   % (("PairwiseMLPModel", "+energy") if args.model == "mlp" else ("LJVirialModel", "+virial"))}
+                   % (("PairwiseMLPModel", "+energy") if args.model == "mlp" else
+                      ("EDSCoordinationModel", "+energy") if args.model == "eds" else ("LJVirialModel", "+virial"))}
 
 
 def cpu_baseline(args, pos, lo, hi, r_cut, K):
