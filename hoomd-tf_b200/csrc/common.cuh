@@ -89,6 +89,15 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles);
 cudaError_t htf_cell_stats(htf_ctx *ctx, int h_stats[3], cudaStream_t st);
+// cudaFuncSetAttribute is per device: launchers cache what they have opted into per device slot
+constexpr int HTF_MAX_DEVICES = 64;
+inline int htf_current_device_slot()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d % HTF_MAX_DEVICES;
+}
+
 cudaError_t htf_launch_integrate(htf_ctx *ctx, int half, float4 *pos, float *vel, const float4 *force, int64_t n, float dt,
                                  float gamma, float kT, int flat, unsigned long long seed, unsigned long long step,
                                  cudaStream_t st);

@@ -455,7 +455,8 @@ cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     if (rows <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(fe, 0, sizeof(float4) * (size_t)rows, st);
     if (e != cudaSuccess) return e;
-    static bool configured = false;
+    static bool configured_dev[HTF_MAX_DEVICES] = {false};  // the attribute is per device
+    bool &configured = configured_dev[htf_current_device_slot()];
     if (!configured) {
         e = cudaFuncSetAttribute(mlp_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM);
         if (e != cudaSuccess) return e;

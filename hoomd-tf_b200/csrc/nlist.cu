@@ -1184,7 +1184,8 @@ __global__ void __launch_bounds__(ROWS_PB) nlist_rows_kernel(const NlistParams p
 template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_rows_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static size_t configured = 0;
+    static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // the attribute is per device
+    size_t &configured = configured_dev[htf_current_device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(nlist_rows_kernel<WITH_IDX, MAPPED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1206,7 +1207,8 @@ size_t rows_block_bytes(int capB, int K, bool with_idx)
 template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_tile_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static size_t configured = 0;
+    static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // the attribute is per device
+    size_t &configured = configured_dev[htf_current_device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(nlist_tile_kernel<WITH_IDX, MAPPED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1228,7 +1230,8 @@ size_t tile_block_bytes(int capB, int capW, int K, bool with_idx)
 template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_variant(const NlistParams &p, int grid, int wpb, size_t smem, cudaStream_t st)
 {
-    static size_t configured = 0;        // per instantiation: largest dynamic smem opted in so far
+    static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // per instantiation and device: largest dynamic smem opted in so far
+    size_t &configured = configured_dev[htf_current_device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(nlist_build_kernel<WITH_IDX, MAPPED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
