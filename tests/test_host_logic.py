@@ -197,3 +197,47 @@ def test_oracle_pairwise_mlp_matches_torch_autograd():
     scale = np.abs(ref).max()
     assert np.abs(out - ref).max() < 1e-5 * scale          # fp32 tolerance of the north star
     assert np.abs(ref[:, :3]).max() > 0.1
+
+
+def test_oracle_pairwise_mlp_force_is_minus_energy_gradient():
+    """oracle.pairwise_mlp's analytic du/dr against a central finite difference of its own energies (float64 weights
+    would hide nothing here: the check is on the derivative chain, tolerance set by the fp32 energy noise)."""
+    import oracle
+    rng = np.random.default_rng(0)
+    raw = np.concatenate([(rng.standard_normal(64 * 32) / np.sqrt(32)), 0.1 * rng.standard_normal(64),
+                          (rng.standard_normal(64 * 64) / 8), 0.1 * rng.standard_normal(64),
+                          (rng.standard_normal(64 * 64) / 8), 0.1 * rng.standard_normal(64),
+                          (rng.standard_normal(64) / 8), 0.1 * rng.standard_normal(1)]).astype(np.float32)
+    nl = np.zeros((1, 4, 4), dtype=np.float32)
+    nl[0, 0, :3] = [0.9, 0.3, -0.2]
+    nl[0, 1, :3] = [-1.1, 0.8, 0.5]
+    nl[0, 2, :3] = [0.2, -1.6, 0.9]                            # slot 3 stays padding
+    out = oracle.pairwise_mlp(nl, raw, 2.5)
+    h = 2e-3
+    for slot in range(3):
+        for ax in range(3):
+            a, b = nl.copy(), nl.copy()
+            a[0, slot, ax] += h; b[0, slot, ax] -= h
+            de = (oracle.pairwise_mlp(a, raw, 2.5)[0, 3] - oracle.pairwise_mlp(b, raw, 2.5)[0, 3]) / (2 * h)
+            # F_i = sum_j 2 dE_i/dd_ij (compute_nlist_forces): moving ONE slot's d changes e_i by de, its share of F is 2 de
+            a1, b1 = nl.copy(), nl.copy()
+            a1[0, :, :] = 0; b1[0, :, :] = 0
+            a1[0, 0] = nl[0, slot]; b1[0, 0] = nl[0, slot]
+            f_slot = oracle.pairwise_mlp(a1, raw, 2.5)[0, ax]   # force of a row holding only this slot
+            assert abs(f_slot - 2 * de) < 2e-3 * max(1.0, abs(f_slot)), (slot, ax, f_slot, 2 * de)
+    assert np.isfinite(out).all()
+
+
+def test_slab_plan_and_roi_cover_the_halo():
+    """host-side planning of the slab exchange: capacity covers both faces, the ROI covers the slab +- r_cut."""
+    from htf import parallel, synthetic
+    pos, lo, hi = synthetic.lattice_fluid((8, 8, 32), 0.7, seed=4)
+    a, b = parallel.row_shard(pos.shape[0], 4, 1)
+    shard = pos[a:b]
+    lo_face, hi_face, width, cap = parallel.slab_plan(shard, 2, 2.5)
+    z = shard[:, 2]
+    assert lo_face == float(z.min()) and hi_face == float(z.max()) and width > 2.5
+    assert cap >= max((z < lo_face + width).sum(), (z > hi_face - width).sum()) and cap % 256 == 0
+    c, hw = parallel.roi_for_rows(shard, lo, hi, 2.5)
+    assert hw[2] >= 0 and c[2] - hw[2] <= lo_face - 2.5 and c[2] + hw[2] >= hi_face + 2.5
+    assert hw[0] < 0 and hw[1] < 0                               # x and y span the box: unrestricted
