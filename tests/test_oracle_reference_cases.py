@@ -198,3 +198,24 @@ def test_eds_layer_statistics(oracle_mod):
     # cv above the set point: gradient = -2 (mean - sp) ssd / period / 2 < 0 -> Adam moves alpha up
     assert alphas[9] > 0.0 and alphas[19] > alphas[9]
     assert eds.n == 0 and eds.t == 3
+
+
+def test_oracle_reproduces_golden_fixtures():
+    """tests/golden/*.npz (made by tests/golden/make_golden.py after an analytic float64 LJ check) pin the oracle."""
+    import glob
+    import os
+    import oracle
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert len(files) >= 3
+    for f in files:
+        g = np.load(f)
+        K, r_cut = int(g["K"]), float(g["r_cut"])
+        nl, idx, cnt = oracle.nlist(g["pos"], g["lo"], g["hi"], r_cut, K)
+        key = np.where(idx < 0, np.iinfo(np.int32).max, idx)
+        order = np.argsort(key, axis=1, kind="stable")
+        assert np.array_equal(np.take_along_axis(idx, order, axis=1), g["idx_sorted"]), f
+        assert np.array_equal(np.take_along_axis(nl, order[:, :, None], axis=1).view(np.uint32), g["nlist_sorted"].view(np.uint32)), f
+        assert np.array_equal(cnt, g["count"])
+        fe, _, v6 = oracle.lj(nl)
+        assert np.array_equal(fe, g["force_energy"]) and np.array_equal(v6, g["virial6"]), f
+        assert np.array_equal(oracle.rdf_hist(nl, (0.0, r_cut), 100), g["rdf_hist"]), f
