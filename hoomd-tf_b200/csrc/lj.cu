@@ -96,10 +96,12 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
 #pragma unroll
             for (int u = 0; u < LJ_UNROLL; u++) {
                 const float dx = d[u].x, dy = d[u].y, dz = d[u].z;
+                float r_guess = 0.f;                     // RDF: any r within a fraction of a bin of the exact one
                 if (FORCES) {
                     const float ax = dx + 1e-7f, ay = dy + 1e-7f, az = dz + 1e-7f;
                     const float rt2 = ax * ax + ay * ay + az * az;
                     const float rt = sqrtf(rt2);
+                    r_guess = rt;
                     if (rt > 3e-6f) {
                         // 1/(rt + 3e-6) (nlist_rinv) is IEEE-rounded: its error is amplified 13x by s^13;
                         // the 1/rt of the gradient enters linearly, the 2-ulp MUFU.RSQ is enough there
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                         if (CV) {
                             // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a
                             const float x = rt * p.cv_inv_r0, x2 = x * x, x6 = x2 * x2 * x2;
-                            const float sw = 1.0f / (1.0f + x6);
+                            const float sw = __fdividef(1.0f, 1.0f + x6);      // 1-ulp reciprocal: 1e-7 relative on s
                             cn += sw;
                             const float cg = -6.0f * x6 * sw * sw * irt * irt;
                             gx += cg * ax; gy += cg * ay; gz += cg * az;
@@ -135,11 +137,15 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                         if (p.type_j >= 0) m = (d[u].w == (float)p.type_j) ? 1.0f : 0.0f;
                         const float x = __fmul_rn(dx, m), y = __fmul_rn(dy, m), z = __fmul_rn(dz, m);
                         const float q = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-                        // first guess from an approximate r, then the exact threshold table decides
-                        int g = (int)((__fsqrt_rn(q) - p.r_lo) * p.inv_step);
+                        // first guess from an approximate r (off by far less than a bin), then the exact threshold
+                        // table decides: thr[g] <= q < thr[g+1], thr[0] = 0, thr[nb] = +inf, so one step each way is
+                        // enough and the clamps make both look-ups safe
+                        if (!FORCES) r_guess = q * rsqrtf(fmaxf(q, 1e-30f));
+                        int g = (int)((r_guess - p.r_lo) * p.inv_step);
                         g = max(0, min(p.nb - 1, g));
-                        while (g < p.nb - 1 && q >= s_thr[g + 1]) g++;
-                        while (g > 0 && q < s_thr[g]) g--;
+                        if (p.type_j >= 0 && m == 0.0f) g = 0;              // masked entry: q = 0 whatever r was
+                        g += (q >= s_thr[g + 1]) ? 1 : 0;
+                        g -= (q < s_thr[g]) ? 1 : 0;
                         if (g == 0) bin0++;
                         else atomicAdd(my_hist + g, 1);
                     }

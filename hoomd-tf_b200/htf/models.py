@@ -243,9 +243,8 @@ class EDSCoordinationModel(SimModel):
         self.cv_avg.update_state(cv)
         alpha = self.eds_bias(cv)
         scale = (alpha / n.to(torch.float32))[0]
-        forces = fe.clone()
-        forces[:, :3] += (2.0 * scale) * cv_row[:, :3]
-        forces[:, 3] += scale * cv_row[:, 3]
+        # one contiguous pass: (F, e) += (2 s, 2 s, 2 s, s) * (grad sums, cn)
+        forces = torch.addcmul(fe, cv_row, torch.stack([2.0 * scale, 2.0 * scale, 2.0 * scale, scale]))
         if bins is not None:
             self.last_bins = bins
             rdf, _ = rdf_from_hist(bins, self.rdf_range, self.nbins)
