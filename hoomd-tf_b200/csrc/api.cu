@@ -340,6 +340,22 @@ int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, fl
     return HTF_OK;
 }
 
+int htf_eds_step(htf_ctx *ctx, const float *d_cv, const float *d_set_point, float *d_mean, float *d_ssd, int32_t *d_n,
+                 float *d_alpha, float *d_adam_m, float *d_adam_v, float *d_adam_t, int period, float learning_rate,
+                 float cv_scale, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_cv || !d_set_point || !d_mean || !d_ssd || !d_n || !d_alpha || !d_adam_m || !d_adam_v || !d_adam_t || period < 1 ||
+        !(cv_scale != 0.0f)) {
+        set_err(ctx, "htf_eds_step: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_eds_step(ctx, d_cv, d_set_point, d_mean, d_ssd, d_n, d_alpha, d_adam_m, d_adam_v, d_adam_t, period,
+                                      learning_rate, cv_scale, (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_integrate_half(htf_ctx *ctx, int half, float *d_pos, float *d_vel, const float *d_force, int64_t n, float dt,
                        float gamma, float kT, int flat, uint64_t seed, uint64_t timestep, void *stream)
 {

@@ -98,6 +98,9 @@ inline int htf_current_device_slot()
     return d % HTF_MAX_DEVICES;
 }
 
+cudaError_t htf_launch_eds_step(htf_ctx *ctx, const float *cv, const float *set_point, float *mean, float *ssd, int *n,
+                                float *alpha, float *adam_m, float *adam_v, float *adam_t, int period, float lr,
+                                float cv_scale, cudaStream_t st);
 cudaError_t htf_launch_integrate(htf_ctx *ctx, int half, float4 *pos, float *vel, const float4 *force, int64_t n, float dt,
                                  float gamma, float kT, int flat, unsigned long long seed, unsigned long long step,
                                  cudaStream_t st);

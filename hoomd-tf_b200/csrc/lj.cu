@@ -295,3 +295,45 @@ cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, in
     if (virial) return bins ? launch_pair<true, true, true, true>(ctx, p, st) : launch_pair<true, true, false, true>(ctx, p, st);
     return bins ? launch_pair<true, false, true, true>(ctx, p, st) : launch_pair<true, false, false, true>(ctx, p, st);
 }
+
+// ---- EDS bias update (htf/layers.py:142-195 EDSLayer.call), one thread: the whole per-step state machine -- Welford
+// mean / ssd over the second half of the period, one tf.compat.v1 Adam step at n == period - 1 -- as a single launch
+// on device-resident state instead of ~50 element-wise launches.  fp32, same operation order as the reference. ----
+namespace {
+__global__ void eds_step_kernel(const float *__restrict__ cv_p, const float *__restrict__ set_point, float *mean, float *ssd,
+                                int *n_p, float *alpha, float *adam_m, float *adam_v, float *adam_t, int period, float lr,
+                                float cv_scale)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float cv = *cv_p;
+    const int n = *n_p, h = period / 2;
+    float mu = *mean, s2 = *ssd;
+    if (n == 0) { mu = 0.f; s2 = 0.f; }                                    // layers.py:161-165
+    if (n > h) {                                                            // :169-178
+        const float delta = cv - mu;
+        mu = mu + delta / (float)(n - h);
+        s2 = s2 + delta * (cv - mu);
+    }
+    if (n == period - 1) {                                                  // :181-190
+        float g = -2.0f * (mu - *set_point) * s2 / (float)period / 2.0f;
+        g = g / cv_scale;
+        const float t = *adam_t + 1.0f;
+        const float m = 0.9f * *adam_m + 0.1f * g;
+        const float v = 0.999f * *adam_v + 0.001f * (g * g);
+        const float lr_t = lr * sqrtf(1.0f - powf(0.999f, t)) / (1.0f - powf(0.9f, t));
+        *alpha = *alpha - lr_t * m / (sqrtf(v) + 1e-8f);
+        *adam_t = t; *adam_m = m; *adam_v = v;
+    }
+    *mean = mu; *ssd = s2;
+    *n_p = (n + 1) % period;                                                // :193
+}
+}  // namespace
+
+cudaError_t htf_launch_eds_step(htf_ctx *ctx, const float *cv, const float *set_point, float *mean, float *ssd, int *n,
+                                float *alpha, float *adam_m, float *adam_v, float *adam_t, int period, float lr,
+                                float cv_scale, cudaStream_t st)
+{
+    eds_step_kernel<<<1, 32, 0, st>>>(cv, set_point, mean, ssd, n, alpha, adam_m, adam_v, adam_t, period, lr, cv_scale);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
 FLAG_DETERMINISTIC = 1
@@ -27,6 +27,7 @@ SYMBOLS = {
     "htf_set_box": (_i32, [_vp, _fp3, _fp3, _fp3]),
     "htf_set_roi": (_i32, [_vp, _fp3, _fp3]),
     "htf_pack_halo": (_i32, [_vp, _vp, _i64, _i32, _f32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "htf_eds_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp]),
     "htf_integrate_half": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _i32, ctypes.c_uint64, ctypes.c_uint64, _vp]),
     "htf_skin_configure": (_i32, [_vp, _f32, _i32]),
     "htf_skin_rebuild": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp]),

@@ -99,6 +99,13 @@ class HtfContext:
                                              _ptr(counts), _ptr(self._overflow), self._stream()))
         return out_lo, out_hi
 
+    def eds_step(self, cv, layer):
+        """One EDSLayer update on the device (``layer``: htf.layers.EDSLayer with CUDA float32 state)."""
+        self._ck(self.lib.htf_eds_step(self._h, _ptr(cv), _ptr(layer.set_point), _ptr(layer.mean), _ptr(layer.ssd),
+                                       _ptr(layer.n), _ptr(layer.alpha), _ptr(layer.adam_m), _ptr(layer.adam_v),
+                                       _ptr(layer.adam_t), int(layer.period), float(layer.learning_rate),
+                                       float(layer.cv_scale), self._stream()))
+
     def integrate_half(self, half, pos, vel, force, dt, gamma=0.0, kT=0.0, flat=False, seed=0, timestep=0):
         """Velocity-Verlet half step on the device (half 0: kick + drift + wrap, half 1: kick); see include/htf_b200.h."""
         _check_dev_f32(pos, "positions", 4)

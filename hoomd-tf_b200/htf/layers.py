@@ -60,6 +60,7 @@ class EDSLayer(torch.nn.Module):
         if isinstance(set_point, int) or (torch.is_tensor(set_point) and not set_point.is_floating_point()):
             raise ValueError("EDS only works with floats, not dtype " + str(type(set_point)))
         self.name = name
+        self.fused = True               # CUDA tensors: htf_eds_step; False keeps the torch formulas (the CPU/test reference)
         self.period = int(period)
         self.cv_scale = float(cv_scale)
         self.learning_rate = float(learning_rate)
@@ -84,6 +85,11 @@ class EDSLayer(torch.nn.Module):
             if b.device != cv.device:
                 self.to(cv.device)
                 break
+        if cv.is_cuda and self.fused:
+            # one libhtf_b200 launch on the device-resident state instead of ~50 element-wise ones
+            from . import ops
+            ops.default_context(cv.device).eds_step(cv.reshape(()).contiguous(), self)
+            return self.alpha.clone()
         h = self.period // 2
         reset_mask = (self.n != 0).to(torch.float32)
         self.mean.mul_(reset_mask)

@@ -230,7 +230,10 @@ class EDSCoordinationModel(SimModel):
         import torch.distributed as dist
         from .simmodel import rdf_from_hist
         fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins)
-        n = torch.tensor([float(nlist.shape[0])], dtype=torch.float64, device=fe.device)
+        key = (int(nlist.shape[0]), fe.device)
+        if getattr(self, "_n_key", None) != key:                # the row count as a device scalar, made once per shape
+            self._n_key, self._n_dev = key, torch.tensor([float(nlist.shape[0])], dtype=torch.float64, device=fe.device)
+        n = self._n_dev
         if self.group is not None or (dist.is_available() and dist.is_initialized() and self.group is not False):
             g = self.group if self.group not in (None, False) else None
             if dist.is_initialized() and dist.get_world_size(g) > 1:

@@ -54,7 +54,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 12
+#define HTF_ABI_VERSION 13
 int htf_abi_version(void);
 
 /*
@@ -113,6 +113,17 @@ int htf_pack_halo(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float t
 int htf_pack_halo_pair(htf_ctx *ctx, const float *d_pos, int64_t n, int axis, float threshold_lo, float threshold_hi,
                        float *d_out_lo, float *d_out_hi, int64_t capacity, int32_t *d_counts, int32_t *d_overflow,
                        void *stream);
+
+/*
+ * EDSLayer.call (htf/layers.py:142-195) as one launch on device-resident scalars: Welford mean / ssd of the collective
+ * variable over the second half of every `period` calls, one tf.compat.v1 Adam step (beta1 .9, beta2 .999, eps 1e-8,
+ * lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)) on alpha at call period - 1, n <- (n + 1) mod period.  d_cv is the current
+ * collective variable (device scalar); all state is fp32 except the int32 counter d_n.  The bias energy alpha * CV and
+ * its forces are applied by the caller (htf_lj_cv_forces gives the CV's gradient row sums).
+ */
+int htf_eds_step(htf_ctx *ctx, const float *d_cv, const float *d_set_point, float *d_mean, float *d_ssd, int32_t *d_n,
+                 float *d_alpha, float *d_adam_m, float *d_adam_v, float *d_adam_t, int period, float learning_rate,
+                 float cv_scale, void *stream);
 
 /*
  * The step either side of the path (what HOOMD's integrator does around the reference's compute:

@@ -553,3 +553,20 @@ def test_cuda_path_matches_golden_fixtures():
         assert_close_rel(v6.cpu().numpy(), g["virial6"], what="golden virial " + os.path.basename(f))
         h = ctx.rdf_hist(nl, (0.0, r_cut), 100).cpu().numpy()
         assert np.array_equal(h, g["rdf_hist"]), f
+
+
+def test_eds_step_kernel_matches_oracle_and_torch_layers(oracle_mod):
+    """htf_eds_step (one launch) against the scalar oracle restatement and the torch masked-arithmetic layer."""
+    import htf
+    fused = htf.layers.EDSLayer(4.0, 6, learning_rate=5e-2, cv_scale=2.0).cuda()
+    plain = htf.layers.EDSLayer(4.0, 6, learning_rate=5e-2, cv_scale=2.0).cuda()
+    plain.fused = False
+    ref = oracle_mod.EDSLayer(4.0, 6, 5e-2, 2.0)
+    rng = np.random.default_rng(3)
+    for i in range(40):
+        cv = float(np.float32(3.0 + rng.normal() * 0.5))
+        a = float(fused(torch.tensor(cv, device="cuda")))
+        b = float(plain(torch.tensor(cv, device="cuda")))
+        c = float(ref(cv))
+        assert abs(a - c) <= 2e-6 * max(1.0, abs(c)) and abs(b - c) <= 2e-6 * max(1.0, abs(c)), (i, a, b, c)
+    assert abs(float(fused.alpha)) > 1e-3 and int(fused.n) == 40 % 6
