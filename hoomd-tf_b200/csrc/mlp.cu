@@ -39,8 +39,17 @@ namespace {
 constexpr int MLP_F = 32;       // radial basis features
 constexpr int MLP_H = 64;       // hidden width
 constexpr int MLP_TM = 128;     // pairs per tile = UMMA M
-constexpr int MLP_SLOTS = 2;    // tile slots per CTA, two warpgroups (column halves) each
-constexpr int MLP_THREADS = MLP_SLOTS * 2 * MLP_TM;
+constexpr int MLP_SLOTS = 2;    // tile slots per CTA
+#ifndef HTF_MLP_PARTS
+#define HTF_MLP_PARTS 2
+#endif
+constexpr int MLP_PARTS = HTF_MLP_PARTS;        // warpgroups per slot: each takes 64 / MLP_PARTS output columns per layer
+                                                // (measured at 1M x 64: 2 -> 6.7 ms, 4 -> 7.9 ms: more barrier participants,
+                                                //  duplicated per-thread set-up, no gain in latency hiding)
+constexpr int MLP_THREADS = MLP_SLOTS * MLP_PARTS * MLP_TM;
+constexpr int PART_COLS = MLP_H / MLP_PARTS;    // fp32 accumulator columns per thread and layer
+constexpr int PART_PAIRS = MLP_F / 2 / MLP_PARTS;   // radial basis centre pairs per thread
+static_assert(MLP_PARTS == 2 || MLP_PARTS == 4, "two or four warpgroups per slot");
 // TMEM columns: per slot Z | Z' (fp32 accumulators) and H | H' (bf16 pairs, A operands); one shared ones block
 constexpr int TM_Z = 0, TM_ZP = 64, TM_H = 128, TM_HP = 160, TM_SLOT = 192, TM_ONES = MLP_SLOTS * TM_SLOT;
 
@@ -158,11 +167,14 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar_s)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
 
-// slot-local barrier: the 256 threads (two warpgroups) of one slot, named barrier 1 + slot
-__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
-// epilogue token: named barriers 3 + slot, 512 participants = the waiting slot (bar.sync) + the releasing slot (bar.arrive)
-__device__ __forceinline__ void token_wait(int slot) { asm volatile("bar.sync %0, 512;" ::"r"(slot + 3) : "memory"); }
-__device__ __forceinline__ void token_arrive(int slot) { asm volatile("bar.arrive %0, 512;" ::"r"(slot + 3) : "memory"); }
+// slot-local barrier: the warpgroups of one slot, named barrier 1 + slot
+__device__ __forceinline__ void slot_sync(int slot)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(MLP_PARTS * MLP_TM) : "memory");
+}
+// epilogue token: named barriers 3 + slot, all threads take part = the waiting slot (bar.sync) + the releasing slot (bar.arrive)
+__device__ __forceinline__ void token_wait(int slot) { asm volatile("bar.sync %0, %1;" ::"r"(slot + 3), "n"(MLP_THREADS) : "memory"); }
+__device__ __forceinline__ void token_arrive(int slot) { asm volatile("bar.arrive %0, %1;" ::"r"(slot + 3), "n"(MLP_THREADS) : "memory"); }
 
 #define TMEM_LD16(taddr, v, o)                                                                              \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
@@ -175,6 +187,9 @@ __device__ __forceinline__ void token_arrive(int slot) { asm volatile("bar.arriv
                  ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),  \
                    "r"(v[o + 6]), "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]),           \
                    "r"(v[o + 12]), "r"(v[o + 13]), "r"(v[o + 14]), "r"(v[o + 15]) : "memory")
+#define TMEM_ST4(taddr, v)                                                                                  \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"                               \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory")
 #define TMEM_ST8(taddr, v)                                                                                  \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                   \
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory")
@@ -293,8 +308,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_force_kernel(const MlpPara
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int t = threadIdx.x;
-    const int slot = t >> 8, half = (t >> 7) & 1, lt = t & 127, lw = lt >> 5;
-    const bool slot_warp0 = (t & 255) < 32;                 // issues this slot's UMMAs and TMA copies
+    const int slot = t / (MLP_PARTS * MLP_TM), part = (t >> 7) % MLP_PARTS, lt = t & 127, lw = lt >> 5;
+    const bool slot_warp0 = (t % (MLP_PARTS * MLP_TM)) < 32;   // issues this slot's UMMAs and TMA copies
     const unsigned sbase = smem_u32(smem);
     const unsigned bar_s = sbase + SM_BAR + 8u * slot;                     // UMMA completion
     const unsigned ldbar_s = sbase + SM_BAR + 8u * MLP_SLOTS + 16u * slot; // pair buffers 0, 1
@@ -360,26 +375,34 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_force_kernel(const MlpPara
         const float ax = d.x + 1e-7f, ay = d.y + 1e-7f, az = d.z + 1e-7f;
         const float r = sqrtf(ax * ax + ay * ay + az * az);
 
-        // ---- radial basis and its derivative: this half's 16 centres by recurrence away from the middle.
-        //      upper half: (16,17), (18,19), ...   lower half: (14,15), (12,13), ...   (K order: rbf_centre_of_k)
+        // ---- radial basis and its derivative: this warpgroup's 32 / MLP_PARTS centres by recurrence away from the
+        //      middle: upper parts (16,17), (18,19), ...; lower parts (14,15), (12,13), ...  (K order: rbf_centre_of_k)
         {
             const float g = p.gap, s = p.inv_gap;
-            const float sgn = half ? 1.f : -1.f, c0 = half ? 16.f : 14.f;
+            const bool up = part >= MLP_PARTS / 2;
+            const int blk = part % (MLP_PARTS / 2);                       // which run of PART_PAIRS pairs inside the half
+            const float sgn = up ? 1.f : -1.f;
+            const float c0 = up ? (float)(16 + 2 * PART_PAIRS * blk) : (float)(14 - 2 * PART_PAIRS * blk);
             const float ua = r - c0 * g, ub = ua - g;
             unsigned long long ph = pk2(__expf(-ua * ua * s), __expf(-ub * ub * s));
             unsigned long long ratio = pk2(__expf(sgn * 4.f * ua - 4.f * g), __expf(sgn * 4.f * ub - 4.f * g));   // phi_{c+-2}/phi_c
             const unsigned long long kk2 = pk2(p.kk, p.kk);
             const float wbase = 2.f * c0 - 2.f * s * r, sgn4 = 4.f * sgn;  // phi'_c = (2c - 2 r/gap) phi_c
-            unsigned f[8], fd[8];
+            unsigned f[PART_PAIRS], fd[PART_PAIRS];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < PART_PAIRS; i++) {
                 const float wa = fmaf(sgn4, (float)i, wbase);
                 f[i] = bf16x2_of(ph);
                 fd[i] = bf16x2_of(mul2(ph, pk2(wa, wa + 2.f)));
-                if (i < 7) { ph = mul2(ph, ratio); ratio = mul2(ratio, kk2); }
+                if (i < PART_PAIRS - 1) { ph = mul2(ph, ratio); ratio = mul2(ratio, kk2); }
             }
-            TMEM_ST8(tz + TM_H + 8u * half + lane_off, f);
-            TMEM_ST8(tz + TM_HP + 8u * half + lane_off, fd);
+            if (PART_PAIRS == 8) {
+                TMEM_ST8(tz + TM_H + 8u * part + lane_off, f);
+                TMEM_ST8(tz + TM_HP + 8u * part + lane_off, fd);
+            } else {
+                TMEM_ST4(tz + TM_H + 4u * part + lane_off, f);
+                TMEM_ST4(tz + TM_HP + 4u * part + lane_off, fd);
+            }
         }
 
         // ---- three hidden layers and Dense(1): UMMA pair -> epilogue back into the A columns ----
@@ -396,7 +419,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_force_kernel(const MlpPara
                 }
                 __syncwarp();
             }
-            if (layer == 0 && half == 0 && pend_tile >= 0)                // previous tile's row sums, under this tile's UMMAs
+            if (layer == 0 && part == 0 && pend_tile >= 0)                // previous tile's row sums, under this tile's UMMAs
                 finish_tile(p, pend_tile, lt, pend_ax, pend_ay, pend_az, pend_r, pend_u, pend_du);
             mbar_wait(bar_s, phase);
             phase ^= 1u;
@@ -406,30 +429,37 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_force_kernel(const MlpPara
             // 6.7 ms with the token, 8.2 ms with free-running slots (they fall into phase and the MUFU pipe idles
             // through both UMMA round trips), 8.5 ms when only the MUFU burst is serialised.
             token_wait(slot);
-            unsigned z[32], zp[32], h[16], hp[16];
-            const unsigned zc = tz + lane_off + 32u * half;               // this half's 32 output columns
-            TMEM_LD16(zc + TM_Z, z, 0); TMEM_LD16(zc + TM_Z + 16, z, 16);
-            TMEM_LD16(zc + TM_ZP, zp, 0); TMEM_LD16(zc + TM_ZP + 16, zp, 16);
+            unsigned z[PART_COLS], zp[PART_COLS], h[PART_COLS / 2], hp[PART_COLS / 2];
+            const unsigned zc = tz + lane_off + (unsigned)(PART_COLS * part);    // this warpgroup's output columns
+            TMEM_LD16(zc + TM_Z, z, 0);
+            if (PART_COLS == 32) TMEM_LD16(zc + TM_Z + 16, z, PART_COLS - 16);
+            TMEM_LD16(zc + TM_ZP, zp, 0);
+            if (PART_COLS == 32) TMEM_LD16(zc + TM_ZP + 16, zp, PART_COLS - 16);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int q = 0; q < 32; q++) z[q] = __float_as_uint(tanh_approx(__uint_as_float(z[q])));
+            for (int q = 0; q < PART_COLS; q++) z[q] = __float_as_uint(tanh_approx(__uint_as_float(z[q])));
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < PART_COLS / 2; q++) {
                 h[q] = pack_bf16x2(__uint_as_float(z[2 * q]), __uint_as_float(z[2 * q + 1]));
                 hp[q] = neg_tangent_bf16x2(h[q], pack_bf16x2(__uint_as_float(zp[2 * q]), __uint_as_float(zp[2 * q + 1])));
             }
-            TMEM_ST16(tz + TM_H + 16u * half + lane_off, h, 0);
-            TMEM_ST16(tz + TM_HP + 16u * half + lane_off, hp, 0);
+            if (PART_COLS == 32) {
+                TMEM_ST16(tz + TM_H + 16u * part + lane_off, h, 0);
+                TMEM_ST16(tz + TM_HP + 16u * part + lane_off, hp, 0);
+            } else {
+                TMEM_ST8(tz + TM_H + 8u * part + lane_off, h);
+                TMEM_ST8(tz + TM_HP + 8u * part + lane_off, hp);
+            }
             token_arrive(1 - slot);
         }
-        if (half == 0) {
+        if (part == 0) {
             pend_u = __uint_as_float(tmem_ld1(tz + TM_Z + lane_off));     // u     = w4 . h3 + b4
             pend_du = -__uint_as_float(tmem_ld1(tz + TM_ZP + lane_off));  // du/dr = w4 . h3' (three sign flips, see neg_tangent)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             pend_tile = tile; pend_ax = ax; pend_ay = ay; pend_az = az; pend_r = r;
         }
     }
-    if (half == 0 && pend_tile >= 0) finish_tile(p, pend_tile, lt, pend_ax, pend_ay, pend_az, pend_r, pend_u, pend_du);
+    if (part == 0 && pend_tile >= 0) finish_tile(p, pend_tile, lt, pend_ax, pend_ay, pend_az, pend_r, pend_u, pend_du);
     // drain the pair copy staged for the round that never ran, then release the TMEM
     mbar_wait(ldbar_s + 8u * (round & 1), (unsigned)(round >> 1) & 1u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
