@@ -19,7 +19,9 @@
  *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as
  *     void*; NULL = the legacy default stream) and is asynchronous: no implicit device
  *     synchronisation (the reference ends every batch with cudaDeviceSynchronize,
- *     htf/TensorflowCompute.cc:208-211).
+ *     htf/TensorflowCompute.cc:208-211).  The exceptions are one-off or explicit: scratch growth
+ *     (cudaMalloc/cudaFree) the first time a size is seen, the 12-byte density read-back of the first
+ *     htf_build_nlist after htf_set_roi (restricted binnings only), and htf_skin_status.
  *   - one context per device, not re-entrant per context (the reference is single
  *     threaded too: htf/tf2hoomd_op/tf2hoomd.cc:11-12).
  *   - "pos" is always float[n][4] = (x, y, z, type) with the type stored as a float
