@@ -59,6 +59,7 @@ int ensure_particles(htf_ctx *ctx, int64_t n)
     int rc;
     if ((rc = dev_realloc(ctx, &ctx->d_cell_of, (size_t)n))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->d_sorted_idx, (size_t)n))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_scattered, (size_t)n))) return rc;
     if ((rc = dev_realloc(ctx, &ctx->d_spos, (size_t)n))) return rc;
     ctx->n_cap = n;
     return HTF_OK;
@@ -244,7 +245,7 @@ void htf_destroy(htf_ctx *ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     if (ctx->skin_ctx) { htf_destroy(ctx->skin_ctx); ctx->skin_ctx = nullptr; }
-    void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx,
+    void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx, ctx->d_scattered,
                     ctx->d_spos, ctx->d_nlist_scratch, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
                     ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {

@@ -148,52 +148,34 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const int *__restrict
 // lanes, then gather the positions into the cell-sorted copy.  The count-down scatter leaves the
 // indices of a cell in atomic order; sorting them makes the row-internal slot order of the
 // neighbor tensor -- and therefore every fp32 force sum -- reproducible run to run.
-template <bool SORT>
+template <bool SORT, int LPC>
 __global__ void __launch_bounds__(256) cell_order_gather_kernel(const float4 *__restrict__ pos,
                                                                 const int *__restrict__ cell_start, int ncell_win,
                                                                 int layer, int z0, int nz,
+                                                                const int *__restrict__ scattered,
                                                                 int *__restrict__ sorted_idx,
                                                                 float4 *__restrict__ spos)
 {
-    const int lane = threadIdx.x & 31;
-    const int cw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // cell inside the z-window
+    // LPC lanes per cell (a warp serves 32 / LPC cells).  Out of place: `scattered` holds the cell's members in
+    // the order the atomics of the scatter produced; the rank of a member is the number of members with a
+    // smaller index (indices are distinct), counted with broadcast loads that hit L1 -- no shuffles, no
+    // intra-warp hand-shake, any cell population.
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cw = gt / LPC, sub = gt % LPC;                                // cell inside the z-window
     if (cw >= ncell_win) return;
     const int lz = cw / layer;
     const int c = ((z0 + lz) % nz) * layer + (cw - lz * layer);
-    const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
-    const int n = e - b;
-    if (n == 0) return;
-    if (n <= 32) {
-        const int v = (lane < n) ? sorted_idx[b + lane] : 0x7fffffff;
-        int dst = lane;
-        if (SORT && n > 1) {
-            // rank by counting (indices are distinct): n shuffles instead of a 15-stage bitonic network
-            __syncwarp();                                       // every lane holds its index before any lane overwrites the run
+    const int b = __ldg(cell_start + c), n = __ldg(cell_start + c + 1) - b;
+    for (int k = sub; k < n; k += LPC) {
+        const int v = __ldg(scattered + b + k);
+        int dst = k;
+        if (SORT) {
             dst = 0;
-            for (int j = 0; j < n; j++) dst += (__shfl_sync(HTF_FULL, v, j) < v) ? 1 : 0;
-            if (lane < n) sorted_idx[b + dst] = v;
+            for (int j = 0; j < n; j++) dst += (__ldg(scattered + b + j) < v) ? 1 : 0;
         }
-        if (lane < n) spos[b + dst] = __ldg(pos + v);
-        return;
+        sorted_idx[b + dst] = v;
+        spos[b + dst] = __ldg(pos + v);
     }
-    // crowded cell (> 32 particles): serial insertion sort by one lane, then a strided gather
-    if (SORT) {
-        if (lane == 0) {
-            for (int a = b + 1; a < e; a++) {
-                const int key = sorted_idx[a];
-                int q = a - 1;
-                while (q >= b) {
-                    const int t = sorted_idx[q];
-                    if (t <= key) break;
-                    sorted_idx[q + 1] = t;
-                    q--;
-                }
-                sorted_idx[q + 1] = key;
-            }
-        }
-        __syncwarp();
-    }
-    for (int s = b + lane; s < e; s += 32) spos[s] = __ldg(pos + sorted_idx[s]);
 }
 
 // ---- cell population statistics (calibrates the staging capacities of the build kernels) ----
@@ -352,16 +334,17 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums);
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
-    cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_sorted_idx);
+    cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_scattered);
     const int layer = g.n[0] * g.n[1];
     const int ncell_win = layer * g.zcount;                     // only the cell layers the region of interest touches
-    const int cb = (ncell_win + 7) / 8;
+    constexpr int LPC = 8;
+    const int cb = (int)(((long long)ncell_win * LPC + 255) / 256);
     if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */)
-        cell_order_gather_kernel<true><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
-                                                           ctx->d_sorted_idx, ctx->d_spos);
+        cell_order_gather_kernel<true, LPC><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
+                                                                ctx->d_scattered, ctx->d_sorted_idx, ctx->d_spos);
     else
-        cell_order_gather_kernel<false><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
-                                                            ctx->d_sorted_idx, ctx->d_spos);
+        cell_order_gather_kernel<false, LPC><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
+                                                                 ctx->d_scattered, ctx->d_sorted_idx, ctx->d_spos);
     ctx->launches += 6;
     return cudaGetLastError();
 }

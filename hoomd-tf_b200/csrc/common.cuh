@@ -43,6 +43,7 @@ struct htf_ctx {
     int ncell_cap;
     int *d_cell_of;       // [n_cap]
     int *d_sorted_idx;    // [n_cap] cell-sorted slot -> particle index
+    int *d_scattered;     // [n_cap] the same before the in-cell ordering (output of the atomic scatter)
     float4 *d_spos;       // [n_cap] cell-sorted positions
     int64_t n_cap;
     int *d_stats;                 // [3] cell population statistics (see htf_cell_stats)
