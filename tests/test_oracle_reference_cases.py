@@ -219,3 +219,29 @@ def test_oracle_reproduces_golden_fixtures():
         fe, _, v6 = oracle.lj(nl)
         assert np.array_equal(fe, g["force_energy"]) and np.array_equal(v6, g["virial6"]), f
         assert np.array_equal(oracle.rdf_hist(nl, (0.0, r_cut), 100), g["rdf_hist"]), f
+
+
+def test_coordination_cv_against_float64_and_finite_differences(oracle_mod):
+    """The smooth coordination CV of BASELINE config 5 has no reference implementation: the oracle is pinned
+    against a float64 evaluation of cn_i = sum_j 1/(1 + (r/r0)^6) and a central difference of it for the gradient sums."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((5, 5, 5), 0.8442, seed=5)
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 2.8, 96)
+    r0 = 1.3
+    cn, g = oracle_mod.coordination_cv(nl, r0)
+
+    def cn64(nl_):
+        a = nl_[..., :3].astype(np.float64) + 1e-7                      # nlist_rinv's safe norm offsets
+        r = np.sqrt((a * a).sum(-1))
+        s = np.where(r > 3e-6, 1.0 / (1.0 + (r / r0) ** 6), 0.0)
+        return s.sum(1)
+    ref = cn64(nl)
+    assert np.abs(cn - ref).max() <= 1e-5 * np.abs(ref).max()
+    h = 1e-3
+    for ax in range(3):
+        up, dn = nl.astype(np.float64), nl.astype(np.float64)          # perturb in float64: h is below fp32 resolution of d
+        mask = (np.abs(nl[..., :3]).sum(-1) > 0)                          # move every real neighbor of every row along ax
+        up[..., ax] += h * mask
+        dn[..., ax] -= h * mask
+        fd = (cn64(up) - cn64(dn)) / (2 * h)
+        assert np.abs(g[:, ax] - fd).max() <= 2e-4 * max(1.0, np.abs(fd).max()), ax
