@@ -10,11 +10,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 namespace {
 
 thread_local char g_create_err[512] = "";
+
+constexpr int HTF_DEFAULT_PIPE_SLABS = 8;
 
 void set_err(htf_ctx *ctx, const char *fmt, ...)
 {
@@ -153,6 +156,87 @@ int upload_rdf_table(htf_ctx *ctx, float r_lo, float r_hi, int nbins, cudaStream
     return HTF_OK;
 }
 
+// ---- pipelined step -------------------------------------------------------------------------------------------
+// The build kernel is instruction-issue bound (it uses ~40 % of the HBM bandwidth), the pair pass is HBM bound (it
+// uses few issue slots).  Run back to back they add up; run side by side they share the SMs.  The z-window of cell
+// layers is cut into slabs: slab i is built on the caller's stream, its pair pass (walking the slab's cell-sorted
+// slots) runs on the context's auxiliary stream as soon as the slab is complete -- while slab i+1 is being built,
+// and while most of slab i's rows are still in the 126 MB L2.
+struct PassSpec {
+    bool cv;
+    float4 *fe; float *virial; int vcomp;
+    const float *thr; int nb; unsigned long long *bins;
+    float r0; float4 *cv_row; double *cv_sum;
+};
+
+int ensure_pipeline(htf_ctx *ctx, int nevents)
+{
+    if (!ctx->aux_stream) {
+        int lo = 0, hi = 0;
+        HTF_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HTF_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));   // pair pass first
+    }
+    if (nevents > ctx->pipe_events_n) {
+        cudaEvent_t *ev = static_cast<cudaEvent_t *>(realloc(ctx->pipe_events, sizeof(cudaEvent_t) * (size_t)nevents));
+        if (!ev) { set_err(ctx, "host allocation failed"); return HTF_ENOMEM; }
+        ctx->pipe_events = ev;
+        for (int i = ctx->pipe_events_n; i < nevents; i++) {
+            HTF_CUDA(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            ctx->pipe_events_n = i + 1;
+        }
+    }
+    return HTF_OK;
+}
+
+cudaError_t launch_pass(htf_ctx *ctx, const PassSpec &ps, const float4 *nl, int64_t rows, const HtfSlab *slab, cudaStream_t st)
+{
+    if (ps.cv)
+        return htf_launch_lj_cv(ctx, nl, rows, ctx->K, ps.fe, ps.virial, ps.vcomp, ps.r0, ps.cv_row, ps.cv_sum, ps.thr, ps.nb,
+                                ps.bins, st, slab);
+    return htf_launch_lj(ctx, nl, rows, ctx->K, ps.fe, ps.virial, ps.vcomp, ps.thr, ps.nb, nullptr, 0, -1, -1, ps.bins, st, slab);
+}
+
+// build rows [row_lo, row_hi) of the binned particles into nl, then the pair pass; pipelined when it pays
+int build_and_pass(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *nl, int32_t *d_overflow, const PassSpec &ps,
+                   cudaStream_t st)
+{
+    const int64_t rows = row_hi - row_lo;
+    const CellGrid &g = ctx->grid;
+    int S = ctx->pipe_slabs;
+    if (S > g.zcount / 2) S = g.zcount / 2;                       // at least two cell layers per slab
+    if (rows < 131072 || S < 2) {                                 // small systems are launch bound: plain sequence
+        HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, nl, nullptr, nullptr, d_overflow, st));
+        HTF_CUDA(ctx, launch_pass(ctx, ps, nl, rows, nullptr, st));
+        return HTF_OK;
+    }
+    // slab boundaries in window-relative layers; a slab never crosses the periodic wrap of the window
+    std::vector<int> cut;
+    for (int i = 0; i <= S; i++) cut.push_back((int)((int64_t)i * g.zcount / S));
+    const int lw = g.n[2] - g.z0;
+    if (lw > 0 && lw < g.zcount) { cut.push_back(lw); std::sort(cut.begin(), cut.end()); cut.erase(std::unique(cut.begin(), cut.end()), cut.end()); }
+    const int nslab = (int)cut.size() - 1;
+    int rc = ensure_pipeline(ctx, nslab + 1);
+    if (rc) return rc;
+    const int layer = g.n[0] * g.n[1];
+    for (int i = 0; i < nslab; i++) {
+        const int la = cut[i], cnt = cut[i + 1] - cut[i];
+        HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, nl, nullptr, nullptr, d_overflow, st, la, cnt));
+        HTF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[i], st));
+        HTF_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->pipe_events[i], 0));
+        const int za = (g.z0 + la) % g.n[2];
+        HtfSlab slab;
+        slab.sorted_idx = ctx->d_sorted_idx;
+        slab.slot_lo = ctx->d_cell_start + (size_t)za * layer;
+        slab.slot_hi = ctx->d_cell_start + (size_t)(za + cnt) * layer;
+        slab.row_lo = row_lo; slab.row_hi = row_hi;
+        const int64_t expect = (int64_t)((double)rows * cnt / g.zcount * 1.25) + 1024;
+        HTF_CUDA(ctx, launch_pass(ctx, ps, nl, expect, &slab, ctx->aux_stream));
+    }
+    HTF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[nslab], ctx->aux_stream));
+    HTF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_events[nslab], 0));
+    return HTF_OK;
+}
+
 }  // namespace
 
 cudaError_t htf_ensure_tile_flags(htf_ctx *ctx, int ntiles)
@@ -229,6 +313,8 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device; ctx->sm_count = sms; ctx->flags = flags; ctx->n_max = n_max; ctx->K = k;
     ctx->r_cut = r_cut; ctx->map_type_start = -1;
+    ctx->pipe_slabs = HTF_DEFAULT_PIPE_SLABS;
+    if (const char *e = getenv("HTF_PIPE_SLABS")) ctx->pipe_slabs = atoi(e);
     for (int a = 0; a < 3; a++) ctx->grid.roi_h[a] = -1.0f;
     DeviceGuard guard(device);
     int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
@@ -254,6 +340,9 @@ void htf_destroy(htf_ctx *ctx)
         if (e != cudaSuccess && getenv("HTF_DEBUG"))
             fprintf(stderr, "htf_destroy: cudaFree #%zu %p: %s\n", i, ptrs[i], cudaGetErrorString(e));
     }
+    for (int i = 0; i < ctx->pipe_events_n; i++) cudaEventDestroy(ctx->pipe_events[i]);
+    free(ctx->pipe_events);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     (void)cudaGetLastError();       // never leave a sticky error behind for the next context
     delete ctx;
 }
@@ -671,17 +760,66 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
         }
         nl = ctx->d_nlist_scratch;
     }
-    HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(nl), nullptr, nullptr,
-                                   d_overflow, st));
-    const float *thr = nullptr;
-    int nb = 0;
+    PassSpec ps = {};
+    ps.cv = false;
+    ps.fe = reinterpret_cast<float4 *>(d_force_energy); ps.virial = d_virial; ps.vcomp = virial_components;
+    ps.bins = reinterpret_cast<unsigned long long *>(d_bins);
     if (d_bins) {
+        if (nbins + 2 > 1024) { set_err(ctx, "htf_lj_step: nbins must be <= 1022"); return HTF_EINVAL; }
         if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, st))) return rc;
-        thr = ctx->d_rdf_thr; nb = nbins + 2;
+        ps.thr = ctx->d_rdf_thr; ps.nb = nbins + 2;
     }
-    HTF_CUDA(ctx, htf_launch_lj(ctx, reinterpret_cast<const float4 *>(nl), rows, ctx->K,
-                                reinterpret_cast<float4 *>(d_force_energy), d_virial, virial_components,
-                                thr, nb, nullptr, 0, -1, -1, reinterpret_cast<unsigned long long *>(d_bins), st));
+    if (rows <= 0) return HTF_OK;
+    return build_and_pass(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(nl), d_overflow, ps, st);
+}
+
+int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                   float *d_nlist_out, float r0, float *d_force_energy, float *d_virial, int virial_components,
+                   float *d_cv_row, double *d_cv_sum, int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi,
+                   int nbins, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (row_lo < 0 || row_hi > n_all || row_lo > row_hi) { set_err(ctx, "htf_lj_cv_step: bad row range"); return HTF_EINVAL; }
+    const int64_t rows = row_hi - row_lo;
+    if (!(r0 > 0.0f) || !d_cv_sum || (rows > 0 && (!d_force_energy || !d_cv_row))) {
+        set_err(ctx, "htf_lj_cv_step: bad arguments"); return HTF_EINVAL;
+    }
+    if (d_virial && virial_components != 6 && virial_components != 9) {
+        set_err(ctx, "htf_lj_cv_step: virial_components must be 6 or 9"); return HTF_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(ctx->device);
+    if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    float *nl = d_nlist_out;
+    if (!nl) {
+        const int64_t need = rows * ctx->K * 4;
+        if (need > ctx->nlist_scratch_elems) {
+            if ((rc = dev_realloc(ctx, &ctx->d_nlist_scratch, (size_t)need))) return rc;
+            ctx->nlist_scratch_elems = need;
+        }
+        nl = ctx->d_nlist_scratch;
+    }
+    PassSpec ps = {};
+    ps.cv = true;
+    ps.fe = reinterpret_cast<float4 *>(d_force_energy); ps.virial = d_virial; ps.vcomp = virial_components;
+    ps.r0 = r0; ps.cv_row = reinterpret_cast<float4 *>(d_cv_row); ps.cv_sum = d_cv_sum;
+    ps.bins = reinterpret_cast<unsigned long long *>(d_bins);
+    if (d_bins) {
+        if (nbins + 2 > 1024) { set_err(ctx, "htf_lj_cv_step: nbins must be <= 1022"); return HTF_EINVAL; }
+        if ((rc = upload_rdf_table(ctx, r_lo, r_hi, nbins, st))) return rc;
+        ps.thr = ctx->d_rdf_thr; ps.nb = nbins + 2;
+    }
+    if (rows <= 0) return HTF_OK;
+    return build_and_pass(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(nl), d_overflow, ps, st);
+}
+
+int htf_set_pipeline(htf_ctx *ctx, int slabs)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slabs < 0 || slabs > 256) { set_err(ctx, "htf_set_pipeline: slabs must be in [0, 256]"); return HTF_EINVAL; }
+    ctx->pipe_slabs = slabs;
     return HTF_OK;
 }
 

@@ -70,6 +70,11 @@ struct htf_ctx {
     float *d_rdf_thr;
     float rdf_lo, rdf_hi;
     int rdf_nbins;
+    // pipelined step: the force pass of cell-layer slab i runs on `aux` while slab i+1 is being built
+    cudaStream_t aux_stream;
+    cudaEvent_t *pipe_events;     // [pipe_events_n]: slab built (i), [last]: aux done
+    int pipe_events_n;
+    int pipe_slabs;               // slabs per step (<= 1: no pipelining)
     int64_t launches;
     char err[512];
 };
@@ -77,12 +82,23 @@ struct htf_ctx {
 // ---- launchers (each returns a cudaError_t from the launch) ----
 cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n, cudaStream_t st);
 
+// zcnt >= 0 restricts the build to cell layers [zoff, zoff + zcnt) of the context's z-window
 cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *out, int32_t *idx_out,
-                             int32_t *count_out, int32_t *overflow, cudaStream_t st);
+                             int32_t *count_out, int32_t *overflow, cudaStream_t st, int zoff = 0, int zcnt = -1);
+
+// Slab mode of the pair pass (pipelined step): walk the cell-sorted slots [*slot_lo, *slot_hi) (device values,
+// e.g. two entries of cell_start) and evaluate row sorted_idx[slot] - row_lo for particles inside [row_lo, row_hi).
+// `rows` of the launcher is then only the expected number of rows (grid sizing).
+struct HtfSlab {
+    const int *sorted_idx;
+    const int *slot_lo, *slot_hi;
+    long long row_lo, row_hi;
+};
 
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                           int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
-                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st);
+                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st,
+                          const HtfSlab *slab = nullptr);
 
 cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *row_type,
                            long long row_type_stride, const float *thr, int nb, int type_i, int type_j,
@@ -114,7 +130,7 @@ cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int ax
 
 cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                              int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
-                             unsigned long long *bins, cudaStream_t st);
+                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab = nullptr);
 
 int htf_mlp_packed_bytes_host();
 int htf_mlp_raw_count_host();

@@ -39,14 +39,16 @@ __global__ void __launch_bounds__(256) integrate_first_kernel(const IntegratePar
     if (i >= p.n) return;
     const float4 f = p.force[i];
     float vx = p.vel[3 * i], vy = p.vel[3 * i + 1], vz = p.vel[3 * i + 2];
-    float ax = f.x, ay = f.y, az = f.z;
+    // friction acts whenever gamma > 0 (gamma = 0 makes it a no-op), the random impulse only when kT > 0:
+    // a damped kT = 0 run gets the same friction in both half kicks
+    float ax = f.x - p.gamma * vx, ay = f.y - p.gamma * vy, az = f.z - p.gamma * vz;
     if (LANGEVIN) {
         curandStatePhilox4_32_10_t st;
         curand_init(p.seed, (unsigned long long)i, p.step * 8ull, &st);
         const float4 g = curand_normal4(&st);
-        ax += -p.gamma * vx + p.noise * g.x;
-        ay += -p.gamma * vy + p.noise * g.y;
-        az += -p.gamma * vz + p.noise * (p.flat ? 0.f : g.z);
+        ax += p.noise * g.x;
+        ay += p.noise * g.y;
+        az += p.noise * (p.flat ? 0.f : g.z);
     }
     const float h = 0.5f * p.dt;
     vx += h * ax; vy += h * ay; vz += h * az;

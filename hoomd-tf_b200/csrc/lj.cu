@@ -48,6 +48,11 @@ struct PairParams {
     float cv_inv_r0;
     float4 *cv_row;            // [rows]: (sum_j ds/dd_ij (x,y,z), sum_j s(r_ij))
     double *cv_sum;            // += sum over rows of the coordination number
+    // slab mode (pipelined step): the pass walks cell-sorted slots [*slot_lo, *slot_hi) and handles row
+    // row_map[slot] - map_row_lo when that particle belongs to [map_row_lo, map_row_hi)
+    const int *row_map;
+    const int *slot_lo, *slot_hi;
+    long long map_row_lo, map_row_hi;
 };
 
 template <int LPR, bool FORCES, bool VIRIAL, bool RDF, bool CV>
@@ -73,10 +78,20 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
         __syncthreads();
     }
 
-    const long long groups = (p.rows + RPW - 1) / RPW;      // one warp-iteration = RPW rows
+    long long nrows = p.rows, slot0 = 0;
+    if (p.row_map) {
+        slot0 = __ldg(p.slot_lo);
+        nrows = (long long)__ldg(p.slot_hi) - slot0;
+    }
+    const long long groups = (nrows + RPW - 1) / RPW;       // one warp-iteration = RPW rows
     for (long long gi = (long long)blockIdx.x * WARPS + warp; gi < groups; gi += (long long)gridDim.x * WARPS) {
-        const long long row = gi * RPW + lane / LPR;
-        const bool active = row < p.rows;
+        long long row = gi * RPW + lane / LPR;
+        bool active = row < nrows;
+        if (p.row_map) {
+            const long long o = active ? (long long)__ldg(p.row_map + slot0 + row) : -1;
+            active = o >= p.map_row_lo && o < p.map_row_hi;
+            row = o - p.map_row_lo;
+        }
         const float4 *rp = p.nlist + (active ? row : 0) * K;
         float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
         float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
@@ -185,9 +200,10 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
             if (VIRIAL && active) {
                 if (p.vcomp == 6) {
                     // xx,xy,xz,yy,yz,zz  (htf/TensorflowCompute.cc:294-299)
-                    if (sub < 6) {
-                        const float v = sub == 0 ? vxx : sub == 1 ? vxy : sub == 2 ? vxz : sub == 3 ? vyy : sub == 4 ? vyz : vzz;
-                        p.virial[row * 6 + sub] = -v;
+                    // LPR < 6 lanes (K < 24) each take several components
+                    for (int c = sub; c < 6; c += LPR) {
+                        const float v = c == 0 ? vxx : c == 1 ? vxy : c == 2 ? vxz : c == 3 ? vyy : c == 4 ? vyz : vzz;
+                        p.virial[row * 6 + c] = -v;
                     }
                 } else {
                     for (int c = sub; c < 9; c += LPR) {
@@ -246,12 +262,21 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 
 }  // namespace
 
+static void set_slab(PairParams &p, const HtfSlab *slab)
+{
+    p.row_map = nullptr; p.slot_lo = p.slot_hi = nullptr; p.map_row_lo = p.map_row_hi = 0;
+    if (!slab) return;
+    p.row_map = slab->sorted_idx; p.slot_lo = slab->slot_lo; p.slot_hi = slab->slot_hi;
+    p.map_row_lo = slab->row_lo; p.map_row_hi = slab->row_hi;
+}
+
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                           int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
-                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st)
+                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st, const HtfSlab *slab)
 {
     if (rows <= 0) return cudaSuccess;
     PairParams p;
+    set_slab(p, slab);
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
@@ -270,6 +295,7 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     if (rows <= 0) return cudaSuccess;
     if (nb > RDF_MAX_BINS) return cudaErrorInvalidValue;
     PairParams p;
+    set_slab(p, nullptr);
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = nullptr; p.virial = nullptr; p.vcomp = 0;
     p.thr = thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
@@ -282,10 +308,11 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
 // LJ forces + virial + smooth coordination CV (+ RDF) in one pass: the EDS-biased model of BASELINE config 5
 cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                              int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
-                             unsigned long long *bins, cudaStream_t st)
+                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab)
 {
     if (rows <= 0) return cudaSuccess;
     PairParams p;
+    set_slab(p, slab);
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
 FLAG_DETERMINISTIC = 1
@@ -46,6 +46,8 @@ SYMBOLS = {
     "htf_mlp_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp]),
     "htf_rdf_hist": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _f32, _f32, _i32, _i32, _i32, _vp, _vp]),
     "htf_lj_step": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i32, _vp]),
+    "htf_lj_cv_step": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _f32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp]),
+    "htf_set_pipeline": (_i32, [_vp, _i32]),
     "htf_launch_count": (_i64, [_vp]),
     "htf_get_cell_grid": (_i32, [_vp, ctypes.POINTER(ctypes.c_int)]),
 }

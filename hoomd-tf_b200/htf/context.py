@@ -29,8 +29,9 @@ class HtfContext:
         if not torch.cuda.is_available():
             raise RuntimeError("htf_b200 needs a CUDA device: the hot path has no CPU fallback")
         self.lib = _lib.load()
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None
-                                   else torch.device(device).index or 0)
+        idx = None if device is None else torch.device(device).index
+        # an index-less "cuda" means the process's current device (one process per GPU sets it to its rank)
+        self.device = torch.device("cuda", torch.cuda.current_device() if idx is None else idx)
         self.K = int(nneighbor_cutoff)
         self.r_cut = float(r_cut)
         self._h = ctypes.c_void_p()
@@ -302,3 +303,23 @@ class HtfContext:
                                       _ptr(virial_out), int(virial_components), _ptr(self._overflow), _ptr(bins),
                                       float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
+
+    def lj_cv_step(self, pos, r0, cv_row, cv_sum, row_lo=0, row_hi=None, nlist_out=None, force_out=None,
+                   virial_out=None, bins=None, r_range=(0.0, 1.0), nbins=100):
+        """One step of the EDS-biased config-5 model: bin, build and the fused LJ + CV (+RDF) pass, pipelined."""
+        _check_dev_f32(pos, "positions", 4)
+        n = pos.shape[0]
+        row_hi = n if row_hi is None else int(row_hi)
+        rows = row_hi - int(row_lo)
+        if force_out is None:
+            force_out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        vc = virial_out.shape[1] if virial_out is not None else 6
+        self._ck(self.lib.htf_lj_cv_step(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(nlist_out), float(r0),
+                                         _ptr(force_out), _ptr(virial_out), int(vc), _ptr(cv_row), _ptr(cv_sum),
+                                         _ptr(self._overflow), _ptr(bins), float(r_range[0]), float(r_range[1]),
+                                         int(nbins), self._stream()))
+        return force_out
+
+    def set_pipeline(self, slabs):
+        """Slabs of the pipelined step (build of slab i+1 overlaps the pair pass of slab i); <= 1 switches it off."""
+        self._ck(self.lib.htf_set_pipeline(self._h, int(slabs)))

@@ -65,11 +65,11 @@ class SimModel(torch.nn.Module):
     # -- Keras ``model(inputs, training)`` --
     def forward(self, inputs, training=False):
         inputs = list(inputs)
-        if self.output_forces or training:
-            # forces come from gradients w.r.t. the nlist / positions (htf/simmodel.py:505,542)
-            for i in (0, 1):
-                if i < len(inputs) and torch.is_tensor(inputs[i]) and inputs[i].is_floating_point():
-                    inputs[i] = inputs[i].detach().requires_grad_(True)
+        # forces come from gradients w.r.t. the nlist / positions (htf/simmodel.py:505,542); tf.gradients works for
+        # any model there (output_forces or not, training or not), so the two inputs are always differentiable leaves
+        for i in (0, 1):
+            if i < len(inputs) and torch.is_tensor(inputs[i]) and inputs[i].is_floating_point():
+                inputs[i] = inputs[i].detach().requires_grad_(True)
         prev = _STATE["training"]
         _STATE["training"] = bool(training)
         try:

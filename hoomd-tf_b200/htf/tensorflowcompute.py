@@ -141,6 +141,9 @@ class tfcompute:
         s = self.system
         if sum(abs(t) for t in s.tilt) >= 1e-4:
             self.ctx.set_box(s.box.lo, s.box.hi, s.tilt)        # raises: "box is skewed"
+        if self.ctx.box is None or list(self.ctx.box[0]) != [float(x) for x in s.box.lo] or \
+                list(self.ctx.box[1]) != [float(x) for x in s.box.hi]:
+            self.ctx.set_box(s.box.lo, s.box.hi)                # the box changed since attach (updateBox runs per step)
         n = s.N
         if self._forces.shape[0] != n:
             self._forces = torch.zeros((n, 4), dtype=torch.float32, device=s.device)

@@ -56,7 +56,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 13
+#define HTF_ABI_VERSION 14
 int htf_abi_version(void);
 
 /*
@@ -264,6 +264,29 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
                 int32_t *d_overflow,
                 int64_t *d_bins, float r_lo, float r_hi, int nbins,
                 void *stream);
+
+/*
+ * The same step for the EDS-biased model of BASELINE config 5: bin, build, then the fused LJ + smooth
+ * coordination CV (+ RDF) pass of htf_lj_cv_forces (replaces, per step, the reference's
+ * computeForces -> Python -> TF graph round trip for an EDSLayer model, htf/TensorflowCompute.cc:130-216,
+ * htf/layers.py:101-195).  d_cv_sum and d_bins are accumulated into (zero them first).
+ */
+int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                   float *d_nlist_out, float r0, float *d_force_energy, float *d_virial, int virial_components,
+                   float *d_cv_row, double *d_cv_sum, int32_t *d_overflow,
+                   int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream);
+
+/*
+ * htf_lj_step / htf_lj_cv_step pipeline the build and the pair pass: the z-window of cell layers is cut into
+ * `slabs` slabs, slab i is built on the caller's stream and its pair pass runs on a stream owned by the context
+ * while slab i+1 is being built (the build is instruction-issue bound, the pair pass HBM bound: side by side they
+ * overlap, and the pass finds most of the slab still in L2).  The caller's stream waits for the last pass, so the
+ * step is stream-ordered as a whole and can be captured into a CUDA graph (call it once outside the capture first:
+ * the auxiliary stream and events are created on first use).  slabs <= 1 switches pipelining off; the default is 8
+ * (environment override HTF_PIPE_SLABS).  Systems below 131072 rows are never pipelined.
+ * The reference runs every stage back to back and ends with cudaDeviceSynchronize (htf/TensorflowCompute.cc:208-211).
+ */
+int htf_set_pipeline(htf_ctx *ctx, int slabs);
 
 /* Number of kernels the library has launched on this context since creation
  * (bench.py's gpu_launches claim). */
