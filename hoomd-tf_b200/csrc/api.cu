@@ -17,7 +17,7 @@ namespace {
 
 thread_local char g_create_err[512] = "";
 
-constexpr int HTF_DEFAULT_PIPE_SLABS = 8;
+constexpr int HTF_DEFAULT_PIPE_SLABS = 0;   // measured on B200: the back-to-back sequence wins at cfg3
 
 void set_err(htf_ctx *ctx, const char *fmt, ...)
 {
@@ -175,6 +175,7 @@ int ensure_pipeline(htf_ctx *ctx, int nevents)
         int lo = 0, hi = 0;
         HTF_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         HTF_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));   // pair pass first
+        HTF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->build2_stream, cudaStreamNonBlocking));
     }
     if (nevents > ctx->pipe_events_n) {
         cudaEvent_t *ev = static_cast<cudaEvent_t *>(realloc(ctx->pipe_events, sizeof(cudaEvent_t) * (size_t)nevents));
@@ -215,13 +216,21 @@ int build_and_pass(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *nl, int
     const int lw = g.n[2] - g.z0;
     if (lw > 0 && lw < g.zcount) { cut.push_back(lw); std::sort(cut.begin(), cut.end()); cut.erase(std::unique(cut.begin(), cut.end()), cut.end()); }
     const int nslab = (int)cut.size() - 1;
-    int rc = ensure_pipeline(ctx, nslab + 1);
+    int rc = ensure_pipeline(ctx, nslab + 3);
     if (rc) return rc;
+    cudaEvent_t ev_binned = ctx->pipe_events[nslab], ev_aux = ctx->pipe_events[nslab + 1], ev_b2 = ctx->pipe_events[nslab + 2];
+    const bool two = ctx->pipe_build_streams > 1;
+    if (two) {
+        HTF_CUDA(ctx, cudaEventRecord(ev_binned, st));
+        HTF_CUDA(ctx, cudaStreamWaitEvent(ctx->build2_stream, ev_binned, 0));
+    }
     const int layer = g.n[0] * g.n[1];
     for (int i = 0; i < nslab; i++) {
         const int la = cut[i], cnt = cut[i + 1] - cut[i];
-        HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, nl, nullptr, nullptr, d_overflow, st, la, cnt));
-        HTF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[i], st));
+        const int lane = (two && (i & 1)) ? 1 : 0;
+        cudaStream_t bs = lane ? ctx->build2_stream : st;
+        HTF_CUDA(ctx, htf_launch_nlist(ctx, row_lo, row_hi, nl, nullptr, nullptr, d_overflow, bs, la, cnt, lane));
+        HTF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[i], bs));
         HTF_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->pipe_events[i], 0));
         const int za = (g.z0 + la) % g.n[2];
         HtfSlab slab;
@@ -229,11 +238,16 @@ int build_and_pass(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *nl, int
         slab.slot_lo = ctx->d_cell_start + (size_t)za * layer;
         slab.slot_hi = ctx->d_cell_start + (size_t)(za + cnt) * layer;
         slab.row_lo = row_lo; slab.row_hi = row_hi;
+        slab.blocks_per_sm = (i + 1 < nslab) ? ctx->pipe_pass_bps : 0;      // the last pass has the machine to itself
         const int64_t expect = (int64_t)((double)rows * cnt / g.zcount * 1.25) + 1024;
         HTF_CUDA(ctx, launch_pass(ctx, ps, nl, expect, &slab, ctx->aux_stream));
     }
-    HTF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[nslab], ctx->aux_stream));
-    HTF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_events[nslab], 0));
+    HTF_CUDA(ctx, cudaEventRecord(ev_aux, ctx->aux_stream));
+    HTF_CUDA(ctx, cudaStreamWaitEvent(st, ev_aux, 0));
+    if (two) {
+        HTF_CUDA(ctx, cudaEventRecord(ev_b2, ctx->build2_stream));
+        HTF_CUDA(ctx, cudaStreamWaitEvent(st, ev_b2, 0));
+    }
     return HTF_OK;
 }
 
@@ -314,13 +328,17 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     ctx->device = device; ctx->sm_count = sms; ctx->flags = flags; ctx->n_max = n_max; ctx->K = k;
     ctx->r_cut = r_cut; ctx->map_type_start = -1;
     ctx->pipe_slabs = HTF_DEFAULT_PIPE_SLABS;
+    ctx->pipe_pass_bps = 2;
+    ctx->pipe_build_streams = 2;
     if (const char *e = getenv("HTF_PIPE_SLABS")) ctx->pipe_slabs = atoi(e);
+    if (const char *e = getenv("HTF_PIPE_PASS_BPS")) ctx->pipe_pass_bps = atoi(e);
+    if (const char *e = getenv("HTF_PIPE_BUILD_STREAMS")) ctx->pipe_build_streams = atoi(e);
     for (int a = 0; a < 3; a++) ctx->grid.roi_h[a] = -1.0f;
     DeviceGuard guard(device);
     int rc = ensure_particles(ctx, n_max > 0 ? n_max : 1);
-    if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 8);          // [0..2] cell statistics, [4..5] flagged-tile counters
-    if (!rc && cudaMemset(ctx->d_stats, 0, 8 * sizeof(int)) != cudaSuccess) rc = HTF_ECUDA;
-    if (!rc) ctx->d_flag_count = ctx->d_stats + 4;
+    if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 16);         // [0..2] cell statistics, [6..7] skin status, [8..11] flagged-tile counters
+    if (!rc && cudaMemset(ctx->d_stats, 0, 16 * sizeof(int)) != cudaSuccess) rc = HTF_ECUDA;
+    if (!rc) ctx->d_flag_count = ctx->d_stats + 8;
     if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
     *out = ctx;
     return HTF_OK;
@@ -343,6 +361,7 @@ void htf_destroy(htf_ctx *ctx)
     for (int i = 0; i < ctx->pipe_events_n; i++) cudaEventDestroy(ctx->pipe_events[i]);
     free(ctx->pipe_events);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->build2_stream) cudaStreamDestroy(ctx->build2_stream);
     (void)cudaGetLastError();       // never leave a sticky error behind for the next context
     delete ctx;
 }
@@ -736,9 +755,9 @@ int htf_rdf_hist(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const 
     return HTF_OK;
 }
 
-int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
-                float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
-                int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream)
+static int lj_step_impl(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                        float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
+                        int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream, bool rebin)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
@@ -750,7 +769,12 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
     }
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(ctx->device);
-    if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    if (rebin) {
+        if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    } else if (!ctx->binned || ctx->n_binned != n_all) {
+        set_err(ctx, "htf_lj_rows: call htf_bin_particles on these %lld particles first", (long long)n_all);
+        return HTF_ESTATE;
+    }
     float *nl = d_nlist_out;
     if (!nl) {
         const int64_t need = rows * ctx->K * 4;
@@ -773,6 +797,22 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
     return build_and_pass(ctx, row_lo, row_hi, reinterpret_cast<float4 *>(nl), d_overflow, ps, st);
 }
 
+int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
+                int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream)
+{
+    return lj_step_impl(ctx, d_pos_all, n_all, row_lo, row_hi, d_nlist_out, d_force_energy, d_virial, virial_components,
+                        d_overflow, d_bins, r_lo, r_hi, nbins, stream, true);
+}
+
+int htf_lj_rows(htf_ctx *ctx, int64_t n_all, int64_t row_lo, int64_t row_hi, float *d_nlist_out, float *d_force_energy,
+                float *d_virial, int virial_components, int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi,
+                int nbins, void *stream)
+{
+    return lj_step_impl(ctx, nullptr, n_all, row_lo, row_hi, d_nlist_out, d_force_energy, d_virial, virial_components,
+                        d_overflow, d_bins, r_lo, r_hi, nbins, stream, false);
+}
+
 int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
                    float *d_nlist_out, float r0, float *d_force_energy, float *d_virial, int virial_components,
                    float *d_cv_row, double *d_cv_sum, int32_t *d_overflow, int64_t *d_bins, float r_lo, float r_hi,
@@ -790,7 +830,12 @@ int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t 
     }
     cudaStream_t st = (cudaStream_t)stream;
     DeviceGuard guard(ctx->device);
-    if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    if (d_pos_all) {
+        if ((rc = htf_bin_particles(ctx, d_pos_all, n_all, stream))) return rc;
+    } else if (!ctx->binned || ctx->n_binned != n_all) {      // NULL positions: the rows of the last htf_bin_particles
+        set_err(ctx, "htf_lj_cv_step: call htf_bin_particles on these %lld particles first", (long long)n_all);
+        return HTF_ESTATE;
+    }
     float *nl = d_nlist_out;
     if (!nl) {
         const int64_t need = rows * ctx->K * 4;

@@ -54,8 +54,8 @@ struct htf_ctx {
     int64_t sel_cap;
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
     int tile_flag_cap;
-    int *d_flag_count;            // two counters (inside d_stats) of tiles the tile kernel flagged, used in turn
-    int flag_parity;
+    int *d_flag_count;            // per build lane two counters (inside d_stats) of tiles the tile kernel flagged, used in turn
+    int flag_parity[2];           // lanes: builds that may run concurrently (pipelined step) use different counters
     // buffered ("skin") lists: candidates within r_cut + skin, rebuilt by htf_skin_rebuild, filtered every step
     float skin;
     int skin_kc;                  // candidate capacity per row
@@ -71,10 +71,13 @@ struct htf_ctx {
     float rdf_lo, rdf_hi;
     int rdf_nbins;
     // pipelined step: the force pass of cell-layer slab i runs on `aux` while slab i+1 is being built
-    cudaStream_t aux_stream;
-    cudaEvent_t *pipe_events;     // [pipe_events_n]: slab built (i), [last]: aux done
+    cudaStream_t aux_stream;      // pair passes
+    cudaStream_t build2_stream;   // every other slab is built here, so that one build's tail overlaps the next one's start
+    cudaEvent_t *pipe_events;     // [pipe_events_n]: slab built (i), then: binned, aux done, build2 done
     int pipe_events_n;
     int pipe_slabs;               // slabs per step (<= 1: no pipelining)
+    int pipe_pass_bps;            // blocks per SM of a slab's pair pass
+    int pipe_build_streams;       // 1 or 2
     int64_t launches;
     char err[512];
 };
@@ -84,7 +87,8 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n, cudaS
 
 // zcnt >= 0 restricts the build to cell layers [zoff, zoff + zcnt) of the context's z-window
 cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *out, int32_t *idx_out,
-                             int32_t *count_out, int32_t *overflow, cudaStream_t st, int zoff = 0, int zcnt = -1);
+                             int32_t *count_out, int32_t *overflow, cudaStream_t st, int zoff = 0, int zcnt = -1,
+                             int lane = 0);
 
 // Slab mode of the pair pass (pipelined step): walk the cell-sorted slots [*slot_lo, *slot_hi) (device values,
 // e.g. two entries of cell_start) and evaluate row sorted_idx[slot] - row_lo for particles inside [row_lo, row_hi).
@@ -93,6 +97,8 @@ struct HtfSlab {
     const int *sorted_idx;
     const int *slot_lo, *slot_hi;
     long long row_lo, row_hi;
+    int blocks_per_sm;      // > 0: cap the grid (the pass then shares every SM with the concurrent build instead of
+                            // taking the whole machine for a moment)
 };
 
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,

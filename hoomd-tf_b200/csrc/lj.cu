@@ -53,6 +53,7 @@ struct PairParams {
     const int *row_map;
     const int *slot_lo, *slot_hi;
     long long map_row_lo, map_row_hi;
+    int blocks_per_sm;         // host only: grid cap of a slab pass
 };
 
 template <int LPR, bool FORCES, bool VIRIAL, bool RDF, bool CV>
@@ -249,6 +250,8 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
     long long grid = blocks_needed;
     const long long persistent = (long long)ctx->sm_count * 8;     // 8 x 256 threads = full occupancy
     if ((RDF || CV) && grid > persistent) grid = persistent;       // fewer histogram / CV flushes
+    if (p.row_map && p.blocks_per_sm > 0 && grid > (long long)ctx->sm_count * p.blocks_per_sm)
+        grid = (long long)ctx->sm_count * p.blocks_per_sm;         // slab pass next to a running build: a slice of every SM
     if (grid < 1) grid = 1;
     switch (lpr) {
     case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
@@ -264,8 +267,9 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 
 static void set_slab(PairParams &p, const HtfSlab *slab)
 {
-    p.row_map = nullptr; p.slot_lo = p.slot_hi = nullptr; p.map_row_lo = p.map_row_hi = 0;
+    p.row_map = nullptr; p.slot_lo = p.slot_hi = nullptr; p.map_row_lo = p.map_row_hi = 0; p.blocks_per_sm = 0;
     if (!slab) return;
+    p.blocks_per_sm = slab->blocks_per_sm;
     p.row_map = slab->sorted_idx; p.slot_lo = slab->slot_lo; p.slot_hi = slab->slot_hi;
     p.map_row_lo = slab->row_lo; p.map_row_hi = slab->row_hi;
 }

@@ -194,6 +194,46 @@ struct RowState {
 // SELF adds the "is this the row's own particle" compare: only the one or two chunks that hold the rows' own
 // particles run that variant.  MASKED adds the "candidate lies past the end of the window" test (tiny grids).
 template <bool WRAP, bool MAPPED, bool MASKED, bool SELF, bool ABS>
+__device__ __forceinline__ void test_one(const NlistParams &p, const float4 c, unsigned addr, unsigned mlen_addr,
+                                         unsigned base, RowState &rs, const f32x2 one)
+{
+    const bool pv = !MASKED || addr < mlen_addr;
+    const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
+#pragma unroll
+    for (int h = 0; h < RPP / 2; h++) {
+        float q[2];
+        const f32x2 dx2 = sub2(cx, rs.x[h]), dy2 = sub2(cy, rs.y[h]), dz2 = sub2(cz, rs.z[h]);
+        if (WRAP) {
+            float dx[2], dy[2], dz[2];
+            unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
+                q[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx[u], dx[u]), __fmul_rn(dy[u], dy[u])), __fmul_rn(dz[u], dz[u]));
+            }
+        } else {
+            // (dx*dx + dy*dy) + dz*dz, every operation rounded on its own
+            unpack2(add2_exact(add2_exact(mul2(dx2, dx2), mul2(dy2, dy2), one), mul2(dz2, dz2), one), q[0], q[1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int r = 2 * h + u;
+            // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
+            bool hit = q[u] <= p.rc2;
+            if (SELF) hit = hit & (addr != rs.self_addr[r]);
+            if (MASKED) hit = hit & pv;
+            if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
+            if (hit) {
+                sts_u16_r(rs.lp[r], ABS ? addr : addr - base);
+                rs.lp[r] += 64u;                    // lists are [k][lane] u16: next k is 32 entries on
+            }
+        }
+    }
+}
+
+template <bool WRAP, bool MAPPED, bool MASKED, bool SELF, bool ABS>
 __device__ __forceinline__ void test_range(const NlistParams &p, unsigned addr, unsigned addr_end, unsigned mlen_addr,
                                            unsigned base, RowState &rs)
 {
@@ -204,40 +244,7 @@ __device__ __forceinline__ void test_range(const NlistParams &p, unsigned addr, 
 #pragma unroll 1
     for (; addr < addr_end; addr += 512u) {
         const float4 c = lds_f4_ro(addr);
-        const bool pv = !MASKED || addr < mlen_addr;
-        const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
-#pragma unroll
-        for (int h = 0; h < RPP / 2; h++) {
-            float q[2];
-            const f32x2 dx2 = sub2(cx, rs.x[h]), dy2 = sub2(cy, rs.y[h]), dz2 = sub2(cz, rs.z[h]);
-            if (WRAP) {
-                float dx[2], dy[2], dz[2];
-                unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
-                    dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
-                    dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
-                    q[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx[u], dx[u]), __fmul_rn(dy[u], dy[u])), __fmul_rn(dz[u], dz[u]));
-                }
-            } else {
-                // (dx*dx + dy*dy) + dz*dz, every operation rounded on its own
-                unpack2(add2_exact(add2_exact(mul2(dx2, dx2), mul2(dy2, dy2), one), mul2(dz2, dz2), one), q[0], q[1]);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int r = 2 * h + u;
-                // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
-                bool hit = q[u] <= p.rc2;
-                if (SELF) hit = hit & (addr != rs.self_addr[r]);
-                if (MASKED) hit = hit & pv;
-                if (MAPPED) hit = hit && (((int)c.w >= p.map_type_start) == ((int)rs.t[r] >= p.map_type_start));
-                if (hit) {
-                    sts_u16_r(rs.lp[r], ABS ? addr : addr - base);
-                    rs.lp[r] += 64u;                    // lists are [k][lane] u16: next k is 32 entries on
-                }
-            }
-        }
+        test_one<WRAP, MAPPED, MASKED, SELF, ABS>(p, c, addr, mlen_addr, base, rs, one);
     }
 }
 
@@ -941,7 +948,7 @@ size_t per_warp_bytes(int cap, int K, bool with_idx)
 }  // namespace
 
 cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float4 *out, int32_t *idx_out,
-                             int32_t *count_out, int32_t *overflow, cudaStream_t st, int zoff, int zcnt)
+                             int32_t *count_out, int32_t *overflow, cudaStream_t st, int zoff, int zcnt, int lane)
 {
     if (row_hi <= row_lo) return cudaSuccess;
     NlistParams p;
@@ -1016,9 +1023,10 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             p.cap_tile = capB;
             p.tile_flag = ctx->d_tile_flag;
             // two counters in turn: this launch counts into one, its per-cell pass zeroes the other for the next launch
-            p.flag_count = ctx->d_flag_count + (ctx->flag_parity & 1);
-            p.flag_count_next = ctx->d_flag_count + ((ctx->flag_parity + 1) & 1);
-            ctx->flag_parity ^= 1;
+            lane &= 1;
+            p.flag_count = ctx->d_flag_count + 2 * lane + (ctx->flag_parity[lane] & 1);
+            p.flag_count_next = ctx->d_flag_count + 2 * lane + ((ctx->flag_parity[lane] + 1) & 1);
+            ctx->flag_parity[lane] ^= 1;
             ctx->launches += 1;
             const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)p.g.zcount);
             e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, tg, bytes, st)

@@ -304,11 +304,27 @@ class HtfContext:
                                       float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
 
+    def lj_rows(self, n_all, row_lo, row_hi, nlist_out=None, force_out=None, virial_out=None, virial_components=6,
+                bins=None, r_range=(0.0, 1.0), nbins=100):
+        """Row batch of the LJ step on the particles of the last ``bin_particles`` (no re-binning)."""
+        rows = int(row_hi) - int(row_lo)
+        if force_out is None:
+            force_out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        if virial_out is not None:
+            virial_components = virial_out.shape[1]
+        self._ck(self.lib.htf_lj_rows(self._h, int(n_all), int(row_lo), int(row_hi), _ptr(nlist_out), _ptr(force_out),
+                                      _ptr(virial_out), int(virial_components), _ptr(self._overflow), _ptr(bins),
+                                      float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
+        return force_out
+
     def lj_cv_step(self, pos, r0, cv_row, cv_sum, row_lo=0, row_hi=None, nlist_out=None, force_out=None,
                    virial_out=None, bins=None, r_range=(0.0, 1.0), nbins=100):
         """One step of the EDS-biased config-5 model: bin, build and the fused LJ + CV (+RDF) pass, pipelined."""
-        _check_dev_f32(pos, "positions", 4)
-        n = pos.shape[0]
+        if isinstance(pos, int):
+            n, pos = pos, None                      # already binned: ``pos`` is the particle count
+        else:
+            _check_dev_f32(pos, "positions", 4)
+            n = pos.shape[0]
         row_hi = n if row_hi is None else int(row_hi)
         rows = row_hi - int(row_lo)
         if force_out is None:

@@ -16,10 +16,16 @@ from .simmodel import (MeanTensor, Mean, SimModel, compute_nlist_forces, compute
 
 
 class LJModel(SimModel):
-    """build_examples.py:67-77 / benchmark.py:12-23, fused."""
+    """build_examples.py:67-77 / benchmark.py:12-23, fused.
+
+    ``compute`` is the drop-in body for a given neighbor tensor; under ``tfcompute`` the whole row batch is ONE
+    library call instead (``fused_rows``: build + LJ pass, pipelined slab by slab, straight into the force rows)."""
 
     def compute(self, nlist, positions, box):
         return ops.lj_forces(nlist)
+
+    def fused_rows(self, tfc, n, off, hi):
+        tfc.ctx.lj_rows(n, off, hi, nlist_out=tfc._nlist_buf, force_out=tfc._forces[off:hi])
 
 
 class LJVirialModel(SimModel):
@@ -27,6 +33,10 @@ class LJVirialModel(SimModel):
 
     def compute(self, nlist, positions, box):
         return ops.lj_forces(nlist, virial=True)
+
+    def fused_rows(self, tfc, n, off, hi):
+        tfc.ctx.lj_rows(n, off, hi, nlist_out=tfc._nlist_buf, force_out=tfc._forces[off:hi],
+                        virial_out=tfc.virial6_rows()[off:hi] if self.virial else None)
 
 
 class LJRDF(SimModel):
@@ -226,13 +236,37 @@ class EDSCoordinationModel(SimModel):
         self.avg_rdf = MeanTensor()
         self.last_bins = None
 
+    fused_whole_shard_only = True      # the CV is a global quantity: row batches cannot be biased one by one
+
     def compute(self, nlist, positions, box):
+        fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins)
+        return self._finish(nlist.shape[0], fe, cv_row, cv_sum, bins)
+
+    def fused_rows(self, tfc, n, off, hi):
+        """Whole shard in one library call: build + fused LJ/CV/RDF pass, pipelined (htf_lj_cv_step)."""
+        rows, dev = hi - off, tfc._forces.device
+        st = getattr(self, "_fused_state", None)
+        if st is None or st[0].shape[0] != rows or st[0].device != dev:
+            st = (torch.empty((rows, 4), dtype=torch.float32, device=dev),
+                  torch.zeros(1, dtype=torch.float64, device=dev),
+                  torch.zeros(self.nbins + 2, dtype=torch.int64, device=dev) if self.rdf_range is not None else None,
+                  torch.empty((rows, 4), dtype=torch.float32, device=dev))
+            self._fused_state = st
+        cv_row, cv_sum, bins, fe = st
+        cv_sum.zero_()
+        if bins is not None:
+            bins.zero_()
+        tfc.ctx.lj_cv_step(n, self.r0, cv_row, cv_sum, off, hi, nlist_out=tfc._nlist_buf, force_out=fe, bins=bins,
+                           r_range=self.rdf_range if self.rdf_range is not None else (0.0, 1.0), nbins=self.nbins)
+        forces, alpha, cv = self._finish(rows, fe, cv_row, cv_sum, bins, out=tfc._forces[off:hi])
+        self.last_outputs = (alpha, cv)
+
+    def _finish(self, nrows, fe, cv_row, cv_sum, bins, out=None):
         import torch.distributed as dist
         from .simmodel import rdf_from_hist
-        fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins)
-        key = (int(nlist.shape[0]), fe.device)
+        key = (int(nrows), fe.device)
         if getattr(self, "_n_key", None) != key:                # the row count as a device scalar, made once per shape
-            self._n_key, self._n_dev = key, torch.tensor([float(nlist.shape[0])], dtype=torch.float64, device=fe.device)
+            self._n_key, self._n_dev = key, torch.tensor([float(nrows)], dtype=torch.float64, device=fe.device)
         n = self._n_dev
         if self.group is not None or (dist.is_available() and dist.is_initialized() and self.group is not False):
             g = self.group if self.group not in (None, False) else None
@@ -241,13 +275,14 @@ class EDSCoordinationModel(SimModel):
                 dist.all_reduce(packed, group=g)
                 cv_sum, n = packed[:1], packed[1:]
                 if bins is not None:
+                    bins = bins.clone()                 # keep the rank-local histogram buffer reusable
                     dist.all_reduce(bins, group=g)
         cv = (cv_sum / n).to(torch.float32)[0]
         self.cv_avg.update_state(cv)
         alpha = self.eds_bias(cv)
         scale = (alpha / n.to(torch.float32))[0]
         # one contiguous pass: (F, e) += (2 s, 2 s, 2 s, s) * (grad sums, cn)
-        forces = torch.addcmul(fe, cv_row, torch.stack([2.0 * scale, 2.0 * scale, 2.0 * scale, scale]))
+        forces = torch.addcmul(fe, cv_row, torch.stack([2.0 * scale, 2.0 * scale, 2.0 * scale, scale]), out=out)
         if bins is not None:
             self.last_bins = bins
             rdf, _ = rdf_from_hist(bins, self.rdf_range, self.nbins)

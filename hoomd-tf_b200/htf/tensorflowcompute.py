@@ -79,8 +79,11 @@ class tfcompute:
         self.dtype = torch.float32
         self._forces = torch.zeros((n, 4), dtype=torch.float32, device=system.device)
         self._virial = torch.zeros((n, 9), dtype=torch.float32, device=system.device)
+        self._virial6 = None        # [n,6] written directly by fused built-in models (what HOOMD keeps of the 3x3)
         self._nlist_buf = None
+        self._nlist_store = None    # reused [batch rows, K, 4] buffer of the fused models
         self._positions_buf = None
+        self._host = None           # pinned host mirrors (forces, virial6) filled batch by batch on a copy stream
         if self.force_mode == "tf2hoomd":
             system.forces.append(self)
         else:
@@ -148,6 +151,7 @@ class tfcompute:
         if self._forces.shape[0] != n:
             self._forces = torch.zeros((n, 4), dtype=torch.float32, device=s.device)
             self._virial = torch.zeros((n, 9), dtype=torch.float32, device=s.device)
+            self._virial6 = None
         if self.batch_size == 0 and self.model._map_nlist:
             self._start_update()
         pos = s.positions
@@ -168,15 +172,71 @@ class tfcompute:
         batch_index = 0
         r0, r1 = self.shard if self.shard is not None else (0, n)
         bs = min(bs, max(r1 - r0, 1))
+        # built-in models whose whole batch is one library call (build + pair pass, pipelined): no model call, the
+        # kernels write straight into the force / virial rows
+        fused = getattr(self.model, "fused_rows", None)
+        saving = self.save_output_period and (self._calls + 1) % self.save_output_period == 0
+        if not (fused is not None and K > 0 and self.force_mode == "tf2hoomd" and not self.train and not saving
+                and getattr(self.model, "fused", True)):
+            fused = None
+        if fused is not None and getattr(self.model, "fused_whole_shard_only", False) and bs < r1 - r0:
+            fused = None
+        if fused is not None and (self._nlist_store is None or self._nlist_store.shape[0] < min(bs, r1 - r0)
+                                  or self._nlist_store.shape[1] != K):
+            self._nlist_store = torch.empty((max(min(bs, r1 - r0), 1), K, 4), dtype=torch.float32, device=s.device)
+        if self._host is not None:
+            torch.cuda.current_stream(s.device).wait_event(self._host["done"])      # last step's copies have left
         for off in range(r0, max(r1, r0 + 1), bs):
             hi = min(r1, off + bs)
-            if K > 0:
-                self._nlist_buf = self.ctx.build_nlist(pos, off, hi, rebin=False)
+            if fused is not None:
+                if batch_index == 0:
+                    self._calls += 1
+                self._nlist_buf = self._nlist_store[:hi - off]
+                self._positions_buf = pos[off:hi]
+                fused(self, n, off, hi)
+                if self.model.check_nlist and self.ctx.overflow() >= K:
+                    raise RuntimeError("Neighbor list is full!")
             else:
-                self._nlist_buf = torch.zeros((1, 1, 4), dtype=torch.float32, device=s.device)
-            self._positions_buf = pos[off:hi]
-            self._finish_update(batch_index, off, hi)
+                if K > 0:
+                    self._nlist_buf = self.ctx.build_nlist(pos, off, hi, rebin=False)
+                else:
+                    self._nlist_buf = torch.zeros((1, 1, 4), dtype=torch.float32, device=s.device)
+                self._positions_buf = pos[off:hi]
+                self._finish_update(batch_index, off, hi)
+            if self._host is not None:
+                self._mirror(off, hi, r0)
             batch_index += 1
+        if self._host is not None:
+            self._host["done"].record(self._host["stream"])
+
+    # ------------------------------------------------------------------ host mirrors
+    def set_host_outputs(self, forces=None, virial6=None):
+        """Pinned host tensors that receive this rank's force rows [rows,4] (and virial rows [rows,6]) after every
+        update, batch by batch on a copy stream: the device->host copy of batch b runs under the kernels of batch
+        b+1.  This is the reference's CPU-HOOMD mode, where TfToHoomd copies the force tensor into host arrays
+        (htf/tf2hoomd_op/tf2hoomd.cc:48-59), without its per-batch device synchronisation.  ``host_sync()`` waits."""
+        dev = self.system.device
+        for t in (forces, virial6):
+            if t is not None and not t.is_pinned():
+                raise ValueError("host outputs must be pinned tensors")
+        self._host = {"f": forces, "v": virial6, "stream": torch.cuda.Stream(device=dev),
+                      "done": torch.cuda.Event(), "ready": torch.cuda.Event()}
+        self._host["done"].record(torch.cuda.current_stream(dev))
+
+    def _mirror(self, off, hi, r0):
+        h = self._host
+        main = torch.cuda.current_stream(self.system.device)
+        h["ready"].record(main)
+        h["stream"].wait_event(h["ready"])
+        with torch.cuda.stream(h["stream"]):
+            if h["f"] is not None:
+                h["f"][off - r0:hi - r0].copy_(self._forces[off:hi], non_blocking=True)
+            if h["v"] is not None:
+                h["v"][off - r0:hi - r0].copy_(self.virial6((off, hi)), non_blocking=True)
+
+    def host_sync(self):
+        if self._host is not None:
+            self._host["stream"].synchronize()
 
     def _start_update(self):
         """precompute: apply the mapping function and write the bead positions back
@@ -240,11 +300,22 @@ class tfcompute:
         return self._forces.detach().cpu().numpy().astype(np.float64)
 
     def get_virial_array(self):
+        if self._virial6 is not None:
+            return self._virial6[:, [0, 1, 2, 1, 3, 4, 2, 4, 5]].detach().cpu().numpy().astype(np.float64)
         return self._virial.detach().cpu().numpy().astype(np.float64).reshape((-1, 9))
+
+    def virial6_rows(self):
+        """The [n,6] buffer fused models write their virial into (allocated on first use)."""
+        n = self._forces.shape[0]
+        if self._virial6 is None or self._virial6.shape[0] != n:
+            self._virial6 = torch.zeros((n, 6), dtype=torch.float32, device=self._forces.device)
+        return self._virial6
 
     def virial6(self, rows=None):
         """Device tensor [rows, 6] = xx, xy, xz, yy, yz, zz: the six components HOOMD keeps of the 3x3 virial
         (receiveVirial, htf/TensorflowCompute.cc:285-301)."""
+        if self._virial6 is not None:
+            return self._virial6 if rows is None else self._virial6[rows[0]:rows[1]]
         v = self._virial if rows is None else self._virial[rows[0]:rows[1]]
         return v[:, [0, 1, 2, 4, 5, 8]]
 

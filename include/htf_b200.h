@@ -266,10 +266,22 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
                 void *stream);
 
 /*
+ * The row-batch form of htf_lj_step: rows [row_lo,row_hi) of the particles binned by the last htf_bin_particles
+ * (n_all of them), no re-binning -- the reference's batch loop builds the neighbor list once and then walks
+ * row chunks (htf/TensorflowCompute.cc:143-150,162-163,188-194).
+ */
+int htf_lj_rows(htf_ctx *ctx, int64_t n_all, int64_t row_lo, int64_t row_hi,
+                float *d_nlist_out, float *d_force_energy, float *d_virial, int virial_components,
+                int32_t *d_overflow,
+                int64_t *d_bins, float r_lo, float r_hi, int nbins,
+                void *stream);
+
+/*
  * The same step for the EDS-biased model of BASELINE config 5: bin, build, then the fused LJ + smooth
  * coordination CV (+ RDF) pass of htf_lj_cv_forces (replaces, per step, the reference's
  * computeForces -> Python -> TF graph round trip for an EDSLayer model, htf/TensorflowCompute.cc:130-216,
  * htf/layers.py:101-195).  d_cv_sum and d_bins are accumulated into (zero them first).
+ * d_pos_all == NULL: no re-binning, the rows of the last htf_bin_particles (n_all particles).
  */
 int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row_lo, int64_t row_hi,
                    float *d_nlist_out, float r0, float *d_force_energy, float *d_virial, int virial_components,
@@ -282,8 +294,10 @@ int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t 
  * while slab i+1 is being built (the build is instruction-issue bound, the pair pass HBM bound: side by side they
  * overlap, and the pass finds most of the slab still in L2).  The caller's stream waits for the last pass, so the
  * step is stream-ordered as a whole and can be captured into a CUDA graph (call it once outside the capture first:
- * the auxiliary stream and events are created on first use).  slabs <= 1 switches pipelining off; the default is 8
- * (environment override HTF_PIPE_SLABS).  Systems below 131072 rows are never pipelined.
+ * the auxiliary stream and events are created on first use).  slabs <= 1 switches pipelining off, which is the
+ * default: measured on B200 the build needs the whole register file for its own occupancy, so a co-resident pass
+ * slows it by as much as it hides (cfg3: 0.63 vs 0.61 ms; cfg5: 3.60 vs 3.73 ms with 8 slabs) -- see DESIGN.md.
+ * Environment override HTF_PIPE_SLABS.  Systems below 131072 rows are never pipelined.
  * The reference runs every stage back to back and ends with cudaDeviceSynchronize (htf/TensorflowCompute.cc:208-211).
  */
 int htf_set_pipeline(htf_ctx *ctx, int slabs);

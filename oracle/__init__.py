@@ -52,6 +52,8 @@ def lib():
         L.htf_oracle_cv.restype = ctypes.c_int
         L.htf_oracle_cv.argtypes = [fp, i64, i32, f32, fp, fp]
         L.htf_oracle_num_threads.restype = ctypes.c_int
+        L.htf_oracle_set_threads.restype = ctypes.c_int
+        L.htf_oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -66,6 +68,12 @@ def _ptr(a, ct):
 
 def num_threads():
     return int(lib().htf_oracle_num_threads())
+
+
+def set_threads(n=0):
+    """OpenMP threads for the following calls (0 = every online processor); returns the count in effect.
+    bench.py calls this because torchrun exports OMP_NUM_THREADS=1."""
+    return int(lib().htf_oracle_set_threads(int(n)))
 
 
 def nlist(pos, box_lo, box_hi, r_cut, K, row_lo=0, row_hi=None, cells=None, map_type_start=-1,

@@ -331,3 +331,17 @@ int htf_oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* Number of OpenMP threads for the following calls (bench.py's CPU legs: torchrun exports
+ * OMP_NUM_THREADS=1, which would otherwise time one core).  n <= 0: all online processors. */
+int htf_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}

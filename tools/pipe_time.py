@@ -41,7 +41,12 @@ fe0, vir0, nl0 = fe.clone(), vir.clone(), nl.clone()
 assert ctx.overflow() == 0
 
 side = torch.cuda.Stream()
-for slabs in (0, 2, 4, 6, 8, 12, 16, 24, 32):
+combos = [(0, 2, 1)] + [(sl, bps, bs) for bs in (1, 2) for bps in (1, 2, 3) for sl in (2, 4, 8)]
+if len(sys.argv) > 2 and sys.argv[-1].startswith("combos="):
+    combos = [tuple(int(x) for x in c.split(",")) for c in sys.argv[-1][7:].split(";")]
+for slabs, bps, bstreams in combos:
+    os.environ["HTF_PIPE_PASS_BPS"] = str(bps); os.environ["HTF_PIPE_BUILD_STREAMS"] = str(bstreams)
+    ctx = htf.HtfContext(n, K, r_cut); ctx.set_box(lo, hi)
     ctx.set_pipeline(slabs)
     fe.zero_(); vir.zero_(); nl.zero_()
     torch.cuda.synchronize()
@@ -50,11 +55,10 @@ for slabs in (0, 2, 4, 6, 8, 12, 16, 24, 32):
             ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir)
     torch.cuda.synchronize()
     same = bool(torch.equal(fe, fe0) and torch.equal(vir, vir0) and torch.equal(nl, nl0))
-    t_eager = timeit(lambda: ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir))
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=side):
         ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir)
     t_graph = timeit(lambda: g.replay(), n=100)
-    print("slabs %2d: eager %.3f ms  graph %.3f ms  -> %.3e particle-steps/s, path %.0f GB/s   identical to serial: %s"
-          % (slabs, t_eager, t_graph, n / t_graph * 1e3, n * (32 * K + 56) / t_graph / 1e6, same))
-    del g
+    print("slabs %2d pass-blocks/SM %d build-streams %d: graph %.3f ms  -> %.3e particle-steps/s, path %.0f GB/s   identical: %s"
+          % (slabs, bps, bstreams, t_graph, n / t_graph * 1e3, n * (32 * K + 56) / t_graph / 1e6, same))
+    del g, ctx
