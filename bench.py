@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- particle-timesteps/s of the nlist -> forces+virial hot path (BASELINE.json metric).
 
-One "step" = one pass of the path over one synthetic LJ fluid: cell binning, padded neighbor
+One "step" = one pass of the path over one synthetic LJ fluid: [halo exchange,] cell binning, padded neighbor
 tensor [N,K,4], LJ forces + per-particle energy + 6-component virial.  Default workload:
 1,048,576 particles, K=64, r_cut=2.5, rho=0.7 (BASELINE.json configs[2] geometry with the LJ
 model, the size the north-star target is quoted on); the 1 GiB neighbor tensor is larger than
 L2, so no flush is needed between steps.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1|cfg5] [--rdf]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1|cfg5] [--model lj|mlp|eds] [--rdf]
   python bench.py --impl reference ...      # the CPU restatement (oracle/) on the host cores
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL): rows are sharded by particle index,
-positions are all-gathered every step (weak scaling: N x 1M particles), the RDF histogram is
-all-reduced when --rdf is on.  Rank 0 prints ONE JSON line.
+N > 1 is launched by torchrun (one rank per GPU, NCCL): rows are sharded by particle index (z-slabs), the two slab
+faces are exchanged every step, the RDF histogram is all-reduced when --rdf is on.  The headline record is weak
+scaling (N x the config's particles); the same line carries a strong-scaling record of the named size under
+"strong".  Every record carries a "parity" block: each rank checks a slice of its rows against the CPU oracle
+outside the timed region and the ranks all-reduce the size-independent sums.  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -58,8 +60,16 @@ def parse():
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
                     help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
+    ap.add_argument("--scaling", default="both", choices=["both", "weak", "strong"],
+                    help="N>1: the headline record is weak scaling (N x the config's particles); 'both' adds a strong-scaling "
+                         "record (the named size split over the N GPUs) under the key 'strong'")
+    ap.add_argument("--shuffle", action="store_true",
+                    help="single GPU: random particle order instead of the generator's spatially coherent lattice order")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle-checked parity leg (it is on by default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-batches", type=int, default=8,
+                    help="row batches per step in the end-to-end leg (device->host copy of batch b overlaps batch b+1)")
     return ap.parse_args()
 
 
@@ -82,12 +92,15 @@ def tensor_peak():
     return 1500.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def ncu_traffic(args, rows, K):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/) -- only when that capture
+    was taken on THIS configuration (same rows per launch and K), else None."""
     path = os.path.join(ROOT, "profiles", "nlist_build_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f)
+            t = json.load(f)
+        if int(t.get("rows", -1)) == int(rows) and int(t.get("K", -1)) == int(K) and args.model != "mlp":
+            return t
     return None
 
 
@@ -154,12 +167,18 @@ class ClockSampler:
         return out
 
 
-def workload(args, world):
+def workload(args, world, scaling="weak"):
+    """Synthetic system of the named config.  weak: one config-size slab per GPU (the box grows along z);
+    strong: the named size itself, split over the GPUs."""
     from htf import synthetic
     c = dict(synthetic.CONFIGS[args.workload])
     sites = list(c["sites"])
-    sites[2] *= world                      # weak scaling: the box grows along z, 1 config-size slab per GPU
+    if scaling == "weak":
+        sites[2] *= world
     pos, lo, hi = synthetic.lattice_fluid(tuple(sites), c["rho"], c["seed"])
+    if args.shuffle:
+        import numpy as np
+        pos = pos[np.random.default_rng(0).permutation(pos.shape[0])]
     return pos, lo, hi, c["r_cut"], c["K"]
 
 
@@ -172,14 +191,15 @@ def run_reference(args):
     import numpy as np
     import oracle
     oracle.build()
-    pos, lo, hi, r_cut, K = workload(args, 1)
+    threads = oracle.set_threads(0)        # torchrun exports OMP_NUM_THREADS=1: take every host core explicitly
+    world = max(1, args.gpus)
+    pos_g, lo, hi, r_cut, K = workload(args, world)          # the b200 arm's system at this N (weak scaling)
+    n_global = pos_g.shape[0]
+    rows = min(n_global, 32768 if args.model == "mlp" else 262144)   # bounded sample: a row slab of that system
+    g0 = (n_global // world - rows) // 2
+    pos, a0 = slab_with_halo(pos_g, g0, g0 + rows, r_cut)    # what one rank of a row-sharded CPU run would hold
     n = pos.shape[0]
-    rows = min(n, 262144)                  # bounded sample: a row slab of the same system
-    a0 = (n - rows) // 2
-
     if args.model == "mlp":
-        rows = min(n, 32768)               # the numpy MLP is ~50x slower per row than the LJ closed form
-        a0 = (n - rows) // 2
         raw = mlp_raw_parameters()
 
     def step():
@@ -191,26 +211,47 @@ def run_reference(args):
             oracle.rdf_hist(nl, (0.0, r_cut), 100)
         return fe
 
-    for _ in range(min(args.warmup, 1)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
-    sample = "%d-row slab of the %d-particle system per step (cell binning over all particles included)" % (rows, n)
+    sample = ("%d-row slab of the %d-particle system per step (cell binning of the slab and its r_cut halo, %d particles, "
+              "included)" % (rows, n_global, n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "steps": args.steps, "warmup": warm, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": cfg_dict(args, n, K, r_cut, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "config": cfg_dict(args, n_global, K, r_cut, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of TensorflowCompute::prepareNeighbors + closed-form LJModel (oracle/), "
                 "not HOOMD+TensorFlow: the reference stack cannot be built or imported here",
     }
     print(json.dumps(line))
     return 0
+
+
+def slab_with_halo(pos, a0, b0, r_cut, skin=0.4):
+    """Rows [a0, b0) of a z-sorted system plus every particle within r_cut + skin of them in z (periodic images are
+    not needed for an interior slab).  Returns (subset positions, index of row a0 inside the subset)."""
+    import numpy as np
+    z = pos[:, 2]
+    zlo, zhi = float(z[a0:b0].min()) - r_cut - skin, float(z[a0:b0].max()) + r_cut + skin
+    keep = np.nonzero((z >= zlo) & (z <= zhi))[0]
+    if keep.size == 0 or keep[0] > a0 or keep[-1] < b0 - 1 or args_shuffled(pos, keep, a0, b0):
+        return pos, a0                                            # not a contiguous slab (e.g. shuffled order): whole system
+    return np.ascontiguousarray(pos[keep]), int(np.searchsorted(keep, a0))
+
+
+def args_shuffled(pos, keep, a0, b0):
+    import numpy as np
+    i0 = int(np.searchsorted(keep, a0))
+    return not np.array_equal(keep[i0:i0 + (b0 - a0)], np.arange(a0, b0))
 
 
 def mlp_raw_parameters(seed=3):
@@ -238,10 +279,7 @@ def cfg_dict(args, n, K, r_cut, world):
 
 # --------------------------------------------------------------------------------------------
 def run_b200(args):
-    import numpy as np
     import torch
-    import htf
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,8 +292,32 @@ def run_b200(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    env = dict(world=world, rank=rank, local=local, dev=dev, dist=dist)
 
-    pos, lo, hi, r_cut, K = workload(args, world)
+    line = measure(args, env, "weak", full=True)           # the headline record: one config-size slab per GPU
+    if world > 1 and args.scaling in ("both", "strong") and args.skin <= 0.0:
+        st = measure(args, env, "strong", full=False)      # the named size itself, split over the GPUs
+        if rank == 0:
+            line["strong"] = {k: st[k] for k in ("value", "ms_per_step", "exchange_ms", "parity", "config") if k in st}
+            line["strong"]["efficiency_inputs"] = {
+                "particles": st["config"]["particles"], "n_gpus": world, "ms_per_step": st["ms_per_step"],
+                "note": "strong-scaling efficiency = value(N) / (N x value(1)) with value(1) from the --gpus 1 line"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure(args, env, scaling, full):
+    """One timed case.  Returns the JSON record (complete on rank 0)."""
+    import numpy as np
+    import torch
+    import htf
+    world, rank, local, dev, dist = env["world"], env["rank"], env["local"], env["dev"], env["dist"]
+
+    pos, lo, hi, r_cut, K = workload(args, world, scaling)
     n = pos.shape[0]
     per = n // world
     row_lo, row_hi = rank * per, (rank + 1) * per if rank < world - 1 else n
@@ -268,6 +330,7 @@ def run_b200(args):
         # bin only what can matter for this rank's rows (slab +- (r_cut + skin)), like HOOMD's ghost layer
         ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
     halo = world > 1 and args.exchange == "halo"
+    xch = None
     if halo:
         # rows are z-slabs (the generator's particle order is z-slowest): exchange only the two faces
         lo_face, hi_face, width, cap_h = htf.parallel.slab_plan(pos[row_lo:row_hi], 2, r_cut)
@@ -297,7 +360,7 @@ def run_b200(args):
     skin = args.skin > 0.0
     if skin:
         if world > 1:
-            raise SystemExit("--skin is single-GPU in this round (the halo layout changes every step)")
+            raise SystemExit("--skin is single-GPU (the halo layout changes every step)")
         ctx.skin_configure(args.skin)
         g = torch.Generator(device="cpu").manual_seed(7)
         v = torch.randn((n, 4), generator=g)
@@ -308,46 +371,32 @@ def run_b200(args):
         d_L = torch.tensor([hi[a] - lo[a] for a in range(3)] + [1.0], dtype=torch.float32, device=dev)
         skin_state = {"t": 0, "rebuilds": 0}
 
-    def skin_step(marks):
-        # the particles move (ballistic, |v| dt = --step-length); every --rebuild-every steps they are wrapped back
-        # into the box and the candidate lists (r_cut + skin) are rebuilt; the distance filter runs every step
-        d_pos_all.add_(d_vel)
-        if skin_state["t"] % args.rebuild_every == 0:
-            wrapped = torch.remainder(d_pos_all - d_lo, d_L) + d_lo
-            wrapped[:, 3] = d_pos_all[:, 3]
-            d_pos_all.copy_(wrapped)
-            ctx.skin_rebuild(d_pos_all)
-            skin_state["rebuilds"] += 1
-        skin_state["t"] += 1
-        if marks is not None:
-            marks[0].record()
-        ctx.skin_nlist(d_pos_all, out=nl)
-        if marks is not None:
-            marks[1].record()
-
-    def step(marks=None):
-        if skin:
-            skin_step(marks)
-            if packed is not None:
-                ctx.mlp_forces(nl, packed, r_cut, out=fe)
-            elif bins is not None:
-                bins.zero_()
-                ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
-            else:
-                ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
-            if marks is not None:
-                marks[2].record()
-            return
+    def phase_exchange():
         if halo:
             xch.exchange()                                            # the path's one exchange step (2 faces)
         elif world > 1:
             dist.all_gather_into_tensor(d_pos_all, d_shard)           # ... or every position
+
+    def phase_bin():
         ctx.bin_particles(d_pos_all)
-        if marks is not None:
-            marks[0].record()
-        ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
-        if marks is not None:
-            marks[1].record()
+
+    def phase_build():
+        if skin:
+            # the particles move (ballistic, |v| dt = --step-length); every --rebuild-every steps they are wrapped back
+            # into the box and the candidate lists (r_cut + skin) are rebuilt; the distance filter runs every step
+            d_pos_all.add_(d_vel)
+            if skin_state["t"] % args.rebuild_every == 0:
+                wrapped = torch.remainder(d_pos_all - d_lo, d_L) + d_lo
+                wrapped[:, 3] = d_pos_all[:, 3]
+                d_pos_all.copy_(wrapped)
+                ctx.skin_rebuild(d_pos_all)
+                skin_state["rebuilds"] += 1
+            skin_state["t"] += 1
+            ctx.skin_nlist(d_pos_all, out=nl)
+        else:
+            ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
+
+    def phase_force():
         if eds_model is not None:
             eds_model.compute(nl, None, None)                         # fused LJ + CV + RDF pass, all-reduces, EDS update, bias
         elif packed is not None:
@@ -359,18 +408,34 @@ def run_b200(args):
                 dist.all_reduce(bins)
         else:
             ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
+
+    def step(marks=None):
+        if marks is not None:
+            marks[0].record()
+        phase_exchange()
+        if marks is not None:
+            marks[1].record()
+        if not skin:
+            phase_bin()
         if marks is not None:
             marks[2].record()
+        phase_build()
+        if marks is not None:
+            marks[3].record()
+        phase_force()
+        if marks is not None:
+            marks[4].record()
 
     if eds_model is not None:
         step()                                                        # one pass to measure the initial CV
         eds_model.eds_bias.set_point.fill_(float(eds_model.cv_avg.result()) * 1.05)
         eds_model.cv_avg.reset()
 
-    # ---- single GPU: capture the step's three phases into CUDA graphs (same kernels, same stream order; the
-    #      events between the phases stay live).  Binning alone is six dependent launches of a few microseconds. ----
+    # ---- the step's phases captured into CUDA graphs (same kernels, same stream order; the events between the
+    #      phases stay live).  Binning alone is six dependent launches of a few microseconds.  NCCL stays eager. ----
     graphs = None
     launches_per_step = None
+    eager_force = eds_model is not None or (bins is not None and world > 1)     # host-side collectives / metric updates
     if not skin and not args.no_graph and (world == 1 or halo):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -379,32 +444,14 @@ def run_b200(args):
                 step()                                          # warm-up on the capture stream (allocations, func attributes)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-
-        def phase_bin():
-            ctx.bin_particles(d_pos_all)
-
-        def phase_build():
-            ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
-
-        def phase_force():
-            if eds_model is not None:
-                return                                          # host-side all-reduce and metric updates: runs eagerly
-            if packed is not None:
-                ctx.mlp_forces(nl, packed, r_cut, out=fe)
-            elif bins is not None:
-                bins.zero_()
-                ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
-            else:
-                ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
-
         graphs = []
         l0 = ctx.launches
         pack_graph = None
-        if halo:                                                # the device half of the exchange; NCCL send/recv stays eager
+        if halo:                                                # the device half of the exchange
             pack_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(pack_graph, stream=side):
                 xch.pack()
-        for fn in (phase_bin, phase_build, phase_force):
+        for fn in (phase_bin, phase_build) + (() if eager_force else (phase_force,)):
             g_ = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_, stream=side):
                 fn()
@@ -412,21 +459,25 @@ def run_b200(args):
         launches_per_step = ctx.launches - l0
 
         def step(marks=None):                                   # noqa: F811 -- the graph replay of the same step
+            if marks is not None:
+                marks[0].record()
             if pack_graph is not None:
                 pack_graph.replay()
                 xch.swap()
-            graphs[0].replay()
-            if marks is not None:
-                marks[0].record()
-            graphs[1].replay()
             if marks is not None:
                 marks[1].record()
-            if eds_model is not None:
-                eds_model.compute(nl, None, None)
+            graphs[0].replay()
+            if marks is not None:
+                marks[2].record()
+            graphs[1].replay()
+            if marks is not None:
+                marks[3].record()
+            if eager_force:
+                phase_force()
             else:
                 graphs[2].replay()
             if marks is not None:
-                marks[2].record()
+                marks[4].record()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -434,14 +485,15 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local) if (rank == 0 and full) else None
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     sync_all()
     assert ctx.overflow() == 0, "neighbor list overflowed K: the run is void"
 
     # ---- timed region: exactly --steps steps, device timed, clocks sampled meanwhile ----
-    marks = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
     skin_t0 = skin_state["t"] if skin else 0
     line0 = sampler.lines() if sampler else 0
     launches0 = ctx.launches
@@ -462,39 +514,56 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    build_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
-    force_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
+    phase = lambda a, b: float(np.mean([m[a].elapsed_time(m[b]) for m in marks]))
+    exchange_ms, bin_ms, build_ms, force_ms = phase(0, 1), phase(1, 2), phase(2, 3), phase(3, 4)
     value = n * args.steps / (ms * 1e-3)
+
+    # ---- parity leg (outside the timed region; the oracle is the checker, never the thing measured) ----
+    parity = None
+    if not args.no_parity and not skin:
+        parity = parity_leg(args, env, htf, ctx, pos, lo, hi, r_cut, K, g_lo, rows, row_lo, row_hi, d_pos_all, nl, fe, vir,
+                            phase_exchange, packed)
 
     # ---- end to end through the public API with host buffers (tfcompute + built-in LJ virial model) ----
     e2e = None
-    if not args.no_e2e:
+    if full and not args.no_e2e:
         e2e = run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, g_lo, g_hi)
 
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         alg_build = rows * (16 * K + 16)
         achieved = alg_build / (build_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
+        traffic = ncu_traffic(args, rows, K) if (full and not skin) else None
+        step_ms = ms / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg_dict(args, n, K, r_cut, world),
             "roofline": {"bound": "hbm", "kernel": "nlist_tile_kernel (+ per-cell fallback pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_build, "kernel_ms": build_ms,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                         "traffic_source": traffic["source"] if traffic else None,
-                         "path_frac": (rows * (32 * K + 56)) / (ms / args.steps * 1e-3) / 1e9 / peak,
-                         "force_kernel_ms": force_ms,
+                         "traffic_source": traffic["source"] if traffic else
+                         "no committed ncu capture for this configuration (profiles/nlist_build_traffic.json is keyed by rows and K)",
+                         "path_frac": (rows * (32 * K + 56)) / (step_ms * 1e-3) / 1e9 / peak,
+                         "path_bytes_per_row": {"nlist written and re-read (32K+56)": 32 * K + 56,
+                                                "nlist written once (16K+56)": 16 * K + 56},
+                         "path_frac_single_write": (rows * (16 * K + 56)) / (step_ms * 1e-3) / 1e9 / peak,
+                         "binning_ms": bin_ms, "force_kernel_ms": force_ms,
                          "force_kernel_frac": rows * (16 * K + 40) / (force_ms * 1e-3) / 1e9 / peak},
+            "exchange_ms": exchange_ms if world > 1 else 0.0,
             "clocks": clocks, "gpu_launches": launches,
+            "launch": ("%d CUDA graphs per step (%sbinning | build%s), %d kernels"
+                       % (len(graphs) + (1 if halo else 0), "halo packing | " if halo else "",
+                          "" if eager_force else " | forces", launches_per_step)
+                       if graphs is not None else "stream launches from the host"),
+            "parity": parity,
             "e2e": e2e,
         }
-        line["config"]["launch"] = ("%d CUDA graphs per step (%sbinning | build | forces), %d kernels"
-                                    % (4 if halo else 3, "halo packing | " if halo else "", launches_per_step)
-                                    if graphs is not None else "stream launches from the host")
+        if args.shuffle:
+            line["config"]["particle_order"] = "shuffled (random permutation of the lattice order)"
         if skin:
             cfg = line["config"]
             cfg["workload"] += "+skin"
@@ -505,29 +574,117 @@ def run_b200(args):
                                    "distance filter every step; particles move ballistically every step"}
             line["roofline"]["kernel"] = "nlist_filter_kernel (per-step pass; the search is amortised inside build_ms)"
         if args.model == "mlp":
-            # the dominant kernel of this workload is the tensor-core MLP: report it against the measured bf16 peak
+            # the dominant kernel of this workload is the tensor-core MLP: report it against the measured bf16 peak,
+            # counting only the VALID (non-padded) pairs as useful work
             tpeak, tsrc = tensor_peak()
-            flop = rows * K * MLP_FLOP_PER_PAIR
+            valid_pairs = int((nl[:, :, :3].abs().sum(-1) > 0).sum().item())
+            flop = valid_pairs * MLP_FLOP_PER_PAIR
             tf = flop / (force_ms * 1e-3) / 1e12
             line["dtype"] = "bf16"
             line["roofline"] = {"bound": "tensor", "kernel": "mlp_force_kernel (tcgen05, operands in TMEM)", "achieved": tf,
                                 "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
                                 "algorithmic_flop_per_launch": flop, "kernel_ms": force_ms, "traffic": None,
-                                "note": "41,216 useful flop per pair (value + tangent through 32-64-64-64-1); the kernel's own "
+                                "valid_pairs": valid_pairs, "slots": rows * K,
+                                "frac_counting_padded_slots": rows * K * MLP_FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12 / tpeak,
+                                "note": "41,216 useful flop per VALID pair (value + tangent through 32-64-64-64-1); the kernel's own "
                                         "bound is the MUFU pipe (200 MUFU per pair at 16 lanes/clk/SM), see DESIGN.md",
                                 "nlist_build_ms": build_ms, "nlist_build_frac": achieved / peak}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and full and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pos, lo, hi, r_cut, K)
-        print(json.dumps(line))
+    del ctx, nl, fe, vir, d_pos_all, d_shard, xch, graphs
+    torch.cuda.empty_cache()
+    return line
+
+
+def _sorted_rows(a):
+    """Rows of a [rows, K, 4] float32 tensor (numpy), each sorted by the bit patterns of (dx, dy, dz, type): slot order
+    is unspecified, the multiset of entries is what must match bit for bit."""
+    import numpy as np
+    u = np.ascontiguousarray(a).view(np.uint32).astype(np.uint64)
+    key1 = (u[..., 0] << np.uint64(32)) | u[..., 1]
+    key2 = (u[..., 2] << np.uint64(32)) | u[..., 3]
+    order = np.lexsort((key2, key1), axis=1)
+    return np.take_along_axis(a, order[:, :, None], axis=1)
+
+
+def parity_leg(args, env, htf, ctx, pos, lo, hi, r_cut, K, g_lo, rows, row_lo, row_hi, d_pos_all, nl, fe, vir,
+               phase_exchange, packed):
+    """Every rank checks a slice of its rows against the CPU oracle (neighbor tensor bit-exact as a multiset, RDF bins of
+    the slice bit-exact, forces / virial 1e-5) and the ranks all-reduce the size-independent sums.  Mirrors the intent
+    of the reference's MPI test (/root/reference htf/test-py/test_mpi_tensorflow.py:59-80): a domain-decomposed run
+    must reproduce the single-domain numbers."""
+    import numpy as np
+    import torch
+    import oracle
+    world, rank, dev, dist = env["world"], env["rank"], env["dev"], env["dist"]
+    oracle.build()
+    oracle.set_threads(max(1, (os.cpu_count() or 1) // world))
+    m = min(rows, 2048)
+    a0 = (rows - m) // 2                                     # slice in the middle of this rank's rows (local numbering)
+    # one untimed LJ step with the RDF histogram through the one-call entry point, on freshly exchanged positions
+    phase_exchange()
+    bins = torch.zeros(102, dtype=torch.int64, device=dev)
+    vir_c = torch.empty((rows, 6), dtype=torch.float32, device=dev)
+    fe_c = ctx.lj_step(d_pos_all, row_lo, row_hi, nlist_out=nl, virial_out=vir_c, bins=bins, r_range=(0.0, r_cut), nbins=100)
+    bins_slice = ctx.rdf_hist(nl[a0:a0 + m], (0.0, r_cut), 100)
+    torch.cuda.synchronize()
+    sub, s0 = slab_with_halo(pos, g_lo + a0, g_lo + a0 + m, r_cut) if world * rows == pos.shape[0] and not args.shuffle \
+        else (pos, g_lo + a0)
+    nl_o, _, cnt_o = oracle.nlist(sub, lo, hi, r_cut, K, s0, s0 + m, cells=True, want_idx=False)
+    fe_o, _, v6_o = oracle.lj(nl_o)
+    h_o = oracle.rdf_hist(nl_o, (0.0, r_cut), 100)
+    nl_g = nl[a0:a0 + m].cpu().numpy()
+    nlist_ok = bool(np.array_equal(_sorted_rows(nl_g).view(np.uint32), _sorted_rows(nl_o).view(np.uint32)))
+    rdf_ok = bool(np.array_equal(bins_slice.cpu().numpy(), h_o))
+
+    def rel(got, want):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        scale = np.sqrt(np.mean(want ** 2)) + 1e-30
+        return float((np.abs(got - want) / np.maximum(np.abs(want), scale)).max())
+
+    f_err = rel(fe_c[a0:a0 + m].cpu().numpy(), fe_o)
+    v_err = rel(vir_c[a0:a0 + m].cpu().numpy(), v6_o)
+    mlp_err = None
+    if packed is not None:
+        mm = min(m, 256)
+        f_mlp = ctx.mlp_forces(nl[a0:a0 + mm].contiguous(), packed, r_cut).cpu().numpy().astype(np.float64)
+        f_ref = oracle.pairwise_mlp(nl_o[:mm], mlp_raw_parameters(), r_cut).astype(np.float64)
+        mlp_err = float(np.abs(f_mlp[:, :3] - f_ref[:, :3]).max() / (np.sqrt(np.mean(f_ref[:, :3] ** 2)) + 1e-30))
+    # size-independent sums over ALL rows of all ranks
+    sums = torch.cat([fe_c[:, :3].double().sum(0), fe_c[:, :3].double().abs().sum().reshape(1),
+                      fe_c[:, 3].double().sum().reshape(1), vir_c.double().sum(0)])
+    flags = torch.tensor([int(nlist_ok), int(rdf_ok)], dtype=torch.int64, device=dev)
+    errs = torch.tensor([f_err, v_err], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        dist.all_reduce(sums)
+        dist.all_reduce(bins)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    sums = sums.cpu().numpy()
+    n_global = pos.shape[0]
+    out = {
+        "checker": "oracle/ (CPU restatement), %d rows per rank from the middle of its shard" % m,
+        "nlist_multiset_bit_exact": bool(flags[0].item()), "rdf_slice_bit_exact": bool(flags[1].item()),
+        "force_energy_max_rel_err": float(errs[0].item()), "virial_max_rel_err": float(errs[1].item()), "tolerance": 1e-5,
+        "rdf_total": int(bins.sum().item()), "rdf_total_expected": int(n_global) * K,
+        "sum_force_over_sum_abs_force": float(np.abs(sums[:3]).max() / max(sums[3], 1e-30)),
+        "sum_energy": float(sums[4]), "sum_virial6": [float(x) for x in sums[5:11]],
+        "rdf_bins_sha": __import__("hashlib").sha1(bins.cpu().numpy().tobytes()).hexdigest()[:16],
+    }
+    if mlp_err is not None:
+        out["mlp_force_max_err_over_rms"] = mlp_err
+        out["mlp_tolerance"] = 1e-1
+    out["ok"] = bool(out["nlist_multiset_bit_exact"] and out["rdf_slice_bit_exact"] and out["force_energy_max_rel_err"] <= 1e-5
+                     and out["virial_max_rel_err"] <= 1e-5 and out["rdf_total"] == out["rdf_total_expected"]
+                     and out["sum_force_over_sum_abs_force"] <= 1e-5 and (mlp_err is None or mlp_err < 1e-1))
+    return out
 
 
 def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi):
-    """Same metric through tfcompute (the user-facing call) with HOST buffers: every step copies the
-    rank's positions from pinned host memory and reads forces+virial back into pinned host memory."""
+    """Same metric through tfcompute (the user-facing call) with HOST buffers: every step copies the rank's positions
+    from pinned host memory and reads forces+virial back into pinned host memory.  The step runs in row batches
+    (tfcompute's batch_size, the reference's own chunking): the device->host copy of batch b leaves on a copy stream
+    while batch b+1 is built and evaluated, so only the first build and the last copy are exposed."""
     import numpy as np
     n = pos.shape[0]
     rows = row_hi - row_lo
@@ -540,9 +697,11 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     else:
         model = htf.models.LJVirialModel(K, virial=True)
     tfc = htf.tfcompute(model)
+    nbatch = args.e2e_batches if args.model == "lj" else 1
+    batch = None if nbatch <= 1 else (rows + nbatch - 1) // nbatch
     h_pos = torch.from_numpy(pos[row_lo:row_hi].copy()).pin_memory()
     h_f = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
-    h_v = torch.empty((rows, 6), dtype=torch.float32).pin_memory()
+    h_v = torch.empty((rows, 6), dtype=torch.float32).pin_memory() if args.model == "lj" else None
     if halo:
         # like the device-resident leg: the rank's system is [own rows | halo from below | halo from above]
         lo_face, hi_face, width, cap_h = htf.parallel.slab_plan(pos[row_lo:row_hi], 2, r_cut)
@@ -551,17 +710,18 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
         cap_h = int(t_.item())
         local0 = np.concatenate([pos[row_lo:row_hi], np.full((2 * cap_h, 4), 1e30, dtype=np.float32)])
         system = htf.sim.System(local0, lo, hi, device=dev)
-        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
+        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=batch)
         xch = htf.parallel.SlabExchange(tfc.ctx, rows, 2, lo_face, hi_face, width, cap_h)
         system.positions = xch.local
         d_shard = xch.own
         out_lo, out_hi = 0, rows
     else:
         system = htf.sim.System(pos, lo, hi, device=dev)
-        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=None)
-        d_shard = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=batch)
+        d_shard = system.positions[row_lo:row_hi] if world == 1 else torch.empty((rows, 4), dtype=torch.float32, device=dev)
         out_lo, out_hi = row_lo, row_hi
     tfc.shard = (out_lo, out_hi)
+    tfc.set_host_outputs(h_f, h_v)
     if world > 1:
         tfc.ctx.set_roi(*htf.parallel.roi_for_rows(pos[row_lo:row_hi], lo, hi, r_cut))
 
@@ -571,16 +731,12 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
             xch.exchange()
         elif world > 1:
             dist.all_gather_into_tensor(system.positions, d_shard)
-        else:
-            system.positions.copy_(d_shard)
-        f = tfc.compute_forces(t)
-        h_f.copy_(f[out_lo:out_hi], non_blocking=True)
-        if args.model == "lj":
-            h_v.copy_(tfc.virial6((out_lo, out_hi)), non_blocking=True)   # the 6 components HOOMD keeps
+        tfc.compute_forces(t)                       # forces (+virial) of every batch are mirrored into h_f / h_v
 
     steps = max(3, min(args.steps, 10))
     for t in range(3):
         step(t)
+    tfc.host_sync()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -589,6 +745,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     e0.record()
     for t in range(steps):
         step(t)
+    torch.cuda.current_stream().wait_event(tfc._host["done"])      # the last device->host copies belong to the step
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -596,9 +753,13 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    # the mirrored host result is the device result
+    ok = bool(torch.equal(h_f, tfc._forces[out_lo:out_hi].cpu()))
     return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4),
-            "d2h_bytes_per_step": int(h_f.numel() * 4 + (h_v.numel() * 4 if args.model == "lj" else 0)), "steps": steps,
-            "api": "htf.tfcompute(%s).compute_forces with pinned host positions in, forces%s out"
+            "d2h_bytes_per_step": int(h_f.numel() * 4 + (h_v.numel() * 4 if h_v is not None else 0)), "steps": steps,
+            "ms_per_step": ms / steps, "row_batches": max(nbatch, 1), "host_result_matches_device": ok,
+            "api": "htf.tfcompute(%s).compute_forces, pinned host positions in, forces%s mirrored to pinned host memory "
+                   "batch by batch (set_host_outputs)"
                    % (("PairwiseMLPModel", "+energy") if args.model == "mlp" else
                       ("EDSCoordinationModel", "+energy") if args.model == "eds" else ("LJVirialModel", "+virial"))}
 
@@ -607,6 +768,7 @@ def cpu_baseline(args, pos, lo, hi, r_cut, K):
     """The CPU restatement (oracle/) timed on this box's host cores on a bounded sample of the workload."""
     import oracle
     oracle.build()
+    oracle.set_threads(0)
     n = pos.shape[0]
     rows = min(n, 32768 if args.model == "mlp" else 262144)
     a0 = (n - rows) // 2
