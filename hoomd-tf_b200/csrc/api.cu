@@ -482,6 +482,17 @@ int htf_integrate_half(htf_ctx *ctx, int half, float *d_pos, float *d_vel, const
     return HTF_OK;
 }
 
+int htf_unstuff4(htf_ctx *ctx, const float *d_pos_hoomd, float *d_pos_out, int64_t n, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n < 0 || n > 2000000000LL || (n > 0 && (!d_pos_hoomd || !d_pos_out))) { set_err(ctx, "htf_unstuff4: bad arguments"); return HTF_EINVAL; }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_unstuff4(ctx, reinterpret_cast<const float4 *>(d_pos_hoomd), reinterpret_cast<float4 *>(d_pos_out), n,
+                                      (cudaStream_t)stream));
+    return HTF_OK;
+}
+
 int htf_skin_configure(htf_ctx *ctx, float skin, int k_candidates)
 {
     int rc = check_ctx(ctx);

@@ -127,6 +127,7 @@ cudaError_t htf_launch_eds_step(htf_ctx *ctx, const float *cv, const float *set_
 cudaError_t htf_launch_integrate(htf_ctx *ctx, int half, float4 *pos, float *vel, const float4 *force, int64_t n, float dt,
                                  float gamma, float kT, int flat, unsigned long long seed, unsigned long long step,
                                  cudaStream_t st);
+cudaError_t htf_launch_unstuff4(htf_ctx *ctx, const float4 *in, float4 *out, int64_t n, cudaStream_t st);
 cudaError_t htf_launch_skin_filter(htf_ctx *ctx, const float4 *pos, int64_t row_lo, int64_t row_hi, float4 *out,
                                    int32_t *idx_out, int32_t *count_out, int32_t *overflow, cudaStream_t st);
 cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr_lo, float thr_hi,

@@ -81,7 +81,27 @@ __global__ void __launch_bounds__(256) integrate_second_kernel(const IntegratePa
     p.vel[3 * i] = vx; p.vel[3 * i + 1] = vy; p.vel[3 * i + 2] = vz;
 }
 
+// HOOMD keeps the particle type as the BIT PATTERN of an int in the w component of its Scalar4 positions; the path
+// works with the type as a float VALUE.  Same conversion as the reference's htf_gpu_unstuff4 kernel
+// (/root/reference htf/TFArrayComm.cu:9-28), as one coalesced float4 pass (in place when in == out).
+__global__ void __launch_bounds__(256) unstuff4_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = in[i];
+    v.w = (float)__float_as_int(v.w);
+    out[i] = v;
+}
+
 }  // namespace
+
+cudaError_t htf_launch_unstuff4(htf_ctx *ctx, const float4 *in, float4 *out, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    unstuff4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, (int)n);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
 
 cudaError_t htf_launch_integrate(htf_ctx *ctx, int half, float4 *pos, float *vel, const float4 *force, int64_t n, float dt,
                                  float gamma, float kT, int flat, unsigned long long seed, unsigned long long step,

@@ -304,6 +304,14 @@ class HtfContext:
                                       float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
 
+    def unstuff4(self, pos_hoomd, out=None):
+        """HOOMD Scalar4 positions (type as int bits in .w) -> positions with the type as a float value."""
+        _check_dev_f32(pos_hoomd, "positions", 4)
+        if out is None:
+            out = torch.empty_like(pos_hoomd)
+        self._ck(self.lib.htf_unstuff4(self._h, _ptr(pos_hoomd), _ptr(out), pos_hoomd.shape[0], self._stream()))
+        return out
+
     def lj_rows(self, n_all, row_lo, row_hi, nlist_out=None, force_out=None, virial_out=None, virial_components=6,
                 bins=None, r_range=(0.0, 1.0), nbins=100):
         """Row batch of the LJ step on the particles of the last ``bin_particles`` (no re-binning)."""

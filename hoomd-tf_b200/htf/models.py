@@ -205,6 +205,18 @@ class TrainModel(SimModel):
         return forces, energy.sum()
 
 
+class WCA(SimModel):
+    """build_examples.py:221-228: trainable WCA repulsion layer -> nlist forces."""
+
+    def setup(self):
+        from .layers import WCARepulsion
+        self.wca = WCARepulsion(0.5)
+
+    def compute(self, nlist):
+        energy = self.wca(nlist)
+        return compute_nlist_forces(nlist, energy)
+
+
 class RBF(SimModel):
     """build_examples.py:231-241: per-pair radial basis features -> Dense(1)."""
 

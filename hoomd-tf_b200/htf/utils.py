@@ -9,6 +9,22 @@ import torch
 from .context import HtfContext
 
 
+_NLIST_CTX = {}
+
+
+def _nlist_context(dev, n, K, r_cut):
+    """One persistent context per device for the trajectory helpers (the reference rebuilds nothing per frame
+    either: its compute_nlist is a traced TF function, htf/utils.py:75-161).  Cutoff, K and box are re-set per call."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ctx = _NLIST_CTX.get(idx)
+    if ctx is None:
+        ctx = HtfContext(max(n, 1), K, float(r_cut), device=torch.device("cuda", idx))
+        _NLIST_CTX[idx] = ctx
+    else:
+        ctx.set_cutoff(float(r_cut), K)
+    return ctx
+
+
 def _wrap_into_box(xyz, lo, L):
     return xyz - torch.floor((xyz - lo) / L) * L
 
@@ -41,11 +57,11 @@ def compute_nlist(positions, r_cut, NN, box_size, sorted=False, return_types=Fal
     hi = L.cpu().numpy()
     K = int(NN)
     while True:
-        ctx = HtfContext(max(n, 1), K, float(r_cut), device=dev)
+        ctx = _nlist_context(dev, n, K, r_cut)
         ctx.set_box([0.0, 0.0, 0.0], hi)
         nl, idx, cnt = ctx.build_nlist(pos4, want_idx=True, want_count=True)
         cmax = int(cnt.max().item()) if n > 0 else 0
-        ctx.close()
+        ctx.overflow()                # reset the sticky "a row is full" flag of the shared context
         if cmax <= K:
             break
         K = cmax                      # more candidates than NN: rebuild wide, then pick NN of them below

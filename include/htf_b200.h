@@ -266,6 +266,14 @@ int htf_lj_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t row
                 void *stream);
 
 /*
+ * HOOMD's Scalar4 positions carry the particle type as the bit pattern of an int in .w; this library takes the
+ * type as a float value.  Replaces TFArrayComm::receiveArray(..., unstuff4) and its kernel
+ * (htf/TFArrayComm.h:86-130, htf/TFArrayComm.cu:9-28): one pass over n positions, in place when
+ * d_pos_hoomd == d_pos_out.  A HOOMD-side binding calls this once per step on its position array.
+ */
+int htf_unstuff4(htf_ctx *ctx, const float *d_pos_hoomd, float *d_pos_out, int64_t n, void *stream);
+
+/*
  * The row-batch form of htf_lj_step: rows [row_lo,row_hi) of the particles binned by the last htf_bin_particles
  * (n_all of them), no re-binning -- the reference's batch loop builds the neighbor list once and then walks
  * row chunks (htf/TensorflowCompute.cc:143-150,162-163,188-194).

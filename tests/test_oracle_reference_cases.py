@@ -245,3 +245,28 @@ def test_coordination_cv_against_float64_and_finite_differences(oracle_mod):
         dn[..., ax] -= h * mask
         fd = (cn64(up) - cn64(dn)) / (2 * h)
         assert np.abs(g[:, ax] - fd).max() <= 2e-4 * max(1.0, np.abs(fd).max()), ax
+
+
+def test_reference_fixture_comparator_and_any_committed_reference_fixtures():
+    """oracle/make_ref_fixtures.py runs the unmodified reference (hoomd + tensorflow) on the golden systems wherever
+    that stack exists and compares with the oracle-made fixtures.  Here: its comparator accepts the oracle's own
+    output, rejects a one-count change of the RDF histogram, and any committed tests/golden/*_ref.npz must pass."""
+    import glob
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_ref_fixtures", os.path.join(root, "oracle", "make_ref_fixtures.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    g = dict(np.load(os.path.join(root, "tests", "golden", "fluid216_rc25.npz")))
+    r = {"nlist_sorted": m.sort_rows_by_value(g["nlist_sorted"]), "count": g["count"], "force_energy": g["force_energy"],
+         "virial6": g["virial6"], "rdf_hist": g["rdf_hist"], "hoomd_double": np.bool_(False),
+         "hoomd_version": np.str_("-"), "tf_version": np.str_("-")}
+    assert m.compare("oracle vs itself", g, r)
+    bad = dict(r)
+    bad["rdf_hist"] = r["rdf_hist"].copy()
+    bad["rdf_hist"][5] += 1
+    assert not m.compare("one count off", g, bad)
+    for f in sorted(glob.glob(os.path.join(root, "tests", "golden", "*_ref.npz"))):
+        name = os.path.basename(f)[:-8]
+        assert m.compare(name, dict(np.load(os.path.join(root, "tests", "golden", name + ".npz"))), dict(np.load(f)))
