@@ -66,6 +66,10 @@ def parse():
     ap.add_argument("--shuffle", action="store_true",
                     help="single GPU: random particle order instead of the generator's spatially coherent lattice order")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-checked parity leg (it is on by default)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="halo exchange transport: p2p = the library's peer-memory windows (fused pack + send over NVLink, "
+                         "flags, no NCCL on the data path), nccl = pack kernels + NCCL send/recv, auto = p2p when the "
+                         "peers can be mapped")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=8,
@@ -298,7 +302,7 @@ def run_b200(args):
     if world > 1 and args.scaling in ("both", "strong") and args.skin <= 0.0:
         st = measure(args, env, "strong", full=False)      # the named size itself, split over the GPUs
         if rank == 0:
-            line["strong"] = {k: st[k] for k in ("value", "ms_per_step", "exchange_ms", "parity", "config") if k in st}
+            line["strong"] = {k: st[k] for k in ("value", "ms_per_step", "exchange_ms", "exchange", "parity", "config") if k in st}
             line["strong"]["efficiency_inputs"] = {
                 "particles": st["config"]["particles"], "n_gpus": world, "ms_per_step": st["ms_per_step"],
                 "note": "strong-scaling efficiency = value(N) / (N x value(1)) with value(1) from the --gpus 1 line"}
@@ -336,13 +340,14 @@ def measure(args, env, scaling, full):
         lo_face, hi_face, width, cap_h = htf.parallel.slab_plan(pos[row_lo:row_hi], 2, r_cut)
         t = torch.tensor([cap_h], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        xch = htf.parallel.SlabExchange(ctx, rows, 2, lo_face, hi_face, width, int(t.item()))
+        xch = htf.parallel.SlabExchange(ctx, rows, 2, lo_face, hi_face, width, int(t.item()), transport=args.transport)
         xch.own.copy_(torch.from_numpy(pos[row_lo:row_hi]).to(dev))
         d_pos_all, d_shard = xch.local, xch.own
         row_lo, row_hi = 0, rows                     # local indexing: own rows come first
     else:
         d_pos_all = torch.from_numpy(pos).to(dev)
         d_shard = d_pos_all[row_lo:row_hi].clone()
+    p2p = xch is not None and xch.transport == "p2p"
     nl = torch.empty((rows, K, 4), dtype=torch.float32, device=dev)
     fe = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     vir = torch.empty((rows, 6), dtype=torch.float32, device=dev)
@@ -405,7 +410,10 @@ def measure(args, env, scaling, full):
             bins.zero_()
             ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
             if world > 1:
-                dist.all_reduce(bins)
+                if p2p:
+                    ctx.comm_allreduce(bins)                          # mailboxes in peer memory, graph-capturable
+                else:
+                    dist.all_reduce(bins)
         else:
             ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
 
@@ -435,7 +443,7 @@ def measure(args, env, scaling, full):
     #      phases stay live).  Binning alone is six dependent launches of a few microseconds.  NCCL stays eager. ----
     graphs = None
     launches_per_step = None
-    eager_force = eds_model is not None or (bins is not None and world > 1)     # host-side collectives / metric updates
+    eager_force = eds_model is not None or (bins is not None and world > 1 and not p2p)   # host-side collectives / metric updates
     if not skin and not args.no_graph and (world == 1 or halo):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -541,6 +549,9 @@ def measure(args, env, scaling, full):
             "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg_dict(args, n, K, r_cut, world),
+            "exchange": ({"transport": xch.transport, "note": xch.transport_note or None,
+                          "what": "fused pack + send into the neighbours' peer-memory windows, flags, gather (htf_comm_exchange_halo)"
+                                  if p2p else "pack kernels + NCCL send/recv"} if xch is not None else None),
             "roofline": {"bound": "hbm", "kernel": "nlist_tile_kernel (+ per-cell fallback pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_build, "kernel_ms": build_ms,
@@ -711,7 +722,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
         local0 = np.concatenate([pos[row_lo:row_hi], np.full((2 * cap_h, 4), 1e30, dtype=np.float32)])
         system = htf.sim.System(local0, lo, hi, device=dev)
         tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, batch_size=batch)
-        xch = htf.parallel.SlabExchange(tfc.ctx, rows, 2, lo_face, hi_face, width, cap_h)
+        xch = htf.parallel.SlabExchange(tfc.ctx, rows, 2, lo_face, hi_face, width, cap_h, transport=args.transport)
         system.positions = xch.local
         d_shard = xch.own
         out_lo, out_hi = 0, rows

@@ -358,6 +358,7 @@ void htf_destroy(htf_ctx *ctx)
         if (e != cudaSuccess && getenv("HTF_DEBUG"))
             fprintf(stderr, "htf_destroy: cudaFree #%zu %p: %s\n", i, ptrs[i], cudaGetErrorString(e));
     }
+    htf_comm_free(ctx);
     for (int i = 0; i < ctx->pipe_events_n; i++) cudaEventDestroy(ctx->pipe_events[i]);
     free(ctx->pipe_events);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -275,11 +275,19 @@ __global__ void __launch_bounds__(256) select_scatter2_kernel(const float4 *__re
                                                               float thr_hi, int nb, const int *__restrict__ block_off,
                                                               const int *__restrict__ total, float4 *__restrict__ out_lo,
                                                               float4 *__restrict__ out_hi, int cap, int *__restrict__ counts,
-                                                              int *__restrict__ overflow)
+                                                              int *__restrict__ overflow, const HtfHaloDst *dst)
 {
     __shared__ int wsum[16];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (dst) {
+        // fused pack + send: the two faces go straight into the neighbours' receive buffers (peer memory over
+        // NVLink), double buffered by the parity of the exchange epoch, which lives in device memory so that a
+        // captured graph advances it by itself
+        const int par = (int)(*reinterpret_cast<const volatile unsigned long long *>(&dst->epoch) & 1ull);
+        out_lo = dst->lo[par];
+        out_hi = dst->hi[par];
+    }
     const int tot_lo = block_off[nb], tot_hi = *total - tot_lo;
     if (i == 0 && counts) { counts[0] = tot_lo; counts[1] = tot_hi; }
     if (i < cap) {
@@ -373,7 +381,8 @@ cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n64, int 
 
 
 cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64, int axis, float thr_lo, float thr_hi,
-                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st)
+                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st,
+                                   const HtfHaloDst *dst)
 {
     const int n = (int)n64;
     const int nb = (n + 255) / 256;
@@ -389,7 +398,7 @@ cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64,
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums, off);
     const int gb = max(nb, (cap + 255) / 256);
     select_scatter2_kernel<<<gb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, off, total, out_lo, out_hi, cap, d_counts,
-                                               d_overflow);
+                                               d_overflow, dst);
     ctx->launches += 5;
     return cudaGetLastError();
 }

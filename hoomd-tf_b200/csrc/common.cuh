@@ -24,6 +24,8 @@ struct CellGrid {
     int z0, zcount;
 };
 
+struct HtfComm;
+
 struct htf_ctx {
     int device;
     int sm_count;
@@ -78,6 +80,7 @@ struct htf_ctx {
     int pipe_slabs;               // slabs per step (<= 1: no pipelining)
     int pipe_pass_bps;            // blocks per SM of a slab's pair pass
     int pipe_build_streams;       // 1 or 2
+    HtfComm *comm;                // peer-memory exchange state (comm.cu), nullptr until htf_comm_create
     int64_t launches;
     char err[512];
 };
@@ -130,8 +133,15 @@ cudaError_t htf_launch_integrate(htf_ctx *ctx, int half, float4 *pos, float *vel
 cudaError_t htf_launch_unstuff4(htf_ctx *ctx, const float4 *in, float4 *out, int64_t n, cudaStream_t st);
 cudaError_t htf_launch_skin_filter(htf_ctx *ctx, const float4 *pos, int64_t row_lo, int64_t row_hi, float4 *out,
                                    int32_t *idx_out, int32_t *count_out, int32_t *overflow, cudaStream_t st);
+// destination table of the fused pack + send (lives in the rank's own comm window; see comm.cu)
+struct HtfHaloDst {
+    float4 *lo[2], *hi[2];           // [parity]: where this rank's low / high face goes (peer memory)
+    unsigned long long epoch;        // halo exchanges completed so far
+};
 cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr_lo, float thr_hi,
-                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st);
+                                   float4 *out_lo, float4 *out_hi, int cap, int *d_counts, int *d_overflow, cudaStream_t st,
+                                   const HtfHaloDst *dst = nullptr);
+void htf_comm_free(htf_ctx *ctx);
 cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int axis, float thr, bool less,
                               float4 *out, int cap, int *d_count, int *d_overflow, cudaStream_t st);
 

@@ -347,3 +347,37 @@ class HtfContext:
     def set_pipeline(self, slabs):
         """Slabs of the pipelined step (build of slab i+1 overlaps the pair pass of slab i); <= 1 switches it off."""
         self._ck(self.lib.htf_set_pipeline(self._h, int(slabs)))
+
+    # ---- peer-memory exchange (one process per GPU of one node; see include/htf_b200.h) ----
+    def comm_create(self, rank, world, halo_capacity):
+        """Allocate this rank's exchange window; returns its 64-byte IPC handle (bytes)."""
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.lib.htf_comm_create(self._h, int(rank), int(world), int(halo_capacity), buf))
+        return buf.raw
+
+    def comm_connect(self, handles):
+        """``handles``: the 64-byte handles of all ranks in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        self._ck(self.lib.htf_comm_connect(self._h, blob))
+
+    def comm_exchange_halo(self, local, n_own, axis, threshold_lo, threshold_hi):
+        _check_dev_f32(local, "local positions", 4)
+        self._ck(self.lib.htf_comm_exchange_halo(self._h, _ptr(local), int(n_own), int(axis), float(threshold_lo),
+                                                 float(threshold_hi), _ptr(self._overflow), self._stream()))
+        return local
+
+    def comm_allreduce(self, values):
+        """In-place sum over all ranks of a small int64 or float64 CUDA vector (<= 2048 values)."""
+        if not values.is_cuda or not values.is_contiguous() or values.dtype not in (torch.int64, torch.float64):
+            raise ValueError("comm_allreduce takes a contiguous int64 or float64 CUDA tensor")
+        fn = self.lib.htf_comm_allreduce_i64 if values.dtype == torch.int64 else self.lib.htf_comm_allreduce_f64
+        self._ck(fn(self._h, _ptr(values), int(values.numel()), self._stream()))
+        return values
+
+    def comm_status(self):
+        v = ctypes.c_int32(0)
+        self._ck(self.lib.htf_comm_status(self._h, ctypes.byref(v), self._stream()))
+        return int(v.value)
+
+    def comm_destroy(self):
+        self._ck(self.lib.htf_comm_destroy(self._h))

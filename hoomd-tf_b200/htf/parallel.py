@@ -3,9 +3,11 @@
 The reference has no multi-GPU code of its own (it inherits HOOMD's MPI domain decomposition,
 /root/reference htf/test-py/test_mpi_tensorflow.py:59-80); its row batching
 (htf/TensorflowCompute.cc:143-150,188-194) is what shards here: rank g builds and evaluates
-rows [g*N/G, (g+1)*N/G).  Per step the path has ONE exchange: the all-gather of the position
-shards; the RDF histogram (int64, order independent, so still bit-exact) and scalar collective
-variables are all-reduced.  NCCL on GPUs, gloo in the CPU tests.
+rows [g*N/G, (g+1)*N/G).  Per step the path has ONE exchange: the two faces of the rank's slab go to
+its two neighbours -- through the library's peer-memory windows (``htf_comm_*``: no NCCL, no host) or,
+where peers cannot be mapped, NCCL send/recv; ``allgather_positions`` keeps the literal all-gather.  The RDF
+histogram (int64, order independent, so still bit-exact) and scalar collective variables are all-reduced.
+NCCL on GPUs, gloo in the CPU tests.
 """
 import torch
 import torch.distributed as dist
@@ -84,7 +86,10 @@ class SlabExchange:
     host.  ``libhtf_b200`` packs the halos (stable, index order); NCCL send/recv moves them.
     """
 
-    def __init__(self, ctx, n_local, axis, lo_face, hi_face, width, capacity, group=None):
+    def __init__(self, ctx, n_local, axis, lo_face, hi_face, width, capacity, group=None, transport="auto"):
+        """``transport``: "p2p" = the library's peer-memory exchange (fused pack + send into the neighbours' windows
+        over NVLink, flags instead of a collective; everything is one stream-ordered, graph-capturable call),
+        "nccl" = pack kernels + NCCL send/recv, "auto" = p2p when every rank can map its peers, else nccl."""
         self.ctx, self.n_local, self.axis, self.cap = ctx, int(n_local), int(axis), int(capacity)
         self.lo_thr, self.hi_thr = float(lo_face) + float(width), float(hi_face) - float(width)
         self.group = group
@@ -93,8 +98,43 @@ class SlabExchange:
         dev = ctx.device
         extra = 2 * self.cap if self.world > 1 else 0
         self.local = torch.empty((self.n_local + extra, 4), dtype=torch.float32, device=dev)
-        self.send_lo = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
-        self.send_hi = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
+        self.transport = "nccl" if self.world > 1 else "none"
+        self.transport_note = ""
+        if self.world > 1 and transport in ("auto", "p2p"):
+            self._connect_p2p(require=(transport == "p2p"))
+        if self.transport != "p2p":
+            self.send_lo = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
+            self.send_hi = torch.empty((self.cap, 4), dtype=torch.float32, device=dev)
+
+    def _connect_p2p(self, require):
+        """Create this rank's window, swap the IPC handles over the process group, map the peers.  Every rank takes
+        part in both collectives whatever happened locally, and the ranks agree on the outcome."""
+        from ._lib import HtfError
+        handle, err = None, ""
+        try:
+            handle = self.ctx.comm_create(self.rank, self.world, self.cap)
+        except HtfError as ex:
+            err = str(ex)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.group)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                self.ctx.comm_connect(handles)
+            except HtfError as ex:
+                ok, err = False, str(ex)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        if all(flags):
+            self.transport = "p2p"
+            return
+        try:
+            self.ctx.comm_destroy()
+        except HtfError:
+            pass
+        self.transport_note = err or "a peer could not map the windows"
+        if require:
+            raise RuntimeError("peer-memory halo exchange unavailable: " + self.transport_note)
 
     @property
     def own(self):
@@ -102,8 +142,13 @@ class SlabExchange:
         return self.local[:self.n_local]
 
     def pack(self):
-        """Device-side half of the exchange (graph-capturable): both faces into the two send buffers."""
-        if self.world > 1:
+        """Device-side part of the exchange (graph-capturable).  p2p: the WHOLE exchange (pack straight into the
+        neighbours' windows, signal, wait, gather); nccl: both faces into the two send buffers."""
+        if self.world <= 1:
+            return
+        if self.transport == "p2p":
+            self.ctx.comm_exchange_halo(self.local, self.n_local, self.axis, self.lo_thr, self.hi_thr)
+        else:
             self.ctx.pack_halo_pair(self.own, self.axis, self.lo_thr, self.hi_thr, self.send_lo, self.send_hi)
 
     def exchange(self):
@@ -112,8 +157,9 @@ class SlabExchange:
         return self.swap()
 
     def swap(self):
-        """NCCL half of the exchange: send the packed faces to the two neighbours, receive theirs."""
-        if self.world == 1:
+        """NCCL half of the exchange: send the packed faces to the two neighbours, receive theirs (nothing left to
+        do for the peer-memory transport)."""
+        if self.world == 1 or self.transport == "p2p":
             return self.local
         prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         a = self.local[self.n_local:self.n_local + self.cap]

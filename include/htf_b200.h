@@ -56,7 +56,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 14
+#define HTF_ABI_VERSION 15
 int htf_abi_version(void);
 
 /*
@@ -309,6 +309,39 @@ int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t 
  * The reference runs every stage back to back and ends with cudaDeviceSynchronize (htf/TensorflowCompute.cc:208-211).
  */
 int htf_set_pipeline(htf_ctx *ctx, int slabs);
+
+/*
+ * ---- exchange step of the row-sharded path over peer memory (NVLink / NVSwitch) ----
+ * One process per GPU of one node.  The reference shards through HOOMD's MPI domain decomposition, whose ghost-particle
+ * exchange is host MPI traffic every step (htf/test-py/test_mpi_tensorflow.py:59-80); here every rank owns a window
+ * of device memory that its peers map (CUDA IPC), and the per-step exchange is device code only -- no NCCL, no host.
+ *
+ *   htf_comm_create   allocates this rank's window (halo receive buffers for `halo_capacity` particles per face,
+ *                     all-reduce mailboxes, flags) and returns its 64-byte IPC handle in h_handle_out.
+ *   htf_comm_connect  h_handles = the handles of ALL ranks, [world][64] in rank order (exchanged by the caller over
+ *                     whatever it has: MPI in a HOOMD plugin, torch.distributed in this repository's host code).
+ *   htf_comm_exchange_halo   rows are slabs along `axis`: packs the own particles (d_local[0..n_own)) below
+ *                     threshold_lo and above threshold_hi (stable order, sentinel padded) DIRECTLY into the previous /
+ *                     next rank's window, signals them, waits for their faces and stores those at
+ *                     d_local[n_own .. n_own + halo_capacity) (from the next rank) and
+ *                     d_local[n_own + halo_capacity .. n_own + 2 halo_capacity) (from the previous rank); d_local
+ *                     is then what htf_bin_particles takes (with htf_set_roi rejecting the sentinels).
+ *                     d_overflow (nullable) receives max(count + 1) when a face exceeds the capacity.
+ *   htf_comm_allreduce_i64 / _f64   in-place sum over all ranks of count <= 2048 values (the RDF histogram, the CV
+ *                     sum and particle count of EDS): contributions are summed in rank order, so every rank gets
+ *                     the same bits.
+ *   htf_comm_status   0, or != 0 when a wait gave up after 20 s (a peer died); synchronises the stream.
+ * All exchange calls are stream-ordered, asynchronous and CUDA-graph capturable (epochs live in device memory).
+ */
+#define HTF_COMM_HANDLE_BYTES 64
+int htf_comm_create(htf_ctx *ctx, int rank, int world, int64_t halo_capacity, unsigned char *h_handle_out);
+int htf_comm_connect(htf_ctx *ctx, const unsigned char *h_handles);
+int htf_comm_exchange_halo(htf_ctx *ctx, float *d_local, int64_t n_own, int axis, float threshold_lo, float threshold_hi,
+                           int32_t *d_overflow, void *stream);
+int htf_comm_allreduce_i64(htf_ctx *ctx, int64_t *d_values, int count, void *stream);
+int htf_comm_allreduce_f64(htf_ctx *ctx, double *d_values, int count, void *stream);
+int htf_comm_status(htf_ctx *ctx, int32_t *h_status, void *stream);
+int htf_comm_destroy(htf_ctx *ctx);
 
 /* Number of kernels the library has launched on this context since creation
  * (bench.py's gpu_launches claim). */
