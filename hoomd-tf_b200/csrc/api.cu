@@ -351,7 +351,8 @@ void htf_destroy(htf_ctx *ctx)
     if (ctx->skin_ctx) { htf_destroy(ctx->skin_ctx); ctx->skin_ctx = nullptr; }
     void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx, ctx->d_scattered,
                     ctx->d_spos, ctx->d_nlist_scratch, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
-                    ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums};
+                    ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums, ctx->d_train_packed, ctx->d_train_pred,
+                    ctx->d_train_partial, ctx->d_train_loss_partial};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
         if (!ptrs[i]) continue;
         cudaError_t e = cudaFree(ptrs[i]);
@@ -746,6 +747,53 @@ int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, cons
     HTF_CUDA(ctx, htf_launch_mlp(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
                                  reinterpret_cast<const unsigned char *>(d_packed), rbf_high,
                                  reinterpret_cast<float4 *>(d_force_energy), (cudaStream_t)stream));
+    return HTF_OK;
+}
+
+int htf_mlp_train_grads(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_raw, float rbf_high,
+                        const float *d_labels, int64_t n_total, float *d_pred_out, float *d_grads, float *d_loss, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (rows < 0 || k < 1 || !(rbf_high > 0.0f) || !d_raw || !d_grads || n_total < 1 || (rows > 0 && (!d_nlist || !d_labels))) {
+        set_err(ctx, "htf_mlp_train_grads: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->d_train_packed) {
+        if ((rc = dev_realloc(ctx, &ctx->d_train_packed, (size_t)htf_mlp_packed_bytes_host()))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_train_partial, (size_t)htf_mlp_train_partial_floats(ctx->sm_count)))) return rc;
+        if ((rc = dev_realloc(ctx, &ctx->d_train_loss_partial, (size_t)2 * ctx->sm_count))) return rc;
+    }
+    float *pred = d_pred_out;
+    if (!pred) {
+        if (rows > ctx->train_pred_rows) {
+            if ((rc = dev_realloc(ctx, &ctx->d_train_pred, (size_t)rows * 4))) return rc;
+            ctx->train_pred_rows = rows;
+        }
+        pred = ctx->d_train_pred;
+    }
+    // pass 1: predictions of the current parameters (tcgen05 inference kernel); pass 2: reverse sweep
+    HTF_CUDA(ctx, htf_launch_mlp_pack(ctx, d_raw, ctx->d_train_packed, st));
+    HTF_CUDA(ctx, htf_launch_mlp(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k, ctx->d_train_packed, rbf_high,
+                                 reinterpret_cast<float4 *>(pred), st));
+    HTF_CUDA(ctx, htf_launch_mlp_train(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k, d_raw, rbf_high,
+                                       reinterpret_cast<const float4 *>(pred), reinterpret_cast<const float4 *>(d_labels), n_total,
+                                       ctx->d_train_partial, ctx->d_train_loss_partial, d_grads, d_loss, st));
+    return HTF_OK;
+}
+
+int htf_adam_step(htf_ctx *ctx, float *d_params, const float *d_grads, float *d_m, float *d_v, float *d_t, int64_t count,
+                  float learning_rate, float beta1, float beta2, float epsilon, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (count < 0 || count > 2000000000LL || (count > 0 && (!d_params || !d_grads || !d_m || !d_v || !d_t))) {
+        set_err(ctx, "htf_adam_step: bad arguments"); return HTF_EINVAL;
+    }
+    DeviceGuard guard(ctx->device);
+    HTF_CUDA(ctx, htf_launch_adam(ctx, d_params, d_grads, d_m, d_v, d_t, (int)count, learning_rate, beta1, beta2, epsilon,
+                                  (cudaStream_t)stream));
     return HTF_OK;
 }
 

@@ -81,6 +81,11 @@ struct htf_ctx {
     int pipe_pass_bps;            // blocks per SM of a slab's pair pass
     int pipe_build_streams;       // 1 or 2
     HtfComm *comm;                // peer-memory exchange state (comm.cu), nullptr until htf_comm_create
+    // scratch of the MLP training step: packed bf16 parameters, predictions, per-block partial gradients / loss sums
+    unsigned char *d_train_packed;
+    float *d_train_pred, *d_train_partial;
+    double *d_train_loss_partial;
+    int64_t train_pred_rows;
     int64_t launches;
     char err[512];
 };
@@ -154,6 +159,14 @@ int htf_mlp_raw_count_host();
 cudaError_t htf_launch_mlp_pack(htf_ctx *ctx, const float *raw, unsigned char *packed, cudaStream_t st);
 cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const unsigned char *packed,
                            float rbf_high, float4 *fe, cudaStream_t st);
+
+// pairwise-MLP training step (mlp_train.cu)
+int htf_mlp_train_partial_floats(int sm_count);
+cudaError_t htf_launch_mlp_train(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *raw, float rbf_high,
+                                 const float4 *pred, const float4 *labels, int64_t n_total, float *partial, double *loss_partial,
+                                 float *grads, float *loss, cudaStream_t st);
+cudaError_t htf_launch_adam(htf_ctx *ctx, float *params, const float *grads, float *m, float *v, float *t, int n, float lr,
+                            float beta1, float beta2, float eps, cudaStream_t st);
 
 // host: thresholds q_b (b = 1..nb-1) in rsq space such that bin(q) = #{b : q >= q_b}
 void htf_rdf_thresholds(float r_lo, float r_hi, int nbins, float *thr /* [nbins+1] */);

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
 FLAG_DETERMINISTIC = 1
@@ -50,6 +50,8 @@ SYMBOLS = {
     "htf_lj_rows": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i32, _vp]),
     "htf_lj_cv_step": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _f32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp]),
     "htf_set_pipeline": (_i32, [_vp, _i32]),
+    "htf_mlp_train_grads": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "htf_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "htf_comm_create": (_i32, [_vp, _i32, _i32, _i64, ctypes.c_char_p]),
     "htf_comm_connect": (_i32, [_vp, ctypes.c_char_p]),
     "htf_comm_exchange_halo": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),

@@ -263,6 +263,37 @@ class HtfContext:
                                          self._stream()))
         return out
 
+    def mlp_train_grads(self, nlist, raw, rbf_high, labels, n_total=None, grads=None, pred=None, loss=None):
+        """Gradient of the force-matching MSE of the pairwise MLP w.r.t. its raw parameters (see include/htf_b200.h).
+        Returns (grads float32[10497], pred float32[rows,4], loss float32[1])."""
+        _check_dev_f32(nlist, "nlist", 4)
+        _check_dev_f32(labels, "labels", 4)
+        rows, k = nlist.shape[0], nlist.shape[1]
+        n_raw, _ = self.mlp_param_sizes()
+        if not (raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous() and raw.numel() == n_raw):
+            raise ValueError("raw MLP parameters must be a contiguous float32 CUDA tensor of %d values" % n_raw)
+        if labels.shape[0] != rows:
+            raise ValueError("labels must have one row per nlist row")
+        if grads is None:
+            grads = torch.empty(n_raw, dtype=torch.float32, device=self.device)
+        if pred is None:
+            pred = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+        if loss is None:
+            loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        self._ck(self.lib.htf_mlp_train_grads(self._h, _ptr(nlist), rows, int(k), _ptr(raw), float(rbf_high), _ptr(labels),
+                                              int(rows if n_total is None else n_total), _ptr(pred), _ptr(grads), _ptr(loss),
+                                              self._stream()))
+        return grads, pred, loss
+
+    def adam_step(self, params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        """Fused Keras-Adam update in place; ``t`` is a float32[1] CUDA step counter that the call increments."""
+        for x in (params, grads, m, v, t):
+            if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+                raise ValueError("adam_step takes contiguous float32 CUDA tensors")
+        self._ck(self.lib.htf_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(t), int(params.numel()),
+                                        float(lr), float(beta1), float(beta2), float(eps), self._stream()))
+        return params
+
     def rdf_hist(self, nlist, r_range, nbins=100, row_pos=None, type_i=None, type_j=None, bins=None,
                  type_tensor=None):
         """compute_rdf's integer histogram: int64[nbins+2], accumulated into ``bins`` if given.

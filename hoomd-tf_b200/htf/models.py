@@ -341,3 +341,63 @@ class PairwiseMLPModel(SimModel):
             return ops.mlp_forces(nlist, self.raw_parameters(), self.r_cut)
         energy = 0.5 * self.pair_energy(nlist).sum(dim=1)
         return compute_nlist_forces(nlist, energy)
+
+    # ---- online force matching (BASELINE config 4): the Keras train_on_batch of the reference as one library call ----
+    def _linears(self):
+        return (self.dense1, self.dense2, self.dense3, self.last)
+
+    def load_raw_parameters(self, raw):
+        """Inverse of ``raw_parameters``: write a flat fp32 blob back into the Linear layers."""
+        o = 0
+        with torch.no_grad():
+            for lin in self._linears():
+                n = lin.weight.numel()
+                lin.weight.copy_(raw[o:o + n].view_as(lin.weight)); o += n
+                n = lin.bias.numel()
+                lin.bias.copy_(raw[o:o + n]); o += n
+
+    def train_on_batch(self, x, y, reset_metrics=False, n_total=None, group=None):
+        """One optimizer step on MSE(forces+energy [N,4], labels [N,4]) (htf/tensorflowcompute.py:367-370).
+
+        With the default Adam optimizer on a CUDA device this is the fused path: ``htf_mlp_train_grads`` (inference pass
+        + hand-written reverse sweep through the force gradient on the tensor cores), a sum of the gradients over the
+        ranks when ``torch.distributed`` is initialised (row shards; ``n_total`` = rows of all ranks), and the fused
+        ``htf_adam_step``.  Any other optimizer / loss, CPU tensors or ``fused=False`` use torch autograd."""
+        nlist = x[0]
+        mse = self.loss is not None and len(self.loss) >= 1 and isinstance(self.loss[0], str) and \
+            self.loss[0].lower() in ("meansquarederror", "mse", "mean_squared_error") and all(l is None for l in self.loss[1:])
+        adam = isinstance(self.optimizer, torch.optim.Adam) and len(self.optimizer.param_groups) == 1
+        if not (self.fused and mse and adam and torch.is_tensor(nlist) and nlist.is_cuda):
+            return super().train_on_batch(x, y, reset_metrics=reset_metrics)
+        import torch.distributed as dist
+        if reset_metrics:
+            for m_ in self.metrics:
+                m_.reset()
+        ctx = ops.default_context(nlist.device)
+        nl = nlist.detach()
+        if nl.dtype != torch.float32 or not nl.is_contiguous():
+            nl = nl.to(torch.float32).contiguous()
+        labels = y.detach().to(torch.float32).contiguous()
+        raw = self.raw_parameters()
+        st = getattr(self, "_fused_adam", None)
+        if st is None or st[0].device != raw.device:
+            st = (torch.zeros_like(raw), torch.zeros_like(raw), torch.zeros(1, dtype=torch.float32, device=raw.device))
+            self._fused_adam = st
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if n_total is None:
+            n_total = nl.shape[0]
+            if world > 1:
+                t_ = torch.tensor([n_total], dtype=torch.int64, device=raw.device)
+                dist.all_reduce(t_, group=group)
+                n_total = int(t_.item())
+        grads, pred, loss = ctx.mlp_train_grads(nl, raw, self.r_cut, labels, n_total=n_total)
+        if world > 1:
+            packed = torch.cat([grads, loss])
+            dist.all_reduce(packed, group=group)                    # ~10.5k floats: the weight-gradient all-reduce
+            grads, loss = packed[:-1].contiguous(), packed[-1:]
+        pg = self.optimizer.param_groups[0]
+        ctx.adam_step(raw, grads, st[0], st[1], st[2], lr=pg["lr"], beta1=pg["betas"][0], beta2=pg["betas"][1], eps=pg["eps"])
+        self.load_raw_parameters(raw)
+        self.last_grads, self.last_pred = grads, pred
+        self.metrics[0].update_state(loss[0])
+        return loss[0]

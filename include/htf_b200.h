@@ -56,7 +56,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 15
+#define HTF_ABI_VERSION 16
 int htf_abi_version(void);
 
 /*
@@ -309,6 +309,28 @@ int htf_lj_cv_step(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t 
  * The reference runs every stage back to back and ends with cudaDeviceSynchronize (htf/TensorflowCompute.cc:208-211).
  */
 int htf_set_pipeline(htf_ctx *ctx, int slabs);
+
+/*
+ * Training step of the pairwise-MLP force field (BASELINE config 4, online force matching): what Keras does behind
+ * model.train_on_batch(x=inputs, y=labels) in the reference's label mode (htf/tensorflowcompute.py:346-370, labels from
+ * htf/TensorflowCompute.cc:177-187,:251-269) -- the gradient of MSE(compute_nlist_forces output [N,4], labels [N,4])
+ * with respect to the parameters, i.e. a backward pass THROUGH the force gradient -- as one reverse sweep on the
+ * tensor cores.  d_raw is the fp32 blob of htf_mlp_pack (10,497 values), d_grads receives the gradient in the same
+ * layout, d_loss (nullable) this rank's share of the loss: sum over its rows / (4 n_total).  n_total = rows of ALL
+ * ranks (the mean of the loss runs over them); with several ranks the caller sums d_grads / d_loss over the ranks
+ * (htf_comm_allreduce_f32 or NCCL).  d_pred_out (nullable, [rows,4]) receives the model's forces + energy.
+ */
+int htf_mlp_train_grads(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const float *d_raw, float rbf_high,
+                        const float *d_labels, int64_t n_total, float *d_pred_out, float *d_grads, float *d_loss,
+                        void *stream);
+
+/*
+ * One Adam step on count parameters, fused (m, v, bias-corrected step, update; the step counter d_t is a device scalar
+ * that the call increments): tf.keras.optimizers.Adam as used by train_on_batch -- lr_t = lr sqrt(1 - b2^t) / (1 - b1^t),
+ * p -= lr_t m / (sqrt(v) + epsilon).  Keras defaults: lr 1e-3, beta 0.9 / 0.999, epsilon 1e-7.
+ */
+int htf_adam_step(htf_ctx *ctx, float *d_params, const float *d_grads, float *d_m, float *d_v, float *d_t, int64_t count,
+                  float learning_rate, float beta1, float beta2, float epsilon, void *stream);
 
 /*
  * ---- exchange step of the row-sharded path over peer memory (NVLink / NVSwitch) ----

@@ -227,3 +227,82 @@ class EDSLayer:
             self.alpha = f(self.alpha - f(lr_t * self.m) / f(f(np.sqrt(self.v)) + f(1e-8)))
         self.n = (self.n + 1) % self.period               # :193
         return self.alpha
+
+
+def pairwise_mlp_train_grads(nl, raw, rbf_high, labels):
+    """Gradient of the force-matching loss of the pairwise MLP with respect to its parameters -- numpy restatement of
+    what Keras ``train_on_batch`` differentiates in the reference's label/training mode
+    (/root/reference htf/tensorflowcompute.py:346-370: MSE between the model's first output [N,4] = forces + energy and
+    the label forces [N,4]), for the config-4 model (RBF(32) -> 3 x Dense(64, tanh) -> Dense(1), e_i = 1/2 sum_j u).
+
+    L = mean over the N x 4 entries of (pred - labels)^2.  With r, u(r), u'(r) per pair, F_i = sum_j u' a / r and
+    e_i = 1/2 sum_j u (valid pairs), dL/dtheta = sum_p [g_p du'_p/dtheta + h_p du_p/dtheta] with
+    g_p = (dF_i . a_p / r_p) / (2N) and h_p = de_i / (4N): the reverse sweep through the value/tangent chain below.
+    Returns (loss, grads in the raw-blob layout of include/htf_b200.h, pred[N,4]).  float64 throughout: this is the
+    checker for the tensor-core training kernel (PARITY UNPINNED against the reference, which has no fixed-weight
+    instance of such a model; pinned against torch autograd in tests/)."""
+    f = np.float64
+    nl = np.asarray(nl, dtype=f)
+    raw = np.asarray(raw, dtype=f)
+    labels = np.asarray(labels, dtype=f)
+    o = 0
+    def take(n, shape):
+        nonlocal o
+        a = raw[o:o + n].reshape(shape); o += n
+        return a
+    W1, b1 = take(64 * 32, (64, 32)), take(64, (64,))
+    W2, b2 = take(64 * 64, (64, 64)), take(64, (64,))
+    W3, b3 = take(64 * 64, (64, 64)), take(64, (64,))
+    w4, b4 = take(64, (64,)), take(1, (1,))
+    N, K = nl.shape[0], nl.shape[1]
+    a = nl[..., :3] + 1e-7
+    r = np.sqrt((a * a).sum(-1))
+    mask = r > 3e-6
+    mu = np.linspace(0.0, rbf_high, 32)
+    gap = mu[1] - mu[0]
+    uc = r[..., None] - mu
+    phi = np.exp(-(uc * uc) / gap)
+    dphi = -2.0 * uc / gap * phi
+    hs, hps = [phi], [dphi]
+    for W, b in ((W1, b1), (W2, b2), (W3, b3)):
+        z, zp = hs[-1] @ W.T + b, hps[-1] @ W.T
+        h = np.tanh(z)
+        hs.append(h); hps.append((1.0 - h * h) * zp)
+    u, du = hs[-1] @ w4 + b4[0], hps[-1] @ w4
+    coef = np.where(mask, du / np.where(mask, r, 1.0), 0.0)
+    pred = np.empty((N, 4))
+    pred[:, :3] = (coef[..., None] * a).sum(1)
+    pred[:, 3] = (0.5 * np.where(mask, u, 0.0)).sum(1)
+    diff = pred - labels
+    loss = float((diff ** 2).mean())
+    g = np.where(mask, (diff[:, None, :3] * a).sum(-1) / np.where(mask, r, 1.0), 0.0) / (2.0 * N)     # weight of du'/dtheta
+    hh = np.where(mask, diff[:, 3:4] / (4.0 * N), 0.0) * np.ones((1, K))                             # weight of du/dtheta
+    # reverse sweep
+    gw4 = (hh[..., None] * hs[3] + g[..., None] * hps[3]).sum((0, 1))
+    gb4 = np.array([hh.sum()])
+    hb, hpb = hh[..., None] * w4, g[..., None] * w4            # adjoints of h3, h3'
+    grads = []
+    for l, W in ((3, W3), (2, W2), (1, W1)):
+        h, hp = hs[l], hps[l]
+        s = 1.0 - h * h
+        zb = s * hb - 2.0 * h * hp * hpb
+        zpb = s * hpb
+        gW = np.einsum("nko,nki->oi", zb, hs[l - 1]) + np.einsum("nko,nki->oi", zpb, hps[l - 1])
+        gb = zb.sum((0, 1))
+        grads.append((gW, gb))
+        hb, hpb = zb @ W, zpb @ W
+    (gW3, gb3), (gW2, gb2), (gW1, gb1) = grads
+    flat = np.concatenate([gW1.ravel(), gb1, gW2.ravel(), gb2, gW3.ravel(), gb3, gw4, gb4])
+    return loss, flat, pred
+
+
+def adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+    """One Keras Adam step (tf.keras.optimizers.Adam, the optimizer behind the reference's ``train_on_batch``;
+    defaults lr 1e-3, epsilon 1e-7): t is the step count AFTER the increment.  fp32, returns (params, m, v)."""
+    f = np.float32
+    params, grads, m, v = (np.asarray(x, dtype=f) for x in (params, grads, m, v))
+    m = (f(beta1) * m + f(1.0 - beta1) * grads).astype(f)
+    v = (f(beta2) * v + f(1.0 - beta2) * grads * grads).astype(f)
+    lr_t = f(lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
+    params = (params - lr_t * m / (np.sqrt(v) + f(eps))).astype(f)
+    return params, m, v

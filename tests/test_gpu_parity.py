@@ -719,3 +719,114 @@ def test_eds_step_kernel_matches_oracle_and_torch_layers(oracle_mod):
         c = float(ref(cv))
         assert abs(a - c) <= 2e-6 * max(1.0, abs(c)) and abs(b - c) <= 2e-6 * max(1.0, abs(c)), (i, a, b, c)
     assert abs(float(fused.alpha)) > 1e-3 and int(fused.n) == 40 % 6
+
+
+TRAIN_TOL_MAX, TRAIN_TOL_RMS = 1e-1, 3e-2       # bf16 operands (activations AND adjoints), fp32 accumulation
+
+
+def _mlp_raw_np(seed=3):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for fo, fi in ((64, 32), (64, 64), (64, 64), (1, 64)):
+        parts.append((rng.standard_normal((fo, fi)) / np.sqrt(fi)).ravel())
+        parts.append(0.1 * rng.standard_normal(fo))
+    return np.concatenate(parts).astype(np.float32)
+
+
+@pytest.mark.parametrize("K,rows_used", [(64, None), (40, 777)])
+def test_mlp_training_gradient_kernel(oracle_mod, K, rows_used):
+    """htf_mlp_train_grads (inference pass + hand-written reverse sweep through the force gradient, warp-level
+    tensor-core MMAs) against the float64 oracle / torch double backward of the same loss.  Stated tolerance: per
+    parameter block (W1, b1, ..., w4, b4), max |dg| <= 1e-1 rms(g_block) and rms dg <= 3e-2 rms(g_block); the loss to
+    1e-2 relative; the predictions at the inference kernel's tolerance.  K = 40 with a ragged row count exercises
+    tiles that straddle rows and the padded tail tile."""
+    from htf import synthetic
+    import htf
+    pos, lo, hi = synthetic.lattice_fluid((12, 12, 12), 0.7, seed=4)
+    r_cut = 2.5 if K == 64 else 2.0
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    nl = ctx.build_nlist(torch.from_numpy(pos).cuda())
+    if rows_used:
+        nl = nl[:rows_used].contiguous()
+    rows = nl.shape[0]
+    nl_h = nl.cpu().numpy()
+    raw = _mlp_raw_np(3)
+    fe_lj, _, _ = oracle_mod.lj(nl_h)
+    labels = (0.05 * fe_lj).astype(np.float32)                 # force-matching target: a scaled LJ fluid
+    loss_o, g_o, pred_o = oracle_mod.pairwise_mlp_train_grads(nl_h, raw, r_cut, labels)
+    grads, pred, loss = ctx.mlp_train_grads(nl, torch.from_numpy(raw).cuda(), r_cut, torch.from_numpy(labels).cuda())
+    torch.cuda.synchronize()
+    g = grads.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    cuts = np.cumsum([0, 2048, 64, 4096, 64, 4096, 64, 64, 1])
+    names = ["W1", "b1", "W2", "b2", "W3", "b3", "w4", "b4"]
+    for i, name in enumerate(names):
+        a, b = g[cuts[i]:cuts[i + 1]], g_o[cuts[i]:cuts[i + 1]]
+        scale = np.sqrt(np.mean(b ** 2)) + 1e-30
+        emax, erms = np.abs(a - b).max() / scale, np.sqrt(np.mean((a - b) ** 2)) / scale
+        print("train grads %s: max %.3e rms %.3e (rms g %.3e)" % (name, emax, erms, scale))
+        assert emax <= TRAIN_TOL_MAX and erms <= TRAIN_TOL_RMS, name
+    cos = float(g @ g_o / (np.linalg.norm(g) * np.linalg.norm(g_o)))
+    assert cos > 0.999
+    assert abs(float(loss) - loss_o) <= 1e-2 * loss_o
+    sf = np.sqrt(np.mean(pred_o[:, :3] ** 2))
+    assert np.abs(pred.cpu().numpy()[:, :3] - pred_o[:, :3]).max() / sf < MLP_TOL_MAX
+    # determinism: the partial sums are combined in block order
+    grads2, _, _ = ctx.mlp_train_grads(nl, torch.from_numpy(raw).cuda(), r_cut, torch.from_numpy(labels).cuda())
+    assert torch.equal(grads, grads2)
+    # n_total rescales the gradient exactly as the mean over all ranks' rows would
+    grads3, _, loss3 = ctx.mlp_train_grads(nl, torch.from_numpy(raw).cuda(), r_cut, torch.from_numpy(labels).cuda(), n_total=4 * rows)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(grads3.cpu().numpy(), 0.25 * grads.cpu().numpy(), rtol=2e-6, atol=1e-12)
+    assert abs(float(loss3) - 0.25 * float(loss)) <= 1e-6 * float(loss)
+
+
+def test_adam_step_kernel_matches_keras_formula(oracle_mod):
+    import htf
+    ctx = htf.HtfContext(8, 8, 1.0)
+    rng = np.random.default_rng(2)
+    n = 10497
+    p0 = rng.standard_normal(n).astype(np.float32)
+    p, m, v = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    dp, dm, dv = torch.from_numpy(p0.copy()).cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    dt = torch.zeros(1, device="cuda")
+    for t in range(1, 5):
+        g = rng.standard_normal(n).astype(np.float32)
+        p, m, v = oracle_mod.adam_step(p, g, m, v, t)
+        ctx.adam_step(dp, torch.from_numpy(g).cuda(), dm, dv, dt)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dp.cpu().numpy(), p, rtol=0, atol=3e-7)
+        np.testing.assert_allclose(dm.cpu().numpy(), m, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(dv.cpu().numpy(), v, rtol=1e-6, atol=1e-12)
+        assert float(dt) == float(t)
+
+
+def test_fused_force_matching_training_reduces_loss_and_tracks_autograd():
+    """BASELINE config 4 in small: PairwiseMLPModel under tfcompute in training mode (labels = LJ forces, the
+    reference's set_reference_forces path): the fused train_on_batch lowers the loss, and its first step equals the
+    torch-autograd step (fused=False) of an identically initialised model to the bf16 tolerance."""
+    import htf
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((10, 10, 10), 0.7, seed=6)
+    K, r_cut = 64, 2.5
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    nl = ctx.build_nlist(torch.from_numpy(pos).cuda())
+    labels = 0.05 * ctx.lj_forces(nl)
+    models = []
+    for fused in (True, False):
+        m = htf.models.PairwiseMLPModel(K, r_cut=r_cut, seed=11, fused=fused).cuda()
+        m.compile("Adam", "MeanSquaredError")
+        models.append(m)
+    l0 = float(models[0].train_on_batch([nl, None, None], labels))
+    l0_ref = float(models[1].train_on_batch([nl, None, None], labels))
+    assert abs(l0 - l0_ref) <= 2e-2 * l0_ref
+    ra, rb = models[0].raw_parameters(), models[1].raw_parameters()
+    # one Adam step moves every parameter by ~lr in the direction of the gradient's sign: compare the moves
+    init = htf.models.PairwiseMLPModel(K, r_cut=r_cut, seed=11).cuda().raw_parameters()
+    da, db = (ra - init), (rb - init)
+    agree = float(((da * db) > 0).float().mean())
+    assert agree > 0.97, agree
+    losses = [l0]
+    for _ in range(15):
+        losses.append(float(models[0].train_on_batch([nl, None, None], labels)))
+    assert losses[-1] < 0.9 * losses[0], losses

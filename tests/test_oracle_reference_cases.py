@@ -270,3 +270,66 @@ def test_reference_fixture_comparator_and_any_committed_reference_fixtures():
     for f in sorted(glob.glob(os.path.join(root, "tests", "golden", "*_ref.npz"))):
         name = os.path.basename(f)[:-8]
         assert m.compare(name, dict(np.load(os.path.join(root, "tests", "golden", name + ".npz"))), dict(np.load(f)))
+
+
+def _mlp_raw(seed=3):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for fo, fi in ((64, 32), (64, 64), (64, 64), (1, 64)):
+        parts.append((rng.standard_normal((fo, fi)) / np.sqrt(fi)).ravel())
+        parts.append(0.1 * rng.standard_normal(fo))
+    return np.concatenate(parts)
+
+
+def test_training_gradient_oracle_matches_torch_double_backward(oracle_mod):
+    """The reverse sweep through the value / tangent chain (oracle.pairwise_mlp_train_grads, the checker of the
+    tensor-core training kernel) against torch differentiating MSE(compute_nlist_forces output, labels) -- the double
+    backward Keras performs in the reference's train_on_batch (htf/tensorflowcompute.py:346-370) -- in float64."""
+    torch = pytest.importorskip("torch")
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((5, 5, 5), 0.7, seed=3)
+    nl, _, _ = oracle_mod.nlist(pos, lo, hi, 2.5, 64)
+    raw = _mlp_raw()
+    labels = np.random.default_rng(1).standard_normal((pos.shape[0], 4))
+    loss, g, pred = oracle_mod.pairwise_mlp_train_grads(nl, raw, 2.5, labels)
+    t = torch.tensor(raw, dtype=torch.float64, requires_grad=True)
+    cuts = np.cumsum([0, 2048, 64, 4096, 64, 4096, 64, 64, 1])
+    W1, b1, W2, b2, W3, b3, w4, b4 = (t[cuts[i]:cuts[i + 1]] for i in range(8))
+    nlt = torch.tensor(nl, dtype=torch.float64, requires_grad=True)
+    a = nlt[..., :3] + 1e-7
+    r = torch.sqrt((a * a).sum(-1))
+    mu = torch.linspace(0, 2.5, 32, dtype=torch.float64)
+    h = torch.exp(-(r[..., None] - mu) ** 2 / (mu[1] - mu[0]))
+    for W, b, fi in ((W1, b1, 32), (W2, b2, 64), (W3, b3, 64)):
+        h = torch.tanh(h @ W.reshape(64, fi).T + b)
+    u = torch.where(r > 3e-6, h @ w4 + b4[0], torch.zeros_like(r))
+    e = 0.5 * u.sum(1)
+    G = torch.autograd.grad(e.sum(), nlt, create_graph=True)[0]
+    predt = torch.cat([(2 * G).sum(1)[:, :3], e[:, None]], 1)
+    L = ((predt - torch.tensor(labels)) ** 2).mean()
+    L.backward()
+    assert abs(loss - float(L)) <= 1e-12 * abs(float(L))
+    np.testing.assert_allclose(pred, predt.detach().numpy(), rtol=1e-10, atol=1e-12)
+    gt = t.grad.numpy()
+    assert np.abs(g - gt).max() <= 1e-10 * np.abs(gt).max()
+    # float32 forward restatement agrees with the float64 predictions
+    pred32 = oracle_mod.pairwise_mlp(nl, raw, 2.5)
+    assert np.abs(pred32 - pred).max() <= 2e-4 * np.abs(pred).max()
+
+
+def test_adam_oracle_matches_torch_adam_shape_and_keras_formula(oracle_mod):
+    """oracle.adam_step is tf.keras.optimizers.Adam's update; the first steps coincide with torch.optim.Adam up to the
+    placement of epsilon (sqrt(v) + eps vs sqrt(v_hat) + eps), i.e. to ~eps / |g| relative."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(50).astype(np.float32)
+    p, m, v = p0.copy(), np.zeros(50, np.float32), np.zeros(50, np.float32)
+    tp = torch.tensor(p0.copy(), requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=1e-3, eps=1e-7)
+    for t in range(1, 6):
+        g = rng.standard_normal(50).astype(np.float32)
+        p, m, v = oracle_mod.adam_step(p, g, m, v, t)
+        tp.grad = torch.tensor(g)
+        opt.step()
+        np.testing.assert_allclose(p, tp.detach().numpy(), rtol=0, atol=2e-6)
+    assert np.abs(p - p0).max() > 1e-3                        # it moved: five steps of about lr each
