@@ -43,10 +43,13 @@ def parse():
                     help="cfg1..cfg5: BASELINE.json configs (default cfg3 = 1M particles, K=64, the size the target is "
                          "quoted on); refbench: the reference's own pytest-benchmark (htf/test-py/benchmark.py: N=256 2-D "
                          "lattice, NN=64, r_cut=3, Langevin, 4000 + 1000 steps, whole simulation) through the public API")
-    ap.add_argument("--model", default="lj", choices=["lj", "mlp", "eds"],
+    ap.add_argument("--model", default="lj", choices=["lj", "mlp", "eds", "mlp-train"],
                     help="lj: closed-form LJ + virial (the headline path); mlp: BASELINE config 3's pairwise-MLP force "
                          "field on the tensor cores (forces + energy); eds: BASELINE config 5's EDS bias on the smooth "
-                         "coordination-number CV + 100-bin RDF + LJ in one fused pass (use with --workload cfg5)")
+                         "coordination-number CV + 100-bin RDF + LJ in one fused pass (use with --workload cfg5); mlp-train: "
+                         "BASELINE config 4's online force matching -- every step trains the pairwise MLP on LJ label forces: "
+                         "inference pass, hand-written reverse sweep through the force gradient, gradient all-reduce, fused "
+                         "Adam (use with --workload cfg4)")
     ap.add_argument("--skin", type=float, default=0.0,
                     help="> 0: buffered neighbor lists like HOOMD's r_buff (the reference's own split): search with "
                          "r_cut + skin every --rebuild-every steps, distance filter every step; the particles then "
@@ -86,6 +89,9 @@ def peaks():
 
 
 MLP_FLOP_PER_PAIR = 2 * 2 * (32 * 64 + 64 * 64 + 64 * 64 + 64)     # value and tangent chains, multiply+add
+# training step, per valid pair: the forward chains (once), the input-gradient chains back to h1 (two 64x64 layers, value
+# and tangent adjoints) and the weight gradients of all three layers (both adjoints) + the last layer
+MLP_TRAIN_FLOP_PER_PAIR = MLP_FLOP_PER_PAIR + 2 * 2 * (2 * 64 * 64) + 2 * 2 * (32 * 64 + 64 * 64 + 64 * 64) + 2 * 2 * 64
 
 
 def tensor_peak():
@@ -199,15 +205,17 @@ def run_reference(args):
     world = max(1, args.gpus)
     pos_g, lo, hi, r_cut, K = workload(args, world)          # the b200 arm's system at this N (weak scaling)
     n_global = pos_g.shape[0]
-    rows = min(n_global, 32768 if args.model == "mlp" else 262144)   # bounded sample: a row slab of that system
+    rows = min(n_global, 2048 if args.model == "mlp-train" else 32768 if args.model == "mlp" else 262144)   # bounded sample
     g0 = (n_global // world - rows) // 2
     pos, a0 = slab_with_halo(pos_g, g0, g0 + rows, r_cut)    # what one rank of a row-sharded CPU run would hold
     n = pos.shape[0]
-    if args.model == "mlp":
+    if args.model in ("mlp", "mlp-train"):
         raw = mlp_raw_parameters()
 
     def step():
         nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
+        if args.model == "mlp-train":
+            return cpu_train_step(oracle, nl, raw, r_cut)
         if args.model == "mlp":
             return oracle.pairwise_mlp(nl, raw, r_cut)
         fe, _, v6 = oracle.lj(nl, virial=True)
@@ -270,10 +278,14 @@ def mlp_raw_parameters(seed=3):
 
 
 def cfg_dict(args, n, K, r_cut, world):
-    return {"workload": "lj_fluid_%s%s%s" % (args.workload, "+rdf100" if args.rdf else "", "+pairwise_mlp" if args.model == "mlp" else ""),
+    return {"workload": "lj_fluid_%s%s%s" % (args.workload, "+rdf100" if args.rdf else "", "+pairwise_mlp" if args.model == "mlp" else "+pairwise_mlp_training" if args.model == "mlp-train" else ""),
             "particles": n, "particles_per_gpu": n // world, "nneighbor_cutoff": K, "r_cut": r_cut,
             "model": ("pairwise MLP: RBF(32) -> 3 x Dense(64, tanh) -> Dense(1), bf16 operands / fp32 accumulation (tcgen05)"
                       if args.model == "mlp" else
+                      "online force matching: pairwise MLP (RBF(32) -> 3 x Dense(64, tanh) -> Dense(1)) trained every step on "
+                      "0.05 x LJ label forces, MSE over [N,4] + Adam(1e-3): inference pass (tcgen05) + reverse sweep through the "
+                      "force gradient (warp MMAs, bf16 / fp32 accumulation) + fused Adam"
+                      if args.model == "mlp-train" else
                       "LJ + EDS bias (period 25, lr 5.0) on the smooth coordination CV (r0 1.3) + 100-bin RDF, one fused pass"
                       if args.model == "eds" else "LJ (nlist_rinv closed form) + 6-component virial"),
             "sharding": ("particle rows (z-slabs), %s per step" % ("halo exchange of the two slab faces"
@@ -355,6 +367,12 @@ def measure(args, env, scaling, full):
     packed = None
     if args.model == "mlp":
         packed = ctx.mlp_pack(torch.from_numpy(mlp_raw_parameters()).to(dev))
+    train = None
+    if args.model == "mlp-train":
+        raw0 = torch.from_numpy(mlp_raw_parameters()).to(dev)
+        train = {"raw": raw0.clone(), "m": torch.zeros_like(raw0), "v": torch.zeros_like(raw0),
+                 "t": torch.zeros(1, dtype=torch.float32, device=dev), "g": torch.empty_like(raw0),
+                 "loss": torch.zeros(1, dtype=torch.float32, device=dev), "labels": None, "raw0": raw0}
     eds_model = None
     if args.model == "eds":
         # EDS period 25, learning rate 5.0 as examples/03; the set point becomes the initial CV + 5 % below
@@ -402,7 +420,13 @@ def measure(args, env, scaling, full):
             ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
 
     def phase_force():
-        if eds_model is not None:
+        if train is not None:
+            # one online force-matching step: gradient of MSE(model forces+energy, labels), summed over ranks, Adam
+            ctx.mlp_train_grads(nl, train["raw"], r_cut, train["labels"], n_total=n, grads=train["g"], pred=fe, loss=train["loss"])
+            if world > 1:
+                dist.all_reduce(train["g"])
+            ctx.adam_step(train["raw"], train["g"], train["m"], train["v"], train["t"], lr=1e-3)
+        elif eds_model is not None:
             eds_model.compute(nl, None, None)                         # fused LJ + CV + RDF pass, all-reduces, EDS update, bias
         elif packed is not None:
             ctx.mlp_forces(nl, packed, r_cut, out=fe)
@@ -434,6 +458,11 @@ def measure(args, env, scaling, full):
         if marks is not None:
             marks[4].record()
 
+    if train is not None:
+        # labels: 0.05 x the LJ forces of the same configuration (the library's own LJ pass, outside every timed region)
+        phase_exchange(); phase_bin(); phase_build()
+        train["labels"] = ctx.lj_forces(nl).mul_(0.05)
+        torch.cuda.synchronize()
     if eds_model is not None:
         step()                                                        # one pass to measure the initial CV
         eds_model.eds_bias.set_point.fill_(float(eds_model.cv_avg.result()) * 1.05)
@@ -443,7 +472,8 @@ def measure(args, env, scaling, full):
     #      phases stay live).  Binning alone is six dependent launches of a few microseconds.  NCCL stays eager. ----
     graphs = None
     launches_per_step = None
-    eager_force = eds_model is not None or (bins is not None and world > 1 and not p2p)   # host-side collectives / metric updates
+    eager_force = eds_model is not None or (bins is not None and world > 1 and not p2p) or \
+        (train is not None and world > 1)                          # host-side collectives / metric updates
     if not skin and not args.no_graph and (world == 1 or halo):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -600,6 +630,21 @@ def measure(args, env, scaling, full):
                                 "note": "41,216 useful flop per VALID pair (value + tangent through 32-64-64-64-1); the kernel's own "
                                         "bound is the MUFU pipe (200 MUFU per pair at 16 lanes/clk/SM), see DESIGN.md",
                                 "nlist_build_ms": build_ms, "nlist_build_frac": achieved / peak}
+        if train is not None:
+            tpeak, tsrc = tensor_peak()
+            valid_pairs = int((nl[:, :, :3].abs().sum(-1) > 0).sum().item())
+            flop = valid_pairs * MLP_TRAIN_FLOP_PER_PAIR
+            tf = flop / (force_ms * 1e-3) / 1e12
+            line["dtype"] = "bf16"
+            line["roofline"] = {"bound": "tensor", "kernel": "training step: mlp_force_kernel (tcgen05) + mlp_train_kernel (warp MMAs) + "
+                                "gradient reduce + Adam", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                "peak_source": tsrc, "algorithmic_flop_per_launch": flop, "kernel_ms": force_ms, "traffic": None,
+                                "valid_pairs": valid_pairs, "slots": rows * K,
+                                "note": "%d useful flop per VALID pair: forward value+tangent chains once, input-gradient chains, "
+                                        "weight gradients (the kernel's own forward recompute and the padded slots are not counted)"
+                                        % MLP_TRAIN_FLOP_PER_PAIR,
+                                "nlist_build_ms": build_ms, "nlist_build_frac": achieved / peak,
+                                "loss_after_timed_region": float(train["loss"].item()), "adam_steps": int(train["t"].item())}
         if world == 1 and full and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pos, lo, hi, r_cut, K)
     del ctx, nl, fe, vir, d_pos_all, d_shard, xch, graphs
@@ -655,6 +700,17 @@ def parity_leg(args, env, htf, ctx, pos, lo, hi, r_cut, K, g_lo, rows, row_lo, r
 
     f_err = rel(fe_c[a0:a0 + m].cpu().numpy(), fe_o)
     v_err = rel(vir_c[a0:a0 + m].cpu().numpy(), v6_o)
+    train_err = None
+    if args.model == "mlp-train":
+        mm = min(m, 256)
+        raw = torch.from_numpy(mlp_raw_parameters()).to(dev)
+        lab = (0.05 * fe_o[:mm]).astype(np.float32)
+        g_k, _, _ = ctx.mlp_train_grads(nl[a0:a0 + mm].contiguous(), raw, r_cut, torch.from_numpy(lab).to(dev))
+        _, g_ref, _ = oracle.pairwise_mlp_train_grads(nl_o[:mm], mlp_raw_parameters(), r_cut, lab)
+        g_k = g_k.cpu().numpy().astype(np.float64)
+        cuts = np.cumsum([0, 2048, 64, 4096, 64, 4096, 64, 64, 1])
+        train_err = max(float(np.abs(g_k[cuts[i]:cuts[i + 1]] - g_ref[cuts[i]:cuts[i + 1]]).max()
+                              / (np.sqrt(np.mean(g_ref[cuts[i]:cuts[i + 1]] ** 2)) + 1e-30)) for i in range(8))
     mlp_err = None
     if packed is not None:
         mm = min(m, 256)
@@ -685,6 +741,13 @@ def parity_leg(args, env, htf, ctx, pos, lo, hi, r_cut, K, g_lo, rows, row_lo, r
     if mlp_err is not None:
         out["mlp_force_max_err_over_rms"] = mlp_err
         out["mlp_tolerance"] = 1e-1
+    if train_err is not None:
+        t_ = torch.tensor([train_err], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        out["train_grad_max_err_over_block_rms"] = float(t_.item())
+        out["train_grad_tolerance"] = 1e-1
+        mlp_err = float(t_.item()) if mlp_err is None else max(mlp_err, float(t_.item()))
     out["ok"] = bool(out["nlist_multiset_bit_exact"] and out["rdf_slice_bit_exact"] and out["force_energy_max_rel_err"] <= 1e-5
                      and out["virial_max_rel_err"] <= 1e-5 and out["rdf_total"] == out["rdf_total_expected"]
                      and out["sum_force_over_sum_abs_force"] <= 1e-5 and (mlp_err is None or mlp_err < 1e-1))
@@ -700,6 +763,8 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     n = pos.shape[0]
     rows = row_hi - row_lo
     halo = world > 1 and args.exchange == "halo"
+    if args.model == "mlp-train":
+        return run_e2e_train(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi)
     if args.model == "mlp":
         model = htf.models.PairwiseMLPModel(K, r_cut=r_cut).to(dev)
     elif args.model == "eds":
@@ -775,20 +840,64 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
                       ("EDSCoordinationModel", "+energy") if args.model == "eds" else ("LJVirialModel", "+virial"))}
 
 
+def run_e2e_train(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row_lo, row_hi):
+    """Config 4 end to end: tfcompute in the reference's label / training mode (attach(train=True) +
+    set_reference_forces, htf/tensorflowcompute.py:265-282,346-370).  Every step the positions come from pinned host
+    memory, the half-step hook builds the neighbor tensor, takes the label forces and runs one fused train_on_batch;
+    the loss is read back into pinned host memory."""
+    n = pos.shape[0]
+    if world > 1:
+        return {"value": None, "unit": UNIT, "note": "the training e2e leg is single-GPU; the multi-GPU gradient all-reduce is in the "
+                                                      "device-resident leg", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    model = htf.models.PairwiseMLPModel(K, r_cut=r_cut, output_forces=False).to(dev)
+    model.compile("Adam", "MeanSquaredError")
+    system = htf.sim.System(pos, lo, hi, device=dev)
+    system.integrator = htf.sim.NVE(0.005)
+    tfc = htf.tfcompute(model)
+    tfc.attach(htf.sim.nlist_cell(system), r_cut=r_cut, train=True)
+    tfc.set_reference_forces(htf.sim.PairLJ(system, r_cut, K, scale=0.05))
+    h_pos = torch.from_numpy(pos.copy()).pin_memory()
+    h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def step(t):
+        system.positions.copy_(h_pos, non_blocking=True)
+        tfc.half_step(t)
+        h_loss.copy_(model.last_loss.reshape(1), non_blocking=True)
+
+    steps = max(3, min(args.steps, 10))
+    for t in range(3):
+        step(t)
+    torch.cuda.synchronize()
+    l_first = float(h_loss[0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        step(t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4), "d2h_bytes_per_step": 4,
+            "steps": steps, "ms_per_step": ms / steps, "loss_first": l_first, "loss_last": float(h_loss[0]),
+            "api": "htf.tfcompute(PairwiseMLPModel).attach(train=True) + set_reference_forces(PairLJ x 0.05): half_step -> "
+                   "build, labels, fused train_on_batch; pinned host positions in, loss out"}
+
+
 def cpu_baseline(args, pos, lo, hi, r_cut, K):
     """The CPU restatement (oracle/) timed on this box's host cores on a bounded sample of the workload."""
     import oracle
     oracle.build()
     oracle.set_threads(0)
     n = pos.shape[0]
-    rows = min(n, 32768 if args.model == "mlp" else 262144)
+    rows = min(n, 2048 if args.model == "mlp-train" else 32768 if args.model == "mlp" else 262144)
     a0 = (n - rows) // 2
-    raw = mlp_raw_parameters() if args.model == "mlp" else None
+    raw = mlp_raw_parameters() if args.model in ("mlp", "mlp-train") else None
     reps, t_tot = 0, 0.0
     while t_tot < 8.0 and reps < 6:
         t0 = time.perf_counter()
         nl, _, _ = oracle.nlist(pos, lo, hi, r_cut, K, a0, a0 + rows, cells=True, want_idx=False)
-        if raw is not None:
+        if args.model == "mlp-train":
+            cpu_train_step(oracle, nl, raw, r_cut)
+        elif raw is not None:
             oracle.pairwise_mlp(nl, raw, r_cut)
         else:
             oracle.lj(nl, virial=True)
@@ -799,6 +908,16 @@ def cpu_baseline(args, pos, lo, hi, r_cut, K):
     return {"value": rows * reps / t_tot, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
             "sample": "%d x a %d-row slab of the %d-particle system (cell binning of all particles included)" % (reps, rows, n),
             "host_cores": os.cpu_count()}
+
+
+def cpu_train_step(oracle, nl, raw, r_cut):
+    """One force-matching step on the CPU: labels 0.05 x LJ, float64 gradient sweep, Adam (oracle/)."""
+    import numpy as np
+    fe, _, _ = oracle.lj(nl, virial=False)
+    loss, g, _ = oracle.pairwise_mlp_train_grads(nl, raw, r_cut, 0.05 * fe)
+    z = np.zeros_like(raw, dtype=np.float32)
+    oracle.adam_step(raw, g, z, z, 1)
+    return loss
 
 
 def run_refbench(args):

@@ -385,11 +385,15 @@ class PairwiseMLPModel(SimModel):
             self._fused_adam = st
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         if n_total is None:
-            n_total = nl.shape[0]
-            if world > 1:
-                t_ = torch.tensor([n_total], dtype=torch.int64, device=raw.device)
-                dist.all_reduce(t_, group=group)
-                n_total = int(t_.item())
+            key = (int(nl.shape[0]), world)
+            if getattr(self, "_n_total_key", None) != key:          # one collective + host read per shard shape, then cached
+                n_total = nl.shape[0]
+                if world > 1:
+                    t_ = torch.tensor([n_total], dtype=torch.int64, device=raw.device)
+                    dist.all_reduce(t_, group=group)
+                    n_total = int(t_.item())
+                self._n_total_key, self._n_total = key, n_total
+            n_total = self._n_total
         grads, pred, loss = ctx.mlp_train_grads(nl, raw, self.r_cut, labels, n_total=n_total)
         if world > 1:
             packed = torch.cat([grads, loss])
@@ -398,6 +402,6 @@ class PairwiseMLPModel(SimModel):
         pg = self.optimizer.param_groups[0]
         ctx.adam_step(raw, grads, st[0], st[1], st[2], lr=pg["lr"], beta1=pg["betas"][0], beta2=pg["betas"][1], eps=pg["eps"])
         self.load_raw_parameters(raw)
-        self.last_grads, self.last_pred = grads, pred
+        self.last_grads, self.last_pred, self.last_loss = grads, pred, loss
         self.metrics[0].update_state(loss[0])
         return loss[0]

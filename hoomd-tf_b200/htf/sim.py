@@ -293,3 +293,26 @@ class ReferenceLJ:
         e = 0.5 * torch.where(mask, 4.0 * self.eps * (sr6 * sr6 - sr6), torch.zeros_like(r2)).sum(1)
         self.forces = torch.cat([f, e[:, None]], dim=1).float()
         return self.forces
+
+
+class PairLJ:
+    """hoomd.md.pair.lj(epsilon = sigma = 1, r_cut) stand-in for LARGE systems: the library's own nlist + LJ kernels
+    (HtfContext.lj_step), optionally scaled.  Used as the label force of online force matching (set_reference_forces,
+    BASELINE config 4) where the O(N^2) ``ReferenceLJ`` is out of reach."""
+
+    def __init__(self, system, r_cut, nneighbor_cutoff=64, scale=1.0):
+        from .context import HtfContext
+        self.system, self.r_cut, self.K, self.scale = system, float(r_cut), int(nneighbor_cutoff), float(scale)
+        self.ctx = HtfContext(max(system.N, 1), self.K, self.r_cut, device=system.device)
+        self.ctx.set_box(system.box.lo, system.box.hi)
+        self.name = "lj"
+        self.forces = None
+
+    def compute_forces(self, timestep=0):
+        s = self.system
+        if self.forces is None or self.forces.shape[0] != s.N:
+            self.forces = torch.empty((s.N, 4), dtype=torch.float32, device=s.device)
+        self.ctx.lj_step(s.positions, force_out=self.forces)
+        if self.scale != 1.0:
+            self.forces.mul_(self.scale)
+        return self.forces
