@@ -16,9 +16,10 @@
 // The predictions (dF, de) come from the inference kernel (mlp_force_kernel) run first; this kernel re-runs the
 // forward per tile -- activations never go to HBM.
 //
-// Implementation: warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 operands, fp32 accumulation).  A block of four
-// warps owns a tile of 64 neighbor slots; warp w runs the forward and backward CHAINS of slots 16w..16w+15 entirely in
-// registers (the accumulator fragment of one layer is the A fragment of the next), and owns rows 16w..16w+15 of every
+// Implementation: warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 operands, fp32 accumulation).  A block walks
+// chunks of 1024 neighbor slots, compacts each chunk's VALID slots (padding is about a third of a dense fluid's tensor
+// and would cost as many MMAs as real pairs) and tiles them 64 at a time.  A block of four warps owns a tile; warp w
+// runs the forward and backward CHAINS of slots 16w..16w+15 entirely in registers (the accumulator fragment of one layer is the A fragment of the next), and owns rows 16w..16w+15 of every
 // weight-gradient accumulator, which stay in registers across all tiles of the block.  The weight gradients contract
 // over the SLOT index, so their operands are transposed views of the activations: the chains leave h, h' and zb, zb'
 // in shared memory as [slot][feature] bf16 and the MMAs read them with ldmatrix.trans.  The bias gradient rides on a
@@ -60,7 +61,11 @@ constexpr int S_A2P = S_A2 + TR_TILE * LD64 * 2;
 constexpr int S_ZB = S_A2P + TR_TILE * LD64 * 2;     // zb, zb' of the layer being differentiated
 constexpr int S_ZBP = S_ZB + TR_TILE * LD64 * 2;
 constexpr int S_RED = S_ZBP + TR_TILE * LD64 * 2;    // fp32 [TR_WARPS][65]: w4 / b4 gradient partials of the warps
-constexpr int TR_SMEM = S_RED + TR_WARPS * 65 * 4;
+constexpr int TR_CHUNK = 1024;                       // slots per chunk: the valid ones are compacted before they are tiled
+constexpr int S_SEG = S_RED + TR_WARPS * 65 * 4 + 16;   // u16 [TR_CHUNK]: per-warp compacted slot offsets; then i32 [TR_WARPS] counts
+constexpr int S_LIST = S_SEG + TR_CHUNK * 2;         // u16 [TR_CHUNK]: the chunk's valid slots, in order
+constexpr int S_CNT = S_LIST + TR_CHUNK * 2;         // i32 [TR_WARPS]
+constexpr int TR_SMEM = S_CNT + TR_WARPS * 4;
 
 struct TrainParams {
     const float4 *nlist;       // [rows][K]
@@ -297,16 +302,51 @@ __global__ void __launch_bounds__(TR_THREADS, 2) mlp_train_kernel(const TrainPar
     for (int i = 0; i < 8; i++) gw4[i][0] = gw4[i][1] = 0.f;
 
     const long long slots = P.rows * P.K;
-    const long long ntiles = (slots + TR_TILE - 1) / TR_TILE;
+    const long long nchunks = (slots + TR_CHUNK - 1) / TR_CHUNK;
     const float gapf = P.rbf_high / 31.0f, inv_gap = 31.0f / P.rbf_high;
     const int row_lo = 16 * warp + g;                       // this lane's two slots inside the tile: row_lo, row_lo + 8
+    unsigned short *seg_s = reinterpret_cast<unsigned short *>(smem + S_SEG);
+    unsigned short *list_s = reinterpret_cast<unsigned short *>(smem + S_LIST);
+    int *cnt_s = reinterpret_cast<int *>(smem + S_CNT);
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+      // ---- compact the chunk's valid (non-padded) slots, order preserved: about a third of a dense fluid's slots are
+      //      padding, and a padded slot would cost exactly as many MMAs as a real pair ----
+      const long long base = chunk * TR_CHUNK;
+      {
+        int cnt = 0;
+#pragma unroll 1
+        for (int it = 0; it < TR_CHUNK / TR_THREADS; it++) {
+            const int off = warp * (TR_CHUNK / TR_WARPS) + it * 32 + lane;
+            const long long s = base + off;
+            bool valid = false;
+            if (s < slots) {
+                const float4 d = __ldg(P.nlist + s);
+                const float ax = d.x + 1e-7f, ay = d.y + 1e-7f, az = d.z + 1e-7f;
+                valid = sqrtf(ax * ax + ay * ay + az * az) > 3e-6f;
+            }
+            const unsigned m = __ballot_sync(HTF_FULL, valid);
+            if (valid) seg_s[warp * (TR_CHUNK / TR_WARPS) + cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)off;
+            cnt += __popc(m);
+        }
+        if (lane == 0) cnt_s[warp] = cnt;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; w++) woff += cnt_s[w];
+        for (int i = lane; i < cnt; i += 32) list_s[woff + i] = seg_s[warp * (TR_CHUNK / TR_WARPS) + i];
+        __syncthreads();
+      }
+      const int nvalid = cnt_s[0] + cnt_s[1] + cnt_s[2] + cnt_s[3];
+      const int ntiles = (nvalid + TR_TILE - 1) / TR_TILE;
+      __syncthreads();                                      // everyone has the counts before a later chunk rewrites them
+
+      for (int tile = 0; tile < ntiles; tile++) {
         // ---- the lane's two slots: geometry and loss weights ----
         float rr[2], gp[2], hw[2];
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            const long long s = tile * TR_TILE + row_lo + 8 * q;
+            const int li = tile * TR_TILE + row_lo + 8 * q;
+            const long long s = li < nvalid ? base + list_s[li] : slots;
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 df = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s < slots) {
@@ -381,6 +421,7 @@ __global__ void __launch_bounds__(TR_THREADS, 2) mlp_train_kernel(const TrainPar
         __syncthreads();
         weight_grad<32, LD32>(acc1, sb + S_ZB, sb + S_ZBP, sb + S_A0, sb + S_A0P, warp, lane);
         __syncthreads();                                                  // A0.. and ZB are rewritten by the next tile
+      }
     }
 
     // ---- write this block's partial gradient (plain stores: every element has one owner) ----
@@ -501,9 +542,9 @@ cudaError_t htf_launch_mlp_train(htf_ctx *ctx, const float4 *nlist, int64_t rows
     P.nlist = nlist; P.rows = rows; P.K = K; P.raw = raw; P.pred = pred; P.labels = labels; P.rbf_high = rbf_high;
     P.inv_2n = (float)(1.0 / (2.0 * (double)n_total)); P.inv_4n = (float)(1.0 / (4.0 * (double)n_total));
     P.partial = partial;
-    const long long ntiles = (rows * K + TR_TILE - 1) / TR_TILE;
+    const long long nchunks = (rows * K + TR_CHUNK - 1) / TR_CHUNK;
     int grid = 2 * ctx->sm_count;
-    if ((long long)grid > ntiles) grid = (int)(ntiles > 0 ? ntiles : 1);
+    if ((long long)grid > nchunks) grid = (int)(nchunks > 0 ? nchunks : 1);
     mlp_train_kernel<<<grid, TR_THREADS, TR_SMEM, st>>>(P);
     mlp_grad_reduce_kernel<<<(T_COUNT + 255) / 256, 256, 0, st>>>(partial, grid, grads);
     ctx->launches += 2;

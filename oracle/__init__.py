@@ -301,8 +301,9 @@ def adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
     defaults lr 1e-3, epsilon 1e-7): t is the step count AFTER the increment.  fp32, returns (params, m, v)."""
     f = np.float32
     params, grads, m, v = (np.asarray(x, dtype=f) for x in (params, grads, m, v))
-    m = (f(beta1) * m + f(1.0 - beta1) * grads).astype(f)
-    v = (f(beta2) * v + f(1.0 - beta2) * grads * grads).astype(f)
+    # Keras holds beta_1 / beta_2 as float32 tensors: 1 - beta is the float32 difference (1 - 0.999f = 0.00100004673)
+    m = (f(beta1) * m + (f(1.0) - f(beta1)) * grads).astype(f)
+    v = (f(beta2) * v + (f(1.0) - f(beta2)) * grads * grads).astype(f)
     lr_t = f(lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
     params = (params - lr_t * m / (np.sqrt(v) + f(eps))).astype(f)
     return params, m, v
