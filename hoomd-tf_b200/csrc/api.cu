@@ -352,7 +352,7 @@ void htf_destroy(htf_ctx *ctx)
     void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx, ctx->d_scattered,
                     ctx->d_spos, ctx->d_nlist_scratch, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
                     ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums, ctx->d_train_packed, ctx->d_train_pred,
-                    ctx->d_train_partial, ctx->d_train_loss_partial};
+                    ctx->d_train_partial, ctx->d_train_loss_partial, ctx->d_mlp_pairs, ctx->d_mlp_blk};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
         if (!ptrs[i]) continue;
         cudaError_t e = cudaFree(ptrs[i]);

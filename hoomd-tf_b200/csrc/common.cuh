@@ -81,6 +81,11 @@ struct htf_ctx {
     int pipe_pass_bps;            // blocks per SM of a slab's pair pass
     int pipe_build_streams;       // 1 or 2
     HtfComm *comm;                // peer-memory exchange state (comm.cu), nullptr until htf_comm_create
+    // compacted valid pairs of the MLP inference pass (one more copy of the tensor) and its block offsets
+    float4 *d_mlp_pairs;
+    int64_t mlp_pairs_cap;
+    int *d_mlp_blk;
+    int mlp_blk_cap;
     // scratch of the MLP training step: packed bf16 parameters, predictions, per-block partial gradients / loss sums
     unsigned char *d_train_packed;
     float *d_train_pred, *d_train_partial;

@@ -596,6 +596,22 @@ def test_pairwise_mlp_tensor_core_vs_fp32():
     rms_f = np.sqrt(np.mean((f[:, :3] - g[:, :3]) ** 2)) / scale_f
     print("pairwise MLP: rms dF / rms F = %.3e" % rms_f)
     assert err_f < MLP_TOL_MAX and err_e < MLP_TOL_MAX and rms_f < MLP_TOL_RMS
+    # the compaction pre-pass (default above 2^20 slots; forced here): same numbers up to the order of the fp32 row sums
+    import os
+    os.environ["HTF_MLP_COMPACT"] = "1"
+    try:
+        compacted = model([nl, None], False)[0]
+        sparse = nl.clone()
+        sparse[::3, 5:] = 0.0                                  # rows with few pairs, all-padding stretches, ragged segments
+        sparse[7] = 0.0                                        # an empty row
+        c_sp = model([sparse, None], False)[0]
+        os.environ["HTF_MLP_COMPACT"] = "0"
+        p_sp = model([sparse, None], False)[0]
+    finally:
+        os.environ.pop("HTF_MLP_COMPACT", None)
+    torch.cuda.synchronize()
+    assert float((compacted - fused).abs().max()) <= 1e-4 * float(fused.abs().max())
+    assert float((c_sp - p_sp).abs().max()) <= 1e-4 * float(p_sp.abs().max()) and float(c_sp[7].abs().sum()) == 0.0
     # other K (generic row reduction path) and a ragged tile count
     ctx2 = _ctx(pos.shape[0], 40, 2.0, lo, hi)
     nl2 = ctx2.build_nlist(torch.from_numpy(pos).cuda())[:1001].contiguous()
