@@ -267,6 +267,42 @@ __global__ void __launch_bounds__(256) select_count2_kernel(const float4 *__rest
         for (int w = 0; w < 8; w++) t += wsum[8 * threadIdx.x + w];
         block_cnt[threadIdx.x * nb + blockIdx.x] = t;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 2) block_cnt[2 * nb] = 0;      // the extra entry that makes off[2 nb] exist
+}
+
+// exclusive scan of a SMALL array (n <= 1024 * SCAN1_ITEMS) by one block, in[] -> out[], grand total -> *total:
+// one launch instead of three for the halo compaction's per-block counts
+constexpr int SCAN1_ITEMS = 16;
+__global__ void __launch_bounds__(1024) scan_one_block_kernel(const int *__restrict__ in, int n, int *__restrict__ out,
+                                                              int *__restrict__ total)
+{
+    __shared__ int wtot[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int per = (n + 1023) / 1024;                        // contiguous items per thread
+    const int b = threadIdx.x * per;
+    int v[SCAN1_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++) {
+        v[k] = (k < per && b + k < n) ? in[b + k] : 0;
+        s += v[k];
+    }
+    int incl = warp_incl_scan(s, lane);
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const int t = wtot[q];
+        if (q < w) base += t;
+        tot += t;
+    }
+    int run = base + incl - s;
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; k++) {
+        if (k < per && b + k < n) out[b + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) *total = tot;
 }
 
 // block_off = exclusive scan of block_cnt[2 nb]; *total = its grand total.  Threads past n only pad: every entry of
@@ -389,17 +425,25 @@ cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64,
     int *cnt = ctx->d_sel_cnt, *off = ctx->d_sel_off, *sums = ctx->d_sel_sums;
     if (nb > 0) select_count2_kernel<<<nb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, cnt);
     const int m = 2 * nb + 1;                                   // one extra (zero) entry so that off[2 nb] exists
-    cudaError_t e = cudaMemsetAsync(cnt + 2 * nb, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
+    if (nb == 0) {
+        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
     const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     int *total = sums + ntiles + 1;
-    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums);
-    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, ntiles, total);
-    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums, off);
+    if (m <= 1024 * SCAN1_ITEMS) {
+        scan_one_block_kernel<<<1, 1024, 0, st>>>(cnt, m, off, total);
+        ctx->launches += 1;
+    } else {
+        scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums);
+        scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, ntiles, total);
+        scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(cnt, m, sums, off);
+        ctx->launches += 3;
+    }
     const int gb = max(nb, (cap + 255) / 256);
     select_scatter2_kernel<<<gb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, off, total, out_lo, out_hi, cap, d_counts,
                                                d_overflow, dst);
-    ctx->launches += 5;
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 

@@ -6,9 +6,10 @@
 // that its peers map with cudaIpcOpenMemHandle.  The per-step traffic never touches the host and needs no NCCL:
 //
 //   halo exchange   the stable compaction of the two slab faces (select_scatter2_kernel, cells.cu) writes the faces
-//                   STRAIGHT INTO the neighbours' windows (fused pack + send); a one-thread kernel then publishes the
-//                   epoch to the neighbours' flags (release, system scope); the gather kernel waits for both own flags
-//                   (acquire) and copies the received faces behind the rank's own rows, where the binning expects them.
+//                   STRAIGHT INTO the neighbours' windows (fused pack + send); the gather kernel then publishes the
+//                   epoch to the neighbours' flags (release, system scope), waits for both own flags (acquire) and
+//                   copies the received faces behind the rank's own rows, where the binning expects them.
+//                   Four launches in all: count, one-block scan, scatter-to-peer, signal + wait + gather.
 //   all-reduce      every rank stores its (small) vector into every peer's window, publishes the epoch, waits for all
 //                   contributions and sums them in rank order -- the same bits on every rank, int64 or fp64.
 //
@@ -66,21 +67,20 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
     return true;
 }
 
-// after the pack kernels (stream order: the faces are in the neighbours' windows): publish the epoch
-__global__ void halo_signal_kernel(CommHeader *own, unsigned long long *flag_at_prev, unsigned long long *flag_at_next)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const unsigned long long e = own->dst.epoch;
-    __threadfence_system();
-    st_release_sys(flag_at_prev, e + 1);              // "the face from your next rank is complete"
-    st_release_sys(flag_at_next, e + 1);              // "the face from your previous rank is complete"
-}
-
-// wait for both faces of this epoch, then copy them behind the rank's own rows: local[n_own + {0, cap} ...]
-__global__ void __launch_bounds__(256) halo_gather_kernel(CommHeader *own, const float4 *recv /* [2 parity][2 side][cap] */,
+// After the pack kernel (stream order: this rank's faces are in the neighbours' windows): block 0 publishes the epoch
+// to both neighbours; every block then waits for both faces of this epoch and copies its share of them behind the
+// rank's own rows: local[n_own + {0, cap} ...]
+__global__ void __launch_bounds__(256) halo_gather_kernel(CommHeader *own, unsigned long long *flag_at_prev,
+                                                          unsigned long long *flag_at_next,
+                                                          const float4 *recv /* [2 parity][2 side][cap] */,
                                                           float4 *local_halo /* [2][cap] */, int cap)
 {
     const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&own->dst.epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(flag_at_prev, e + 1);          // "the face from your next rank is complete"
+        st_release_sys(flag_at_next, e + 1);          // "the face from your previous rank is complete"
+    }
     if (threadIdx.x == 0) {
         const bool ok = wait_flag(&own->halo_flag[0], e + 1) && wait_flag(&own->halo_flag[1], e + 1);
         if (!ok) atomicExch(&own->status, 1);
@@ -284,15 +284,14 @@ int htf_comm_exchange_halo(htf_ctx *ctx, float *d_local, int64_t n_own, int axis
         // 1. fused pack + send: both faces, stable order, sentinel padded, written into the neighbours' windows
         cudaError_t e = htf_launch_select_pair(ctx, local, n_own, axis, threshold_lo, threshold_hi, nullptr, nullptr, (int)c->cap,
                                                nullptr, d_overflow, st, &own->dst);
-        // 2. publish the epoch to both neighbours
+        // 2. publish the epoch to both neighbours, wait for both of their faces, copy them behind the own rows
         if (e == cudaSuccess) {
-            halo_signal_kernel<<<1, 32, 0, st>>>(own, &reinterpret_cast<CommHeader *>(c->peer[prev])->halo_flag[0],
-                                                 &reinterpret_cast<CommHeader *>(c->peer[next])->halo_flag[1]);
-            // 3. wait for both faces, copy them behind the own rows
             const int blocks = (int)((2 * c->cap + 255) / 256 < 64 ? (2 * c->cap + 255) / 256 : 64);
-            halo_gather_kernel<<<blocks, 256, 0, st>>>(own, reinterpret_cast<const float4 *>(c->window + c->off_halo),
+            halo_gather_kernel<<<blocks, 256, 0, st>>>(own, &reinterpret_cast<CommHeader *>(c->peer[prev])->halo_flag[0],
+                                                       &reinterpret_cast<CommHeader *>(c->peer[next])->halo_flag[1],
+                                                       reinterpret_cast<const float4 *>(c->window + c->off_halo),
                                                        local + n_own, (int)c->cap);
-            ctx->launches += 2;
+            ctx->launches += 1;
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) { set_comm_err(ctx, "htf_comm_exchange_halo", e); rc = HTF_ECUDA; }
