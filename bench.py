@@ -424,7 +424,10 @@ def measure(args, env, scaling, full):
             # one online force-matching step: gradient of MSE(model forces+energy, labels), summed over ranks, Adam
             ctx.mlp_train_grads(nl, train["raw"], r_cut, train["labels"], n_total=n, grads=train["g"], pred=fe, loss=train["loss"])
             if world > 1:
-                dist.all_reduce(train["g"])
+                if p2p:
+                    ctx.comm_allreduce(train["g"])                    # ~10.5k weight gradients through the peer mailboxes
+                else:
+                    dist.all_reduce(train["g"])
             ctx.adam_step(train["raw"], train["g"], train["m"], train["v"], train["t"], lr=1e-3)
         elif eds_model is not None:
             eds_model.compute(nl, None, None)                         # fused LJ + CV + RDF pass, all-reduces, EDS update, bias
@@ -473,7 +476,7 @@ def measure(args, env, scaling, full):
     graphs = None
     launches_per_step = None
     eager_force = eds_model is not None or (bins is not None and world > 1 and not p2p) or \
-        (train is not None and world > 1)                          # host-side collectives / metric updates
+        (train is not None and world > 1 and not p2p)              # host-side collectives / metric updates
     if not skin and not args.no_graph and (world == 1 or halo):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

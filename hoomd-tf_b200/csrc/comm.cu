@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int COMM_MAX_WORLD = 16;
-constexpr int COMM_AR_MAX = 2048;                     // 8-byte words per all-reduce
+constexpr int COMM_AR_MAX = 16384;                    // values per all-reduce (mailbox slots are 8 bytes wide)
 constexpr unsigned long long COMM_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 // header of a window; peers write the flags and the data areas, the owner reads them
@@ -300,7 +300,7 @@ int htf_comm_exchange_halo(htf_ctx *ctx, float *d_local, int64_t n_own, int axis
     return rc;
 }
 
-static int comm_allreduce(htf_ctx *ctx, void *d_values, int count, bool is_f64, void *stream)
+static int comm_allreduce(htf_ctx *ctx, void *d_values, int count, int kind /* 0 i64, 1 f64, 2 f32 */, void *stream)
 {
     if (!ctx) return HTF_EINVAL;
     HtfComm *c = ctx->comm;
@@ -311,7 +311,12 @@ static int comm_allreduce(htf_ctx *ctx, void *d_values, int count, bool is_f64, 
     cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     CommHeader *own = reinterpret_cast<CommHeader *>(c->window);
-    if (is_f64) {
+    if (kind == 2) {
+        ar_push_kernel<float><<<c->world, 256, 0, st>>>(own, static_cast<const float *>(d_values), count, c->rank,
+                                                        reinterpret_cast<float *const *>(c->d_peer_data), c->d_peer_flag);
+        ar_sum_kernel<float><<<1, 256, 0, st>>>(own, reinterpret_cast<const float *>(c->window + c->off_ar),
+                                                static_cast<float *>(d_values), count, c->world);
+    } else if (kind == 1) {
         ar_push_kernel<double><<<c->world, 256, 0, st>>>(own, static_cast<const double *>(d_values), count, c->rank,
                                                          reinterpret_cast<double *const *>(c->d_peer_data), c->d_peer_flag);
         ar_sum_kernel<double><<<1, 256, 0, st>>>(own, reinterpret_cast<const double *>(c->window + c->off_ar),
@@ -331,12 +336,17 @@ static int comm_allreduce(htf_ctx *ctx, void *d_values, int count, bool is_f64, 
 
 int htf_comm_allreduce_i64(htf_ctx *ctx, int64_t *d_values, int count, void *stream)
 {
-    return comm_allreduce(ctx, d_values, count, false, stream);
+    return comm_allreduce(ctx, d_values, count, 0, stream);
 }
 
 int htf_comm_allreduce_f64(htf_ctx *ctx, double *d_values, int count, void *stream)
 {
-    return comm_allreduce(ctx, d_values, count, true, stream);
+    return comm_allreduce(ctx, d_values, count, 1, stream);
+}
+
+int htf_comm_allreduce_f32(htf_ctx *ctx, float *d_values, int count, void *stream)
+{
+    return comm_allreduce(ctx, d_values, count, 2, stream);
 }
 
 int htf_comm_status(htf_ctx *ctx, int32_t *h_status, void *stream)

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
 FLAG_DETERMINISTIC = 1
@@ -57,6 +57,7 @@ SYMBOLS = {
     "htf_comm_exchange_halo": (_i32, [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
     "htf_comm_allreduce_i64": (_i32, [_vp, _vp, _i32, _vp]),
     "htf_comm_allreduce_f64": (_i32, [_vp, _vp, _i32, _vp]),
+    "htf_comm_allreduce_f32": (_i32, [_vp, _vp, _i32, _vp]),
     "htf_comm_status": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32), _vp]),
     "htf_comm_destroy": (_i32, [_vp]),
     "htf_launch_count": (_i64, [_vp]),

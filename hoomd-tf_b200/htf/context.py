@@ -398,10 +398,12 @@ class HtfContext:
         return local
 
     def comm_allreduce(self, values):
-        """In-place sum over all ranks of a small int64 or float64 CUDA vector (<= 2048 values)."""
-        if not values.is_cuda or not values.is_contiguous() or values.dtype not in (torch.int64, torch.float64):
-            raise ValueError("comm_allreduce takes a contiguous int64 or float64 CUDA tensor")
-        fn = self.lib.htf_comm_allreduce_i64 if values.dtype == torch.int64 else self.lib.htf_comm_allreduce_f64
+        """In-place sum over all ranks of a small int64 / float64 / float32 CUDA vector (<= 16384 values)."""
+        fns = {torch.int64: self.lib.htf_comm_allreduce_i64, torch.float64: self.lib.htf_comm_allreduce_f64,
+               torch.float32: self.lib.htf_comm_allreduce_f32}
+        if not values.is_cuda or not values.is_contiguous() or values.dtype not in fns:
+            raise ValueError("comm_allreduce takes a contiguous int64, float64 or float32 CUDA tensor")
+        fn = fns[values.dtype]
         self._ck(fn(self._h, _ptr(values), int(values.numel()), self._stream()))
         return values
 

@@ -56,7 +56,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 16
+#define HTF_ABI_VERSION 17
 int htf_abi_version(void);
 
 /*
@@ -349,9 +349,9 @@ int htf_adam_step(htf_ctx *ctx, float *d_params, const float *d_grads, float *d_
  *                     d_local[n_own + halo_capacity .. n_own + 2 halo_capacity) (from the previous rank); d_local
  *                     is then what htf_bin_particles takes (with htf_set_roi rejecting the sentinels).
  *                     d_overflow (nullable) receives max(count + 1) when a face exceeds the capacity.
- *   htf_comm_allreduce_i64 / _f64   in-place sum over all ranks of count <= 2048 values (the RDF histogram, the CV
- *                     sum and particle count of EDS): contributions are summed in rank order, so every rank gets
- *                     the same bits.
+ *   htf_comm_allreduce_i64 / _f64 / _f32   in-place sum over all ranks of count <= 16384 values (the RDF histogram,
+ *                     the CV sum and particle count of EDS, the ~10.5k weight gradients of the training step):
+ *                     contributions are summed in rank order, so every rank gets the same bits.
  *   htf_comm_status   0, or != 0 when a wait gave up after 20 s (a peer died); synchronises the stream.
  * All exchange calls are stream-ordered, asynchronous and CUDA-graph capturable (epochs live in device memory).
  */
@@ -362,6 +362,7 @@ int htf_comm_exchange_halo(htf_ctx *ctx, float *d_local, int64_t n_own, int axis
                            int32_t *d_overflow, void *stream);
 int htf_comm_allreduce_i64(htf_ctx *ctx, int64_t *d_values, int count, void *stream);
 int htf_comm_allreduce_f64(htf_ctx *ctx, double *d_values, int count, void *stream);
+int htf_comm_allreduce_f32(htf_ctx *ctx, float *d_values, int count, void *stream);
 int htf_comm_status(htf_ctx *ctx, int32_t *h_status, void *stream);
 int htf_comm_destroy(htf_ctx *ctx);
 

@@ -86,7 +86,13 @@ def _worker(rank, world, port, out_dir):
             ctx.comm_allreduce(bins)
             v = torch.tensor([0.1 * (rank + 1), 1e-17 * (rank + 1), float(it)], dtype=torch.float64, device="cuda")
             ctx.comm_allreduce(v)
+            gvec = torch.arange(10497, dtype=torch.float32, device="cuda") * (rank + 1) * 1e-3   # weight-gradient sized
+            ctx.comm_allreduce(gvec)
             torch.cuda.synchronize()
+            want_g = np.zeros(10497, dtype=np.float32)
+            for r in range(world):
+                want_g = want_g + (np.arange(10497, dtype=np.float32) * np.float32(r + 1) * np.float32(1e-3))
+            assert np.array_equal(gvec.cpu().numpy(), want_g)
             assert np.array_equal(bins.cpu().numpy(), want_bins)
             want_v = np.zeros(3)
             for r in range(world):

@@ -818,7 +818,7 @@ def test_adam_step_kernel_matches_keras_formula(oracle_mod):
         p, m, v = oracle_mod.adam_step(p, g, m, v, t)
         ctx.adam_step(dp, torch.from_numpy(g).cuda(), dm, dv, dt)
         torch.cuda.synchronize()
-        np.testing.assert_allclose(dp.cpu().numpy(), p, rtol=0, atol=3e-7)
+        np.testing.assert_allclose(dp.cpu().numpy(), p, rtol=3e-7, atol=1e-7)          # a couple of ulps of the parameter
         # the kernel contracts beta * m + (1 - beta) * g into an FMA: one rounding less than the numpy restatement
         np.testing.assert_allclose(dm.cpu().numpy(), m, rtol=1e-6, atol=5e-8)
         np.testing.assert_allclose(dv.cpu().numpy(), v, rtol=2e-6, atol=1e-9)
