@@ -94,10 +94,9 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
             row = o - p.map_row_lo;
         }
         const float4 *rp = p.nlist + (active ? row : 0) * K;
-        const float2 zero2 = make_float2(0.f, 0.f);
-        float2 fx2 = zero2, fy2 = zero2, fz2 = zero2, en2 = zero2;
-        float2 vxx2 = zero2, vxy2 = zero2, vxz2 = zero2, vyy2 = zero2, vyz2 = zero2, vzz2 = zero2;
-        float2 cn2 = zero2, gx2 = zero2, gy2 = zero2, gz2 = zero2;
+        float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+        float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
+        float cn = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
         bool row_in_rdf = false;
         if (RDF) {
             row_in_rdf = active;
@@ -110,60 +109,44 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                 const int s = s0 + u * LPR;
                 d[u] = (active && s < K) ? ld_stream(rp + s) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float r_guess[LJ_UNROLL];                    // RDF: any r within a fraction of a bin of the exact one
 #pragma unroll
-            for (int u = 0; u < LJ_UNROLL; u++) r_guess[u] = 0.f;
-            if (FORCES) {
-                // two slots per instruction on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2): the pass is
-                // issue bound next to HBM bound, and the LJ / virial / CV arithmetic is two thirds of its instructions.
-                // Padded slots (rt <= 3e-6) run the same code with a zero 1/r, so there is no branch per slot.
-#pragma unroll
-                for (int u = 0; u < LJ_UNROLL; u += 2) {
-                    const float2 dx = make_float2(d[u].x, d[u + 1].x), dy = make_float2(d[u].y, d[u + 1].y),
-                                 dz = make_float2(d[u].z, d[u + 1].z);
-                    const float2 eps = make_float2(1e-7f, 1e-7f);
-                    const float2 ax = __fadd2_rn(dx, eps), ay = __fadd2_rn(dy, eps), az = __fadd2_rn(dz, eps);
-                    const float2 rt2 = __ffma2_rn(az, az, __ffma2_rn(ay, ay, __fmul2_rn(ax, ax)));
-                    const float rt0 = sqrtf(rt2.x), rt1 = sqrtf(rt2.y);
-                    r_guess[u] = rt0; r_guess[u + 1] = rt1;
-                    // 1/(rt + 3e-6) (nlist_rinv) is IEEE-rounded: its error is amplified 13x by s^13;
-                    // the 1/rt of the gradient enters linearly, the 2-ulp MUFU.RSQ is enough there
-                    const float2 si = make_float2(rt0 > 3e-6f ? 1.0f / (rt0 + 3e-6f) : 0.f, rt1 > 3e-6f ? 1.0f / (rt1 + 3e-6f) : 0.f);
-                    const float2 irt = make_float2(rsqrtf(rt2.x), rsqrtf(rt2.y));
-                    const float2 s2 = __fmul2_rn(si, si);
-                    const float2 s6 = __fmul2_rn(__fmul2_rn(s2, s2), s2);
-                    en2 = __ffma2_rn(make_float2(2.0f, 2.0f), __ffma2_rn(s6, s6, make_float2(-s6.x, -s6.y)), en2);
-                    // (24 s^7 - 48 s^13) / rt = s6 si irt (24 - 48 s6)
-                    const float2 coef = __fmul2_rn(__fmul2_rn(__fmul2_rn(s6, si), irt),
-                                                   __ffma2_rn(make_float2(-48.0f, -48.0f), s6, make_float2(24.0f, 24.0f)));
-                    fx2 = __ffma2_rn(coef, ax, fx2); fy2 = __ffma2_rn(coef, ay, fy2); fz2 = __ffma2_rn(coef, az, fz2);
-                    if (VIRIAL) {
-                        // |F_pair| / (2 |d|) = |coef| |a| / (2 |d|); |a| and |d| differ by the 1e-7 offset of
-                        // safe_norm only (< 2.2e-7 relative for r >= 0.8), far inside the 1e-5 contract
-                        const float2 w = make_float2(0.5f * fabsf(coef.x), 0.5f * fabsf(coef.y));
-                        const float2 wx = __fmul2_rn(w, dx), wy = __fmul2_rn(w, dy), wz = __fmul2_rn(w, dz);
-                        vxx2 = __ffma2_rn(wx, dx, vxx2); vxy2 = __ffma2_rn(wx, dy, vxy2); vxz2 = __ffma2_rn(wx, dz, vxz2);
-                        vyy2 = __ffma2_rn(wy, dy, vyy2); vyz2 = __ffma2_rn(wy, dz, vyz2); vzz2 = __ffma2_rn(wz, dz, vzz2);
-                    }
-                    if (CV) {
-                        // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a   (zero for padded slots)
-                        const float2 ir0 = make_float2(p.cv_inv_r0, p.cv_inv_r0);
-                        const float2 x = __fmul2_rn(make_float2(rt0, rt1), ir0), x2 = __fmul2_rn(x, x);
-                        const float2 x6 = __fmul2_rn(__fmul2_rn(x2, x2), x2);
-                        const float2 den = __fadd2_rn(x6, make_float2(1.0f, 1.0f));
-                        // 1-ulp reciprocal: 1e-7 relative on s
-                        const float2 sw = make_float2(rt0 > 3e-6f ? __fdividef(1.0f, den.x) : 0.f, rt1 > 3e-6f ? __fdividef(1.0f, den.y) : 0.f);
-                        cn2 = __fadd2_rn(cn2, sw);
-                        const float2 swi = __fmul2_rn(sw, irt);
-                        const float2 cg = __fmul2_rn(__fmul2_rn(make_float2(-6.0f, -6.0f), x6), __fmul2_rn(swi, swi));
-                        gx2 = __ffma2_rn(cg, ax, gx2); gy2 = __ffma2_rn(cg, ay, gy2); gz2 = __ffma2_rn(cg, az, gz2);
+            for (int u = 0; u < LJ_UNROLL; u++) {
+                const float dx = d[u].x, dy = d[u].y, dz = d[u].z;
+                float r_guess = 0.f;                     // RDF: any r within a fraction of a bin of the exact one
+                if (FORCES) {
+                    const float ax = dx + 1e-7f, ay = dy + 1e-7f, az = dz + 1e-7f;
+                    const float rt2 = ax * ax + ay * ay + az * az;
+                    const float rt = sqrtf(rt2);
+                    r_guess = rt;
+                    if (rt > 3e-6f) {
+                        // 1/(rt + 3e-6) (nlist_rinv) is IEEE-rounded: its error is amplified 13x by s^13;
+                        // the 1/rt of the gradient enters linearly, the 2-ulp MUFU.RSQ is enough there
+                        const float si = 1.0f / (rt + 3e-6f);
+                        const float irt = rsqrtf(rt2);
+                        const float s2 = si * si, s6 = s2 * s2 * s2;
+                        en += 2.0f * (s6 * s6 - s6);
+                        const float coef = (24.0f * s6 * si - 48.0f * s6 * s6 * si) * irt;
+                        const float px = coef * ax, py = coef * ay, pz = coef * az;
+                        fx += px; fy += py; fz += pz;
+                        if (VIRIAL) {
+                            // |F_pair| / (2 |d|) = |coef| |a| / (2 |d|); |a| and |d| differ by the 1e-7 offset of
+                            // safe_norm only (< 2.2e-7 relative for r >= 0.8), far inside the 1e-5 contract
+                            const float w = 0.5f * fabsf(coef);
+                            const float wx = w * dx, wy = w * dy, wz = w * dz;
+                            vxx += wx * dx; vxy += wx * dy; vxz += wx * dz;
+                            vyy += wy * dy; vyz += wy * dz; vzz += wz * dz;
+                        }
+                        if (CV) {
+                            // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a
+                            const float x = rt * p.cv_inv_r0, x2 = x * x, x6 = x2 * x2 * x2;
+                            const float sw = __fdividef(1.0f, 1.0f + x6);      // 1-ulp reciprocal: 1e-7 relative on s
+                            cn += sw;
+                            const float cg = -6.0f * x6 * sw * sw * irt * irt;
+                            gx += cg * ax; gy += cg * ay; gz += cg * az;
+                        }
                     }
                 }
-            }
-            if (RDF) {
-#pragma unroll
-                for (int u = 0; u < LJ_UNROLL; u++) {
-                    const float dx = d[u].x, dy = d[u].y, dz = d[u].z;
+                if (RDF) {
                     const int s = s0 + u * LPR;
                     if (row_in_rdf && s < K) {
                         float m = 1.0f;
@@ -173,9 +156,8 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                         // first guess from an approximate r (off by far less than a bin), then the exact threshold
                         // table decides: thr[g] <= q < thr[g+1], thr[0] = 0, thr[nb] = +inf, so one step each way is
                         // enough and the clamps make both look-ups safe
-                        float rg = r_guess[u];
-                        if (!FORCES) rg = q * rsqrtf(fmaxf(q, 1e-30f));
-                        int g = (int)((rg - p.r_lo) * p.inv_step);
+                        if (!FORCES) r_guess = q * rsqrtf(fmaxf(q, 1e-30f));
+                        int g = (int)((r_guess - p.r_lo) * p.inv_step);
                         g = max(0, min(p.nb - 1, g));
                         if (p.type_j >= 0 && m == 0.0f) g = 0;              // masked entry: q = 0 whatever r was
                         g += (q >= s_thr[g + 1]) ? 1 : 0;
@@ -186,11 +168,6 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                 }
             }
         }
-        // the two halves of the packed accumulators (even / odd slots of this lane)
-        float fx = fx2.x + fx2.y, fy = fy2.x + fy2.y, fz = fz2.x + fz2.y, en = en2.x + en2.y;
-        float vxx = vxx2.x + vxx2.y, vxy = vxy2.x + vxy2.y, vxz = vxz2.x + vxz2.y, vyy = vyy2.x + vyy2.y,
-              vyz = vyz2.x + vyz2.y, vzz = vzz2.x + vzz2.y;
-        float cn = cn2.x + cn2.y, gx = gx2.x + gx2.y, gy = gy2.x + gy2.y, gz = gz2.x + gz2.y;
         if (FORCES) {
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) {
