@@ -75,7 +75,7 @@ def parse():
                          "peers can be mapped")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-batches", type=int, default=8,
+    ap.add_argument("--e2e-batches", type=int, default=4,
                     help="row batches per step in the end-to-end leg (device->host copy of batch b overlaps batch b+1)")
     return ap.parse_args()
 
