@@ -303,12 +303,14 @@ def run_b200(args):
         raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    globals()["_NUMA_NOTE"] = numa
     dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    env = dict(world=world, rank=rank, local=local, dev=dev, dist=dist)
+    env = dict(world=world, rank=rank, local=local, dev=dev, dist=dist, numa=numa)
 
     line = measure(args, env, "weak", full=True)           # the headline record: one config-size slab per GPU
     if world > 1 and args.scaling in ("both", "strong") and args.skin <= 0.0:
@@ -324,6 +326,21 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end leg
+    (allocated afterwards, first touch) and the copy submissions sit on the GPU's own NUMA node / PCIe root.  torchrun
+    does not bind ranks.  Returns a short description, or None when NVML is not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "NVML ideal CPU affinity: %d CPUs (%d..%d)" % (len(cpus), cpus[0], cpus[-1])
+    except Exception as ex:                                  # noqa: BLE001 -- optional tuning, reported in the record
+        return "not bound (%s)" % type(ex).__name__
 
 
 def measure(args, env, scaling, full):
@@ -836,7 +853,7 @@ def run_e2e(args, htf, torch, dist, world, rank, dev, pos, lo, hi, r_cut, K, row
     ok = bool(torch.equal(h_f, tfc._forces[out_lo:out_hi].cpu()))
     return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_pos.numel() * 4),
             "d2h_bytes_per_step": int(h_f.numel() * 4 + (h_v.numel() * 4 if h_v is not None else 0)), "steps": steps,
-            "ms_per_step": ms / steps, "row_batches": max(nbatch, 1), "host_result_matches_device": ok,
+            "ms_per_step": ms / steps, "row_batches": max(nbatch, 1), "host_result_matches_device": ok, "cpu_binding": globals().get("_NUMA_NOTE"),
             "api": "htf.tfcompute(%s).compute_forces, pinned host positions in, forces%s mirrored to pinned host memory "
                    "batch by batch (set_host_outputs)"
                    % (("PairwiseMLPModel", "+energy") if args.model == "mlp" else
