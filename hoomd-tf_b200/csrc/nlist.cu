@@ -31,6 +31,7 @@
 #include "common.cuh"
 
 #include <math_constants.h>
+#include <cstdlib>
 #ifdef HTF_DEBUG_FLAGS
 #include <cstdio>
 #include <vector>
@@ -63,6 +64,7 @@ struct NlistParams {
     int *flag_count;            // tiles flagged by this launch's tile kernel (nullptr: unknown, always scan)
     int *flag_count_next;       // the other parity's counter, zeroed by the per-cell kernel for the next launch
     int use_flags;       // per-cell kernel: process only cells of flagged tiles
+    int tile_axis;       // 0: flagged tiles run along x (first tile kernel), 1: along y (second form)
     float4 *out;
     int *idx_out;
     int *count_out;
@@ -634,15 +636,24 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
         if (blockIdx.x == 0 && threadIdx.x == 0) *p.flag_count_next = 0;
         if (nflag == 0) return;
     }
-    const int nx = p.g.n[0], tiles_x = (nx + TILE - 1) / TILE;
-    const int per_layer = tiles_x * p.g.n[1];
+    const int nx = p.g.n[0], ny = p.g.n[1];
+    const int tiles_t = ((p.tile_axis ? ny : nx) + TILE - 1) / TILE;
+    const int per_layer = tiles_t * (p.tile_axis ? nx : ny);
     const int ntiles_win = per_layer * p.g.zcount;                  // tiles of the z-window only
     for (int tw = blockIdx.x * wpb + warp; tw < ntiles_win; tw += gridDim.x * wpb) {
         const int lz = tw / per_layer;
-        const int tile = ((p.g.z0 + lz) % p.g.n[2]) * per_layer + (tw - lz * per_layer);
+        const int cz = (p.g.z0 + lz) % p.g.n[2];
+        const int tile = cz * per_layer + (tw - lz * per_layer);
         if (!p.tile_flag[tile]) continue;
-        const int tx = tile % tiles_x, row = tile / tiles_x;        // row = cz * ny + cy
-        for (int c = 0; c < TILE && tx * TILE + c < nx; c++) build_cell<WITH_IDX, MAPPED>(p, row * nx + tx * TILE + c, smem_raw);
+        if (p.tile_axis) {
+            // tile = (cz * tiles_y + ty) * nx + cx: cells (cx, ty * TILE + c, cz)
+            const int cx = tile % nx, ty = (tile / nx) % tiles_t;
+            for (int c = 0; c < TILE && ty * TILE + c < ny; c++)
+                build_cell<WITH_IDX, MAPPED>(p, (cz * ny + ty * TILE + c) * nx + cx, smem_raw);
+        } else {
+            const int tx = tile % tiles_t, row = tile / tiles_t;        // row = cz * ny + cy
+            for (int c = 0; c < TILE && tx * TILE + c < nx; c++) build_cell<WITH_IDX, MAPPED>(p, row * nx + tx * TILE + c, smem_raw);
+        }
     }
 }
 
@@ -900,6 +911,487 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile kernel, second form.  Same block shape (TILE cells, one warp each, the shared neighbourhood
+// staged once by TMA), with three changes that cut warp instructions per row:
+//   * the tile runs along y, so that the three x cells of a stencil row are ONE contiguous run of the
+//     cell-sorted array: (TILE+2) x 3 bulk copies per block instead of (TILE+2) x 9;
+//   * hits are not appended to lists in shared memory: every lane keeps one 32-bit mask per row, bit k =
+//     "my candidate of chunk k is a neighbor" (a window is at most 32 chunks = 1024 candidates, larger
+//     ones go to the per-cell kernel).  The test loop has no self test and no shared-memory store; the
+//     row's own particle is one bit cleared afterwards;
+//   * emit: after the scan of the lane counts, every lane walks its own bits, derives d for each of its
+//     hits (conflict-free: lane l only reads column l of the staged chunks) and writes the finished
+//     (dx,dy,dz,type) to its slots of a per-warp row stage; the row then leaves as coalesced 16-byte
+//     stores, zero padding included.  No slot map, no gather with bank conflicts.
+// Slot order inside a row: lane-major, within a lane from the last chunk to the first.
+constexpr int NP2 = 64;          // piece table capacity of the second form: (TILE + 2) * 9 <= NP2
+constexpr int TILE2_HDR = (2 * NP2 + 32) * 4;
+static_assert((TILE + 2) * 9 <= NP2, "tile size");
+#ifndef HTF_T2_MINB
+#define HTF_T2_MINB 10
+#endif
+
+__device__ __forceinline__ float4 lds_f4_v(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f4_v(unsigned addr, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_i32_v(unsigned addr, int v)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned bfind_u32(unsigned m)
+{
+    unsigned k;
+    asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(m));
+    return k;
+}
+
+// m |= bit under a predicate (one predicated LOP3; the plain C form compiles to SEL + LOP3)
+__device__ __forceinline__ void or_if(unsigned &m, const bool h, const unsigned bit)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "r"((unsigned)h), "r"(bit));
+}
+
+struct RowPair {
+    f32x2 x, y, z;          // the two rows packed for the f32x2 pipe
+    float t[2];             // row types (mapped-nlist rule)
+};
+
+// One lane's share of the window [addr, end): candidate chunk k sets bit k of m0 / m1 when it is within the cutoff
+// of row 0 / row 1.  Per chunk: 1 LDS.128, 3 packed subs, 3 packed squares, 2 packed (exact) sums, 2 compares,
+// 2 predicated ORs, shift, add, compare, branch.
+template <bool WRAP, bool MAPPED, bool MASKED>
+__device__ __forceinline__ void test_window_bits(const NlistParams &p, unsigned addr, const unsigned end,
+                                                 const unsigned mlen_addr, const RowPair &rp, const f32x2 one,
+                                                 const float rc2, unsigned &m0, unsigned &m1)
+{
+    unsigned bit = 1u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(addr));
+#pragma unroll 1
+    for (; addr < end; addr += 512u, bit <<= 1) {
+        const float4 c = lds_f4_ro(addr);
+        const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
+        const f32x2 dx2 = sub2(cx, rp.x), dy2 = sub2(cy, rp.y), dz2 = sub2(cz, rp.z);
+        float q[2];
+        if (WRAP) {
+            float dx[2], dy[2], dz[2];
+            unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
+                dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
+                dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
+                q[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx[u], dx[u]), __fmul_rn(dy[u], dy[u])), __fmul_rn(dz[u], dz[u]));
+            }
+        } else {
+            unpack2(add2_exact(add2_exact(mul2(dx2, dx2), mul2(dy2, dy2), one), mul2(dz2, dz2), one), q[0], q[1]);
+        }
+        // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
+        bool h0 = q[0] <= rc2, h1 = q[1] <= rc2;
+        if (MASKED) { const bool pv = addr < mlen_addr; h0 = h0 & pv; h1 = h1 & pv; }
+        if (MAPPED) {
+            const bool cm = (int)c.w >= p.map_type_start;
+            h0 = h0 && (cm == ((int)rp.t[0] >= p.map_type_start));
+            h1 = h1 && (cm == ((int)rp.t[1] >= p.map_type_start));
+        }
+        or_if(m0, h0, bit);
+        or_if(m1, h1, bit);
+    }
+}
+
+// This lane's hits of one row -> (d, type) into the lane's slots of the row stage, from the highest set bit of m
+// down.  Branch-free steps: a lane that has run out of bits computes on a harmless address (bfind(0) = -1 puts it
+// 512 bytes below the lane's first candidate, inside the block's header) and only its store is predicated off.
+template <bool WITH_IDX, bool WRAP>
+__device__ __forceinline__ void emit_own_hits(const NlistParams &p, unsigned m, unsigned qa, unsigned qi,
+                                              const unsigned lane_cand, const unsigned cand_s, const unsigned candidx_s,
+                                              const float px, const float py, const float pz)
+{
+    auto step = [&]() {
+        const bool act = m != 0u;
+        const unsigned k = bfind_u32(m);
+        unsigned bitk;
+        asm("shl.b32 %0, 1, %1;" : "=r"(bitk) : "r"(k));        // 0 when k = 0xffffffff (shift counts clamp at 32)
+        m ^= bitk;
+        const unsigned a = lane_cand + (k << 9);
+        const float4 cd = lds_f4_ro(a);
+        float dx = __fsub_rn(cd.x, px), dy = __fsub_rn(cd.y, py), dz = __fsub_rn(cd.z, pz);
+        if (WRAP) {
+            dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
+            dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
+            dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
+        }
+        if (act) sts_f4_v(qa, dx, dy, dz, cd.w);
+        if (WITH_IDX) {
+            if (act) sts_i32_v(qi, lds_i32(candidx_s + ((a - cand_s) >> 2)));
+            qi += 4u;
+        }
+        qa += 16u;
+    };
+#pragma unroll
+    for (int j = 0; j < 4; j++) step();
+    while (__any_sync(HTF_FULL, m != 0u)) step();
+}
+
+// A row with more than K hits: hit number q lands in slot q mod K and only the last K hits are written
+// (htf/TensorflowCompute.cc:370, "the last writer of a slot wins").  Cold path.
+template <bool WITH_IDX>
+__device__ __forceinline__ void emit_own_hits_over(const unsigned K, const float3 half, const float3 L, unsigned m, unsigned q, const unsigned first,
+                                                const unsigned stage_s, const unsigned istage_s, const unsigned lane_cand,
+                                                const unsigned cand_s, const unsigned candidx_s, const float px,
+                                                const float py, const float pz)
+{
+    while (m) {
+        const unsigned k = bfind_u32(m);
+        m ^= 1u << k;
+        const unsigned a = lane_cand + (k << 9);
+        const float4 cd = lds_f4_ro(a);
+        float dx = __fsub_rn(cd.x, px), dy = __fsub_rn(cd.y, py), dz = __fsub_rn(cd.z, pz);
+        dz = wrap_axis(dz, -half.z, half.z, L.z);     // a no-op for interior cells
+        dy = wrap_axis(dy, -half.y, half.y, L.y);
+        dx = wrap_axis(dx, -half.x, half.x, L.x);
+        if (q >= first) {
+            const unsigned slot = q % K;
+            sts_f4_v(stage_s + slot * 16u, dx, dy, dz, cd.w);
+            if (WITH_IDX) sts_i32_v(istage_s + slot * 4u, lds_i32(candidx_s + ((a - cand_s) >> 2)));
+        }
+        q++;
+    }
+}
+
+template <bool WITH_IDX, bool MAPPED, int KC>
+__global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(const NlistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int capB = p.cap_tile;
+    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [NP2] inclusive prefix of piece lengths
+    int *ptab_adj = ptab_end + NP2;                           // [NP2] source slot - staged index
+    int *colstart = ptab_adj + NP2;                           // [<= TILE+3] staged offset of each column
+    int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
+    float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE2_HDR);
+    int *candidx = reinterpret_cast<int *>(cand + capB + 32);
+    const unsigned istage_bytes = WITH_IDX ? (unsigned)(((size_t)2 * (KC ? KC : p.K) * 4 + 15) & ~(size_t)15) : 0u;
+    const unsigned per_warp = 2u * (unsigned)(KC ? KC : p.K) * 16u + istage_bytes;
+    // one opaque base register: otherwise every shared address below is re-derived from SR_CgaCtaId where it is used
+    unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem_s));
+    const unsigned cand_s = smem_s + (unsigned)TILE2_HDR;
+    const unsigned candidx_s = cand_s + (unsigned)(capB + 32) * 16u;
+    const unsigned stage_s = (WITH_IDX ? candidx_s + (unsigned)(capB + 32) * 4u : candidx_s) + per_warp * (unsigned)warp;   // [2][K] float4
+    const unsigned istage_s = stage_s + 2u * (unsigned)(KC ? KC : p.K) * 16u;                                      // [2][K] int
+
+    const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
+    const int tiles_y = gridDim.y;                              // = ceil(ny / TILE)
+    const int cx = blockIdx.x, ty = blockIdx.y;
+    const int cz = (p.g.z0 + (int)blockIdx.z) % nz;            // grid.z = cell layers of the z-window
+    const int bid = (cz * tiles_y + ty) * nx + cx;
+    const int cy0 = ty * TILE;
+    const int nact = min(TILE, ny - cy0);                       // cells of this tile
+    const int nlx = min(nx, 3), nlz = min(nz, 3);
+    const bool ys = ny >= 3;                                    // y stencil = {c-1, c, c+1}; else every y cell
+    const int ncol = ys ? nact + 2 : ny;
+    const bool merge = nx >= 3 && cx >= 1 && cx <= nx - 2;      // cells cx-1..cx+1 are one contiguous run
+    const int ppc = merge ? nlz : nlz * nlx;                    // pieces per column
+    const int npieces = ncol * ppc;                             // <= (TILE + 2) * 9
+
+    // ---- piece table: prefix sums of the piece lengths give the staged (column-major) layout ----
+    int pl = 0, pb = 0;
+    if (tid < npieces) {
+        const int col = tid / ppc, j = tid - col * ppc;
+        const int jz = merge ? j : j / nlx, jx = merge ? 0 : j - jz * nlx;
+        int sy = ys ? cy0 - 1 + col : col;
+        sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
+        int sz = nz <= 3 ? jz : cz + jz - 1;
+        sz = sz < 0 ? sz + nz : (sz >= nz ? sz - nz : sz);
+        int sx = merge ? cx - 1 : (nx <= 3 ? jx : cx + jx - 1);
+        sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
+        const int c0 = (sz * ny + sy) * nx + sx;
+        pb = __ldg(p.cell_start + c0);
+        pl = __ldg(p.cell_start + c0 + (merge ? 3 : 1)) - pb;
+    }
+    int incl = pl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(HTF_FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31 && warp < 4) wtot[warp] = incl;              // totals of pieces [32w, 32w+32)
+    const unsigned stage_bar = (unsigned)__cvta_generic_to_shared(wtot + 4);   // mbarrier of the bulk copies (8-byte aligned)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stage_bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int w = 0; w < warp && w < 4; w++) incl += wtot[w];
+    if (tid < NP2) {
+        ptab_end[tid] = incl;
+        ptab_adj[tid] = pb - (incl - pl);
+        if (tid < npieces && tid % ppc == 0) colstart[tid / ppc] = incl - pl;
+        if (tid == npieces - 1) colstart[ncol] = incl;
+    }
+    __syncthreads();
+    const int mblock = colstart[ncol];
+    bool fits = mblock <= capB;
+    for (int w = 0; w < nact; w++) {
+        const int wl = ys ? colstart[w + 3] - colstart[w] : mblock;
+        fits = fits && wl <= 1024;                              // 32 chunks: one mask bit each
+    }
+    if (tid == 0) {
+        p.tile_flag[bid] = fits ? 0 : 1;
+        if (!fits && p.flag_count) atomicAdd(p.flag_count, 1);
+    }
+    if (!fits) return;                                          // block-uniform
+    const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
+    const int cy = cy0 + warp;
+    const int cell = (cz * ny + min(cy, ny - 1)) * nx + cx;
+    int b = 0, e = 0;
+    if (warp < nact) { b = __ldg(p.cell_start + cell); e = __ldg(p.cell_start + cell + 1); }
+    // the rows of this warp's cell: lane l holds the particle index of row b + l (-1: not a row of this launch)
+    int my_o = -1;
+    if (b + lane < e) {
+        my_o = __ldg(p.sorted_idx + b + lane);
+        if (!full && (my_o < p.row_lo || my_o >= p.row_hi)) my_o = -1;
+    }
+    if (!full) {
+        // sharded build: skip the tile (before staging anything) when none of its cells holds a local row
+        bool any = my_o >= 0;
+        for (int s = b + 32 + lane; s < e; s += 32) {
+            const int o = __ldg(p.sorted_idx + s);
+            any |= (o >= p.row_lo && o < p.row_hi);
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+
+    // ---- stage the whole neighbourhood once: one TMA bulk copy per piece, issued by the thread that owns the
+    //      piece's table entry; completion is counted in bytes on one mbarrier ----
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stage_bar), "r"((unsigned)mblock * 16u) : "memory");
+    if (tid < npieces && pl > 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(cand_s + (unsigned)(incl - pl) * 16u), "l"(p.spos + pb), "r"((unsigned)pl * 16u), "r"(stage_bar) : "memory");
+    if (WITH_IDX) {
+        // original indices ride along as 4-byte cp.async (bulk copies need 16-byte granules): warp w takes pieces w, w+TILE, ...
+        for (int q = warp; q < npieces; q += TILE) {
+            const int qend = ptab_end[q], qadj = ptab_adj[q];
+            const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
+            for (int t = qbeg + lane; t < qend; t += 32) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    // 32 sentinels behind the staged data: the last chunk of the last window may read past its end
+    if (warp == 0) {
+        cand[mblock + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+        // one warp polls the barrier, the others sleep in the block barrier below
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                     "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(stage_bar) : "memory");
+    }
+    __syncthreads();
+    if (warp != 0)      // completed by now: observing the phase makes the bulk copies visible to this thread too
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                     "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(stage_bar) : "memory");
+
+    // ---- one warp per cell of the tile ----
+    if (warp >= nact || e == b) return;
+    if (!full) {
+        bool any = my_o >= 0;
+        for (int s = b + 32 + lane; s < e; s += 32) {
+            const int o = __ldg(p.sorted_idx + s);
+            any |= (o >= p.row_lo && o < p.row_hi);
+        }
+        if (!__any_sync(HTF_FULL, any)) return;
+    }
+    const bool wrap = !((nx >= 5 && cx >= 1 && cx <= nx - 2) && (ny >= 5 && cy >= 1 && cy <= ny - 2) &&
+                        (nz >= 5 && cz >= 1 && cz <= nz - 2));
+    const int ws = ys ? colstart[warp] : 0;
+    const int mlen_true = (ys ? colstart[warp + 3] : mblock) - ws;
+    const int mround = (mlen_true + 31) & ~31;
+    // With >= TILE + 2 cells along the tile axis, whatever follows the window in the buffer is the column two
+    // cells away (or the sentinels): farther than r_cut by construction of the grid, so the "past the end of the
+    // window" mask is unnecessary.  Smaller grids alias the periodic image of the warp's own stencil there.
+    const bool masked = ny < TILE + 2;
+    // staged position of this cell's own particles
+    const int ps = (ys ? warp + 1 : cy) * ppc + (nz <= 3 ? cz : 1) * (merge ? 1 : nlx) + (merge ? 0 : (nx <= 3 ? cx : 1));
+    const int self_base = -ptab_adj[ps] - ws;                   // row slot s sits at window index self_base + s
+    const unsigned cand_ws = cand_s + (unsigned)ws * 16u;
+    const unsigned lane_cand = cand_ws + (unsigned)lane * 16u;
+    const unsigned wend = cand_ws + (unsigned)mround * 16u, mlen_addr = cand_ws + (unsigned)mlen_true * 16u;
+
+    // the test loop's two constants as per-thread registers (through a shuffle, so that ptxas cannot prove them
+    // uniform): as uniform-register operands they are re-loaded from the constant bank in every iteration
+    f32x2 one_v = p.one2;
+    float rc2_v = p.rc2;
+#ifndef HTF_T2_UCONST
+    {
+        unsigned lo = (unsigned)one_v, hi = (unsigned)(one_v >> 32);
+        lo = __shfl_sync(HTF_FULL, lo, 0); hi = __shfl_sync(HTF_FULL, hi, 0);
+        one_v = (f32x2)lo | ((f32x2)hi << 32);
+        rc2_v = __shfl_sync(HTF_FULL, rc2_v, 0);
+    }
+#endif
+
+    const int K = KC ? KC : p.K;
+    const unsigned st_lane = stage_s + (unsigned)lane * 16u;     // this lane's slot of row 0 in the row stage
+    const unsigned ist_lane = istage_s + (unsigned)lane * 4u;
+    const unsigned rowbytes = (unsigned)K * 16u;
+    const bool need_count = p.count_out != nullptr;
+
+    for (int sb = b; sb < e; sb += 32) {
+        if (sb != b) {                                          // cells with more than 32 rows (rare): next 32 indices
+            my_o = -1;
+            if (sb + lane < e) {
+                my_o = __ldg(p.sorted_idx + sb + lane);
+                if (!full && (my_o < p.row_lo || my_o >= p.row_hi)) my_o = -1;
+            }
+        }
+        const int nrow = min(32, e - sb);
+        unsigned pa = cand_ws + (unsigned)(self_base + sb) * 16u;        // shared address of row sb's own particle
+        for (int r0 = 0; r0 < nrow; r0 += 2, pa += 32u) {
+            const int o0 = __shfl_sync(HTF_FULL, my_o, r0), o1 = __shfl_sync(HTF_FULL, my_o, r0 + 1);   // r0 + 1 <= 31
+            if ((o0 & o1) < 0) continue;                        // neither row belongs to this launch
+            const unsigned pa1 = pa + ((r0 + 1 < nrow) ? 16u : 0u);
+            const float4 pi0 = lds_f4_ro(pa), pi1 = lds_f4_ro(pa1);
+            RowPair rp;
+            {
+                // a row that is not emitted tests as +inf (never a hit).  The selects double as the moves that pair
+                // the rows' coordinates in adjacent registers; plain moves get re-materialised inside the test loop.
+                const bool v0 = o0 >= 0, v1 = o1 >= 0;
+                rp.x = pack2_pinned(v0 ? pi0.x : CUDART_INF_F, v1 ? pi1.x : CUDART_INF_F);
+                rp.y = pack2_pinned(v0 ? pi0.y : CUDART_INF_F, v1 ? pi1.y : CUDART_INF_F);
+                rp.z = pack2_pinned(v0 ? pi0.z : CUDART_INF_F, v1 ? pi1.z : CUDART_INF_F);
+            }
+            rp.t[0] = pi0.w; rp.t[1] = pi1.w;
+            // the rows' own particles pass the test (d = 0): their bits are cleared afterwards.  Lane l holds the
+            // candidates at lane_cand + 512 k, so the own particle is this lane's iff the address difference is a
+            // multiple of 512.
+            unsigned clr0 = 0xffffffffu, clr1 = 0xffffffffu;
+            {
+                const unsigned d0 = pa - lane_cand, d1 = pa1 - lane_cand;
+                if ((d0 & 511u) == 0u) clr0 = ~(1u << (d0 >> 9));
+                if ((d1 & 511u) == 0u) clr1 = ~(1u << (d1 >> 9));
+            }
+            unsigned m0 = 0u, m1 = 0u;
+            if (!wrap) test_window_bits<false, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
+            else if (!masked) test_window_bits<true, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
+            else test_window_bits<true, MAPPED, true>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
+            m0 &= clr0; m1 &= clr1;
+            float px0, px1, py0, py1, pz0, pz1;                 // the register halves of the packed rows: no moves
+            unpack2(rp.x, px0, px1); unpack2(rp.y, py0, py1); unpack2(rp.z, pz0, pz1);
+
+            // ---- emit.  Lane counts of the two rows share one 32-bit scan (16 bits each). ----
+            const unsigned packed = (unsigned)__popc(m0) | ((unsigned)__popc(m1) << 16);
+            unsigned inc = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}" : "+r"(inc) : "r"(o));
+            const unsigned all = __shfl_sync(HTF_FULL, inc, 31);
+            const unsigned ex = inc - packed;
+            const unsigned tot0 = all & 0xffffu, tot1 = all >> 16;
+
+            __syncwarp();                                       // the previous batch's slot phase has left the row stage
+            if (o0 >= 0) {
+                const unsigned q = ex & 0xffffu;
+                if (tot0 <= (unsigned)K) {
+                    if (!wrap) emit_own_hits<WITH_IDX, false>(p, m0, stage_s + q * 16u, istage_s + q * 4u, lane_cand, cand_s, candidx_s, px0, py0, pz0);
+                    else emit_own_hits<WITH_IDX, true>(p, m0, stage_s + q * 16u, istage_s + q * 4u, lane_cand, cand_s, candidx_s, px0, py0, pz0);
+                } else {
+                    emit_own_hits_over<WITH_IDX>((unsigned)K, make_float3(p.g.half[0], p.g.half[1], p.g.half[2]),
+                                                 make_float3(p.g.L[0], p.g.L[1], p.g.L[2]), m0, q, tot0 - (unsigned)K, stage_s,
+                                                 istage_s, lane_cand, cand_s, candidx_s, px0, py0, pz0);
+                }
+            }
+            if (o1 >= 0) {
+                const unsigned q = ex >> 16;
+                const unsigned st1 = stage_s + rowbytes, ist1 = istage_s + (unsigned)K * 4u;
+                if (tot1 <= (unsigned)K) {
+                    if (!wrap) emit_own_hits<WITH_IDX, false>(p, m1, st1 + q * 16u, ist1 + q * 4u, lane_cand, cand_s, candidx_s, px1, py1, pz1);
+                    else emit_own_hits<WITH_IDX, true>(p, m1, st1 + q * 16u, ist1 + q * 4u, lane_cand, cand_s, candidx_s, px1, py1, pz1);
+                } else {
+                    emit_own_hits_over<WITH_IDX>((unsigned)K, make_float3(p.g.half[0], p.g.half[1], p.g.half[2]),
+                                                 make_float3(p.g.L[0], p.g.L[1], p.g.L[2]), m1, q, tot1 - (unsigned)K, st1,
+                                                 ist1, lane_cand, cand_s, candidx_s, px1, py1, pz1);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int orig = r ? o1 : o0;
+                if (orig < 0) continue;                          // warp-uniform
+                const int total = (int)(r ? tot1 : tot0);
+                const int nvalid = min(total, K);
+                const unsigned row = (unsigned)(orig - p.row_lo);
+                const unsigned st_r = st_lane + (r ? rowbytes : 0u), ist_r = ist_lane + (r ? (unsigned)K * 4u : 0u);
+                float4 *dst = p.out + (size_t)row * (size_t)K + lane;
+                int *idst = WITH_IDX ? p.idx_out + (size_t)row * (size_t)K + lane : nullptr;
+                if (KC) {
+#pragma unroll
+                    for (int i = 0; i < (KC ? KC / 32 : 1); i++) {
+                        const bool valid = lane + 32 * i < nvalid;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) v = lds_f4_v(st_r + 512u * i);
+                        if (!WITH_IDX || p.out) dst[32 * i] = v;
+                        if (WITH_IDX) idst[32 * i] = valid ? lds_i32(ist_r + 128u * i) : -1;
+                    }
+                } else {
+                    unsigned sa = st_r, ia = ist_r;
+                    for (int sl = lane; sl < K; sl += 32, sa += 512u, ia += 128u, dst += 32) {
+                        const bool valid = sl < nvalid;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) v = lds_f4_v(sa);
+                        if (!WITH_IDX || p.out) *dst = v;
+                        if (WITH_IDX) { *idst = valid ? lds_i32(ia) : -1; idst += 32; }
+                    }
+                }
+                if ((need_count || total >= K) && lane == 0) {
+                    if (need_count) p.count_out[row] = total;
+                    if (total >= K && p.overflow) atomicMax(p.overflow, total);
+                }
+            }
+        }
+    }
+}
+
+template <bool WITH_IDX, bool MAPPED, int KC>
+cudaError_t launch_tile2_kc(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // the attribute is per device
+    size_t &configured = configured_dev[htf_current_device_slot()];
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nlist_tile2_kernel<WITH_IDX, MAPPED, KC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    nlist_tile2_kernel<WITH_IDX, MAPPED, KC><<<grid, TILE * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// the slot phase is unrolled for the two cutoffs of the benchmark configurations (K = 64, 96)
+template <bool WITH_IDX, bool MAPPED>
+cudaError_t launch_tile2_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    if (!WITH_IDX && p.K == 64) return launch_tile2_kc<WITH_IDX, MAPPED, 64>(p, grid, smem, st);
+    if (!WITH_IDX && p.K == 96) return launch_tile2_kc<WITH_IDX, MAPPED, 96>(p, grid, smem, st);
+    return launch_tile2_kc<WITH_IDX, MAPPED, 0>(p, grid, smem, st);
+}
+
+size_t tile2_block_bytes(int capB, int K, bool with_idx)
+{
+    size_t b = TILE2_HDR + (size_t)(capB + 32) * 16;
+    if (with_idx) b += (size_t)(capB + 32) * 4;
+    b += (size_t)TILE * ((size_t)2 * K * 16 + (with_idx ? (((size_t)2 * K * 4 + 15) & ~(size_t)15) : 0));
+    return b;
+}
+
 template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_tile_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
@@ -1009,7 +1501,39 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     p.tile_flag = nullptr;
     p.flag_count = nullptr;
     p.flag_count_next = nullptr;
+    p.tile_axis = 0;
     bool tiled = false;
+    static const int tile_form = [] { const char *e = getenv("HTF_TILE_KERNEL"); return e ? atoi(e) : 2; }();
+    if (tile_form == 2) {
+        // second form: tiles along y, hit masks in registers (see nlist_tile2_kernel)
+        const int tiles_y = (g.n[1] + TILE - 1) / TILE;
+        const int ncol = g.n[1] >= 3 ? min(TILE, g.n[1]) + 2 : g.n[1];
+        const double bmean = (double)ncol * min(g.n[0], 3) * min(g.n[2], 3) * cell_mean;
+        // mean + 4.5 sigma (Poisson): about 3e-6 of the tiles of a homogeneous fluid go to the per-cell kernel
+        int capB = (int)(bmean + 4.5 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
+        capB = (capB + 31) / 32 * 32;
+        const size_t bytes = tile2_block_bytes(capB, p.K, with_idx);
+        if (bytes <= 100 * 1024 && tiles_y <= 65535 && g.n[2] <= 65535) {
+            const int ntiles2 = tiles_y * g.n[0] * g.n[2];
+            if ((e = htf_ensure_tile_flags(ctx, ntiles2)) != cudaSuccess) return e;
+            p.cap = cap;
+            p.cap_tile = capB;
+            p.tile_axis = 1;
+            p.tile_flag = ctx->d_tile_flag;
+            lane &= 1;
+            p.flag_count = ctx->d_flag_count + 2 * lane + (ctx->flag_parity[lane] & 1);
+            p.flag_count_next = ctx->d_flag_count + 2 * lane + ((ctx->flag_parity[lane] + 1) & 1);
+            ctx->flag_parity[lane] ^= 1;
+            ctx->launches += 1;
+            const dim3 tg((unsigned)g.n[0], (unsigned)tiles_y, (unsigned)p.g.zcount);
+            e = with_idx ? (mapped ? launch_tile2_variant<true, true>(p, tg, bytes, st)
+                                   : launch_tile2_variant<true, false>(p, tg, bytes, st))
+                         : (mapped ? launch_tile2_variant<false, true>(p, tg, bytes, st)
+                                   : launch_tile2_variant<false, false>(p, tg, bytes, st));
+            if (e != cudaSuccess) return e;
+            tiled = true;
+        }
+    }
     if (!tiled) {
         const int ncol = g.n[0] >= 3 ? min(TILE, g.n[0]) + 2 : g.n[0];
         const double bmean = (double)ncol * min(g.n[1], 3) * min(g.n[2], 3) * cell_mean;
@@ -1052,7 +1576,10 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     p.cap = cap;
     const size_t smem = per_warp_bytes(cap, p.K, with_idx) * wpb;
     int grid = (g.n[0] * g.n[1] * p.g.zcount + wpb - 1) / wpb;
-    if (tiled) grid = min((tiles_x * g.n[1] * p.g.zcount + wpb - 1) / wpb, 2 * ctx->sm_count);   // persistent flag scan
+    if (tiled) {                                                                                 // persistent flag scan
+        const int ntw = (p.tile_axis ? (g.n[1] + TILE - 1) / TILE * g.n[0] : tiles_x * g.n[1]) * p.g.zcount;
+        grid = min((ntw + wpb - 1) / wpb, 2 * ctx->sm_count);
+    }
     ctx->launches += 1;
     if (with_idx) return mapped ? launch_variant<true, true>(p, grid, wpb, smem, st)
                                 : launch_variant<true, false>(p, grid, wpb, smem, st);
