@@ -1035,8 +1035,29 @@ __device__ __forceinline__ void emit_own_hits(const NlistParams &p, unsigned m, 
         }
         qa += 16u;
     };
+    if (!WITH_IDX && !WRAP) {
+        // the same four steps spelled out: in the C form the predicated store becomes a branch per step and the
+        // slot address is re-derived inside each of them
 #pragma unroll
-    for (int j = 0; j < 4; j++) step();
+        for (int j = 0; j < 4; j++)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 k, b, a;\n\t.reg .f32 x, y, z, w;\n\t"
+                         "setp.ne.u32 p, %0, 0;\n\t"
+                         "bfind.u32 k, %0;\n\t"
+                         "shl.b32 b, 1, k;\n\t"
+                         "xor.b32 %0, %0, b;\n\t"
+                         "shl.b32 a, k, 9;\n\t"
+                         "add.u32 a, a, %2;\n\t"
+                         "ld.shared.v4.f32 {x, y, z, w}, [a];\n\t"
+                         "sub.rn.f32 x, x, %3;\n\t"
+                         "sub.rn.f32 y, y, %4;\n\t"
+                         "sub.rn.f32 z, z, %5;\n\t"
+                         "@p st.shared.v4.f32 [%1], {x, y, z, w};\n\t"
+                         "add.u32 %1, %1, 16;\n\t}"
+                         : "+r"(m), "+r"(qa) : "r"(lane_cand), "f"(px), "f"(py), "f"(pz) : "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) step();
+    }
     while (__any_sync(HTF_FULL, m != 0u)) step();
 }
 
@@ -1085,7 +1106,8 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
     asm volatile("mov.u32 %0, %0;" : "+r"(smem_s));
     const unsigned cand_s = smem_s + (unsigned)TILE2_HDR;
     const unsigned candidx_s = cand_s + (unsigned)(capB + 32) * 16u;
-    const unsigned stage_s = (WITH_IDX ? candidx_s + (unsigned)(capB + 32) * 4u : candidx_s) + per_warp * (unsigned)warp;   // [2][K] float4
+    unsigned stage_s = (WITH_IDX ? candidx_s + (unsigned)(capB + 32) * 4u : candidx_s) + per_warp * (unsigned)warp;   // [2][K] float4
+    asm volatile("mov.u32 %0, %0;" : "+r"(stage_s));
     const unsigned istage_s = stage_s + 2u * (unsigned)(KC ? KC : p.K) * 16u;                                      // [2][K] int
 
     const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
@@ -1223,7 +1245,8 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
     const int ps = (ys ? warp + 1 : cy) * ppc + (nz <= 3 ? cz : 1) * (merge ? 1 : nlx) + (merge ? 0 : (nx <= 3 ? cx : 1));
     const int self_base = -ptab_adj[ps] - ws;                   // row slot s sits at window index self_base + s
     const unsigned cand_ws = cand_s + (unsigned)ws * 16u;
-    const unsigned lane_cand = cand_ws + (unsigned)lane * 16u;
+    unsigned lane_cand = cand_ws + (unsigned)lane * 16u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane_cand));
     const unsigned wend = cand_ws + (unsigned)mround * 16u, mlen_addr = cand_ws + (unsigned)mlen_true * 16u;
 
     // the test loop's two constants as per-thread registers (through a shuffle, so that ptxas cannot prove them
@@ -1240,10 +1263,17 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
 #endif
 
     const int K = KC ? KC : p.K;
-    const unsigned st_lane = stage_s + (unsigned)lane * 16u;     // this lane's slot of row 0 in the row stage
+    unsigned st_lane = stage_s + (unsigned)lane * 16u;           // this lane's slot of row 0 in the row stage
     const unsigned ist_lane = istage_s + (unsigned)lane * 4u;
     const unsigned rowbytes = (unsigned)K * 16u;
     const bool need_count = p.count_out != nullptr;
+    float4 *out_lane = p.out + lane;
+    unsigned long long out_lane_a = (unsigned long long)__cvta_generic_to_global(p.out + lane);
+    int count_from = need_count ? 0 : K;                         // rows with at least this many hits report (count / overflow)
+    // opaque copies: under the register cap ptxas otherwise re-derives these from tid / the parameters at every use
+    asm volatile("mov.u32 %0, %0;" : "+r"(st_lane));
+    asm volatile("mov.u64 %0, %0;" : "+l"(out_lane_a));
+    asm volatile("mov.u32 %0, %0;" : "+r"(count_from));
 
     for (int sb = b; sb < e; sb += 32) {
         if (sb != b) {                                          // cells with more than 32 rows (rare): next 32 indices
@@ -1273,17 +1303,17 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
             // the rows' own particles pass the test (d = 0): their bits are cleared afterwards.  Lane l holds the
             // candidates at lane_cand + 512 k, so the own particle is this lane's iff the address difference is a
             // multiple of 512.
-            unsigned clr0 = 0xffffffffu, clr1 = 0xffffffffu;
-            {
-                const unsigned d0 = pa - lane_cand, d1 = pa1 - lane_cand;
-                if ((d0 & 511u) == 0u) clr0 = ~(1u << (d0 >> 9));
-                if ((d1 & 511u) == 0u) clr1 = ~(1u << (d1 >> 9));
-            }
+            // pa - lane_cand rotated right by 9: the chunk number when the difference is a multiple of 512, a
+            // number >= 2^27 otherwise -- and shl clamps shift counts at 32, so only the owning lane gets a bit
+            unsigned clr0, clr1;
+            asm("{\n\t.reg .b32 d, s;\n\tsub.u32 d, %2, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %0, 1, s;\n\t"
+                "sub.u32 d, %3, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %1, 1, s;\n\t}"
+                : "=r"(clr0), "=r"(clr1) : "r"(pa), "r"(pa1), "r"(lane_cand));
             unsigned m0 = 0u, m1 = 0u;
             if (!wrap) test_window_bits<false, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
             else if (!masked) test_window_bits<true, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
             else test_window_bits<true, MAPPED, true>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
-            m0 &= clr0; m1 &= clr1;
+            m0 &= ~clr0; m1 &= ~clr1;
             float px0, px1, py0, py1, pz0, pz1;                 // the register halves of the packed rows: no moves
             unpack2(rp.x, px0, px1); unpack2(rp.y, py0, py1); unpack2(rp.z, pz0, pz1);
 
@@ -1330,9 +1360,19 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
                 const int nvalid = min(total, K);
                 const unsigned row = (unsigned)(orig - p.row_lo);
                 const unsigned st_r = st_lane + (r ? rowbytes : 0u), ist_r = ist_lane + (r ? (unsigned)K * 4u : 0u);
-                float4 *dst = p.out + (size_t)row * (size_t)K + lane;
+                float4 *dst = out_lane + (size_t)row * (size_t)K;
                 int *idst = WITH_IDX ? p.idx_out + (size_t)row * (size_t)K + lane : nullptr;
-                if (KC) {
+                if (KC && !WITH_IDX) {
+                    const unsigned long long dsta = out_lane_a + (unsigned long long)row * (unsigned long long)(KC * 16);
+#pragma unroll
+                    for (int i = 0; i < (KC ? KC / 32 : 1); i++)
+                        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x, y, z, w;\n\t"
+                                     "setp.lt.s32 p, %2, %3;\n\t"
+                                     "mov.f32 x, 0f00000000;\n\tmov.f32 y, 0f00000000;\n\tmov.f32 z, 0f00000000;\n\tmov.f32 w, 0f00000000;\n\t"
+                                     "@p ld.shared.v4.f32 {x, y, z, w}, [%1];\n\t"
+                                     "st.global.v4.f32 [%0], {x, y, z, w};\n\t}"
+                                     :: "l"(dsta + 512ull * i), "r"(st_r + 512u * i), "r"(lane + 32 * i), "r"(nvalid) : "memory");
+                } else if (KC) {
 #pragma unroll
                     for (int i = 0; i < (KC ? KC / 32 : 1); i++) {
                         const bool valid = lane + 32 * i < nvalid;
@@ -1351,7 +1391,7 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
                         if (WITH_IDX) { *idst = valid ? lds_i32(ia) : -1; idst += 32; }
                     }
                 }
-                if ((need_count || total >= K) && lane == 0) {
+                if (total >= count_from && lane == 0) {
                     if (need_count) p.count_out[row] = total;
                     if (total >= K && p.overflow) atomicMax(p.overflow, total);
                 }
