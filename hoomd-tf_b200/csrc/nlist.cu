@@ -931,6 +931,10 @@ static_assert((TILE + 2) * 9 <= NP2, "tile size");
 #ifndef HTF_T2_MINB
 #define HTF_T2_MINB 10
 #endif
+#ifndef HTF_T2_NPB
+#define HTF_T2_NPB 1
+#endif
+constexpr int NPB = HTF_T2_NPB;   // row pairs tested per candidate load (1 or 2)
 
 __device__ __forceinline__ float4 lds_f4_v(unsigned addr)
 {
@@ -964,13 +968,14 @@ struct RowPair {
     float t[2];             // row types (mapped-nlist rule)
 };
 
-// One lane's share of the window [addr, end): candidate chunk k sets bit k of m0 / m1 when it is within the cutoff
-// of row 0 / row 1.  Per chunk: 1 LDS.128, 3 packed subs, 3 packed squares, 2 packed (exact) sums, 2 compares,
-// 2 predicated ORs, shift, add, compare, branch.
-template <bool WRAP, bool MAPPED, bool MASKED>
+// One lane's share of the window [addr, end): candidate chunk k sets bit k of m[2h] / m[2h+1] when it is within the
+// cutoff of the rows of pair h.  Per chunk and pair: 3 packed subs, 3 packed squares, 2 packed (exact) sums,
+// 2 compares, 2 predicated ORs; per chunk: 1 LDS.128, shift, add, compare, branch.  NP = 2 tests four rows per
+// candidate load: half the shared-memory traffic per row.
+template <bool WRAP, bool MAPPED, bool MASKED, int NP>
 __device__ __forceinline__ void test_window_bits(const NlistParams &p, unsigned addr, const unsigned end,
-                                                 const unsigned mlen_addr, const RowPair &rp, const f32x2 one,
-                                                 const float rc2, unsigned &m0, unsigned &m1)
+                                                 const unsigned mlen_addr, const RowPair (&rp)[NP], const f32x2 one,
+                                                 const float rc2, unsigned (&m)[2 * NP])
 {
     unsigned bit = 1u;
     asm volatile("mov.u32 %0, %0;" : "+r"(addr));
@@ -978,31 +983,34 @@ __device__ __forceinline__ void test_window_bits(const NlistParams &p, unsigned 
     for (; addr < end; addr += 512u, bit <<= 1) {
         const float4 c = lds_f4_ro(addr);
         const f32x2 cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z);
-        const f32x2 dx2 = sub2(cx, rp.x), dy2 = sub2(cy, rp.y), dz2 = sub2(cz, rp.z);
-        float q[2];
-        if (WRAP) {
-            float dx[2], dy[2], dz[2];
-            unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
-                dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
-                dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
-                q[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx[u], dx[u]), __fmul_rn(dy[u], dy[u])), __fmul_rn(dz[u], dz[u]));
+        for (int h = 0; h < NP; h++) {
+            const f32x2 dx2 = sub2(cx, rp[h].x), dy2 = sub2(cy, rp[h].y), dz2 = sub2(cz, rp[h].z);
+            float q[2];
+            if (WRAP) {
+                float dx[2], dy[2], dz[2];
+                unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    dz[u] = wrap_axis(dz[u], -p.g.half[2], p.g.half[2], p.g.L[2]);
+                    dy[u] = wrap_axis(dy[u], -p.g.half[1], p.g.half[1], p.g.L[1]);
+                    dx[u] = wrap_axis(dx[u], -p.g.half[0], p.g.half[0], p.g.L[0]);
+                    q[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx[u], dx[u]), __fmul_rn(dy[u], dy[u])), __fmul_rn(dz[u], dz[u]));
+                }
+            } else {
+                unpack2(add2_exact(add2_exact(mul2(dx2, dx2), mul2(dy2, dy2), one), mul2(dz2, dz2), one), q[0], q[1]);
             }
-        } else {
-            unpack2(add2_exact(add2_exact(mul2(dx2, dx2), mul2(dy2, dy2), one), mul2(dz2, dz2), one), q[0], q[1]);
+            // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
+            bool h0 = q[0] <= rc2, h1 = q[1] <= rc2;
+            if (MASKED) { const bool pv = addr < mlen_addr; h0 = h0 & pv; h1 = h1 & pv; }
+            if (MAPPED) {
+                const bool cm = (int)c.w >= p.map_type_start;
+                h0 = h0 && (cm == ((int)rp[h].t[0] >= p.map_type_start));
+                h1 = h1 && (cm == ((int)rp[h].t[1] >= p.map_type_start));
+            }
+            or_if(m[2 * h], h0, bit);
+            or_if(m[2 * h + 1], h1, bit);
         }
-        // rsq <= rc2 is !(rsq > rc2) for every non-NaN rsq; +inf rows / sentinels give inf or NaN -> no hit
-        bool h0 = q[0] <= rc2, h1 = q[1] <= rc2;
-        if (MASKED) { const bool pv = addr < mlen_addr; h0 = h0 & pv; h1 = h1 & pv; }
-        if (MAPPED) {
-            const bool cm = (int)c.w >= p.map_type_start;
-            h0 = h0 && (cm == ((int)rp.t[0] >= p.map_type_start));
-            h1 = h1 && (cm == ((int)rp.t[1] >= p.map_type_start));
-        }
-        or_if(m0, h0, bit);
-        or_if(m1, h1, bit);
     }
 }
 
@@ -1267,7 +1275,6 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
     const unsigned ist_lane = istage_s + (unsigned)lane * 4u;
     const unsigned rowbytes = (unsigned)K * 16u;
     const bool need_count = p.count_out != nullptr;
-    float4 *out_lane = p.out + lane;
     unsigned long long out_lane_a = (unsigned long long)__cvta_generic_to_global(p.out + lane);
     int count_from = need_count ? 0 : K;                         // rows with at least this many hits report (count / overflow)
     // opaque copies: under the register cap ptxas otherwise re-derives these from tid / the parameters at every use
@@ -1285,115 +1292,119 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
         }
         const int nrow = min(32, e - sb);
         unsigned pa = cand_ws + (unsigned)(self_base + sb) * 16u;        // shared address of row sb's own particle
-        for (int r0 = 0; r0 < nrow; r0 += 2, pa += 32u) {
-            const int o0 = __shfl_sync(HTF_FULL, my_o, r0), o1 = __shfl_sync(HTF_FULL, my_o, r0 + 1);   // r0 + 1 <= 31
-            if ((o0 & o1) < 0) continue;                        // neither row belongs to this launch
-            const unsigned pa1 = pa + ((r0 + 1 < nrow) ? 16u : 0u);
-            const float4 pi0 = lds_f4_ro(pa), pi1 = lds_f4_ro(pa1);
-            RowPair rp;
-            {
-                // a row that is not emitted tests as +inf (never a hit).  The selects double as the moves that pair
-                // the rows' coordinates in adjacent registers; plain moves get re-materialised inside the test loop.
-                const bool v0 = o0 >= 0, v1 = o1 >= 0;
-                rp.x = pack2_pinned(v0 ? pi0.x : CUDART_INF_F, v1 ? pi1.x : CUDART_INF_F);
-                rp.y = pack2_pinned(v0 ? pi0.y : CUDART_INF_F, v1 ? pi1.y : CUDART_INF_F);
-                rp.z = pack2_pinned(v0 ? pi0.z : CUDART_INF_F, v1 ? pi1.z : CUDART_INF_F);
+        for (int r0 = 0; r0 < nrow; r0 += 2 * NPB, pa += 32u * NPB) {
+            int o[2 * NPB];
+            int oall = -1;
+#pragma unroll
+            for (int j = 0; j < 2 * NPB; j++) { o[j] = __shfl_sync(HTF_FULL, my_o, r0 + j); oall &= o[j]; }   // r0 + j <= 31
+            if (oall < 0) continue;                             // no row of this batch belongs to this launch
+            RowPair rp[NPB];
+            unsigned clr[2 * NPB], m[2 * NPB];
+#pragma unroll
+            for (int h = 0; h < NPB; h++) {
+                // rows past the end of the cell repeat the batch's first row; they test as +inf like every row that is
+                // not emitted.  The selects double as the moves that pair the rows' coordinates in adjacent
+                // registers; plain moves get re-materialised inside the test loop.
+                const unsigned pa0 = pa + ((r0 + 2 * h < nrow) ? 32u * h : 0u);
+                const unsigned pa1 = pa + ((r0 + 2 * h + 1 < nrow) ? 32u * h + 16u : 0u);
+                const float4 pi0 = lds_f4_ro(pa0), pi1 = lds_f4_ro(pa1);
+                const bool v0 = o[2 * h] >= 0, v1 = o[2 * h + 1] >= 0;
+                rp[h].x = pack2_pinned(v0 ? pi0.x : CUDART_INF_F, v1 ? pi1.x : CUDART_INF_F);
+                rp[h].y = pack2_pinned(v0 ? pi0.y : CUDART_INF_F, v1 ? pi1.y : CUDART_INF_F);
+                rp[h].z = pack2_pinned(v0 ? pi0.z : CUDART_INF_F, v1 ? pi1.z : CUDART_INF_F);
+                rp[h].t[0] = pi0.w; rp[h].t[1] = pi1.w;
+                // The rows' own particles pass the test (d = 0): their bits are cleared afterwards.  Lane l holds the
+                // candidates at lane_cand + 512 k; pa - lane_cand rotated right by 9 is the chunk number when the
+                // difference is a multiple of 512 and a number >= 2^27 otherwise -- and shl clamps shift counts at
+                // 32, so only the owning lane gets a bit.
+                asm("{\n\t.reg .b32 d, s;\n\tsub.u32 d, %2, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %0, 1, s;\n\t"
+                    "sub.u32 d, %3, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %1, 1, s;\n\t}"
+                    : "=r"(clr[2 * h]), "=r"(clr[2 * h + 1]) : "r"(pa0), "r"(pa1), "r"(lane_cand));
+                m[2 * h] = 0u; m[2 * h + 1] = 0u;
             }
-            rp.t[0] = pi0.w; rp.t[1] = pi1.w;
-            // the rows' own particles pass the test (d = 0): their bits are cleared afterwards.  Lane l holds the
-            // candidates at lane_cand + 512 k, so the own particle is this lane's iff the address difference is a
-            // multiple of 512.
-            // pa - lane_cand rotated right by 9: the chunk number when the difference is a multiple of 512, a
-            // number >= 2^27 otherwise -- and shl clamps shift counts at 32, so only the owning lane gets a bit
-            unsigned clr0, clr1;
-            asm("{\n\t.reg .b32 d, s;\n\tsub.u32 d, %2, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %0, 1, s;\n\t"
-                "sub.u32 d, %3, %4;\n\tshf.r.wrap.b32 s, d, d, 9;\n\tshl.b32 %1, 1, s;\n\t}"
-                : "=r"(clr0), "=r"(clr1) : "r"(pa), "r"(pa1), "r"(lane_cand));
-            unsigned m0 = 0u, m1 = 0u;
-            if (!wrap) test_window_bits<false, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
-            else if (!masked) test_window_bits<true, MAPPED, false>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
-            else test_window_bits<true, MAPPED, true>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m0, m1);
-            m0 &= ~clr0; m1 &= ~clr1;
-            float px0, px1, py0, py1, pz0, pz1;                 // the register halves of the packed rows: no moves
-            unpack2(rp.x, px0, px1); unpack2(rp.y, py0, py1); unpack2(rp.z, pz0, pz1);
+            if (NPB == 2 && r0 + 2 >= nrow) {
+                // only the first pair holds rows: test it alone
+                RowPair rp1[1] = {rp[0]};
+                unsigned m1[2] = {0u, 0u};
+                if (!wrap) test_window_bits<false, MAPPED, false, 1>(p, lane_cand, wend, mlen_addr, rp1, one_v, rc2_v, m1);
+                else if (!masked) test_window_bits<true, MAPPED, false, 1>(p, lane_cand, wend, mlen_addr, rp1, one_v, rc2_v, m1);
+                else test_window_bits<true, MAPPED, true, 1>(p, lane_cand, wend, mlen_addr, rp1, one_v, rc2_v, m1);
+                m[0] = m1[0]; m[1] = m1[1];
+            } else {
+                if (!wrap) test_window_bits<false, MAPPED, false, NPB>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m);
+                else if (!masked) test_window_bits<true, MAPPED, false, NPB>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m);
+                else test_window_bits<true, MAPPED, true, NPB>(p, lane_cand, wend, mlen_addr, rp, one_v, rc2_v, m);
+            }
 
-            // ---- emit.  Lane counts of the two rows share one 32-bit scan (16 bits each). ----
-            const unsigned packed = (unsigned)__popc(m0) | ((unsigned)__popc(m1) << 16);
-            unsigned inc = packed;
+            // ---- emit, pair by pair (the row stage holds two rows).  Lane counts of a pair share one 32-bit scan. ----
+            unsigned ex[NPB], all[NPB];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}" : "+r"(inc) : "r"(o));
-            const unsigned all = __shfl_sync(HTF_FULL, inc, 31);
-            const unsigned ex = inc - packed;
-            const unsigned tot0 = all & 0xffffu, tot1 = all >> 16;
-
-            __syncwarp();                                       // the previous batch's slot phase has left the row stage
-            if (o0 >= 0) {
-                const unsigned q = ex & 0xffffu;
-                if (tot0 <= (unsigned)K) {
-                    if (!wrap) emit_own_hits<WITH_IDX, false>(p, m0, stage_s + q * 16u, istage_s + q * 4u, lane_cand, cand_s, candidx_s, px0, py0, pz0);
-                    else emit_own_hits<WITH_IDX, true>(p, m0, stage_s + q * 16u, istage_s + q * 4u, lane_cand, cand_s, candidx_s, px0, py0, pz0);
-                } else {
-                    emit_own_hits_over<WITH_IDX>((unsigned)K, make_float3(p.g.half[0], p.g.half[1], p.g.half[2]),
-                                                 make_float3(p.g.L[0], p.g.L[1], p.g.L[2]), m0, q, tot0 - (unsigned)K, stage_s,
-                                                 istage_s, lane_cand, cand_s, candidx_s, px0, py0, pz0);
-                }
+            for (int h = 0; h < NPB; h++) {
+                m[2 * h] &= ~clr[2 * h]; m[2 * h + 1] &= ~clr[2 * h + 1];
+                const unsigned packed = (unsigned)__popc(m[2 * h]) | ((unsigned)__popc(m[2 * h + 1]) << 16);
+                unsigned inc = packed;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}" : "+r"(inc) : "r"(d));
+                all[h] = __shfl_sync(HTF_FULL, inc, 31);
+                ex[h] = inc - packed;
             }
-            if (o1 >= 0) {
-                const unsigned q = ex >> 16;
-                const unsigned st1 = stage_s + rowbytes, ist1 = istage_s + (unsigned)K * 4u;
-                if (tot1 <= (unsigned)K) {
-                    if (!wrap) emit_own_hits<WITH_IDX, false>(p, m1, st1 + q * 16u, ist1 + q * 4u, lane_cand, cand_s, candidx_s, px1, py1, pz1);
-                    else emit_own_hits<WITH_IDX, true>(p, m1, st1 + q * 16u, ist1 + q * 4u, lane_cand, cand_s, candidx_s, px1, py1, pz1);
-                } else {
-                    emit_own_hits_over<WITH_IDX>((unsigned)K, make_float3(p.g.half[0], p.g.half[1], p.g.half[2]),
-                                                 make_float3(p.g.L[0], p.g.L[1], p.g.L[2]), m1, q, tot1 - (unsigned)K, st1,
-                                                 ist1, lane_cand, cand_s, candidx_s, px1, py1, pz1);
-                }
-            }
-            __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const int orig = r ? o1 : o0;
-                if (orig < 0) continue;                          // warp-uniform
-                const int total = (int)(r ? tot1 : tot0);
-                const int nvalid = min(total, K);
-                const unsigned row = (unsigned)(orig - p.row_lo);
-                const unsigned st_r = st_lane + (r ? rowbytes : 0u), ist_r = ist_lane + (r ? (unsigned)K * 4u : 0u);
-                float4 *dst = out_lane + (size_t)row * (size_t)K;
-                int *idst = WITH_IDX ? p.idx_out + (size_t)row * (size_t)K + lane : nullptr;
-                if (KC && !WITH_IDX) {
-                    const unsigned long long dsta = out_lane_a + (unsigned long long)row * (unsigned long long)(KC * 16);
+            for (int h = 0; h < NPB; h++) {
+                if ((o[2 * h] & o[2 * h + 1]) < 0) continue;    // warp-uniform
+                float px[2], py[2], pz[2];                      // the register halves of the packed rows: no moves
+                unpack2(rp[h].x, px[0], px[1]); unpack2(rp[h].y, py[0], py[1]); unpack2(rp[h].z, pz[0], pz[1]);
+                const unsigned tot[2] = {all[h] & 0xffffu, all[h] >> 16};
+                __syncwarp();                                   // the previous pair's slot phase has left the row stage
 #pragma unroll
-                    for (int i = 0; i < (KC ? KC / 32 : 1); i++)
-                        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x, y, z, w;\n\t"
-                                     "setp.lt.s32 p, %2, %3;\n\t"
-                                     "mov.f32 x, 0f00000000;\n\tmov.f32 y, 0f00000000;\n\tmov.f32 z, 0f00000000;\n\tmov.f32 w, 0f00000000;\n\t"
-                                     "@p ld.shared.v4.f32 {x, y, z, w}, [%1];\n\t"
-                                     "st.global.v4.f32 [%0], {x, y, z, w};\n\t}"
-                                     :: "l"(dsta + 512ull * i), "r"(st_r + 512u * i), "r"(lane + 32 * i), "r"(nvalid) : "memory");
-                } else if (KC) {
-#pragma unroll
-                    for (int i = 0; i < (KC ? KC / 32 : 1); i++) {
-                        const bool valid = lane + 32 * i < nvalid;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) v = lds_f4_v(st_r + 512u * i);
-                        if (!WITH_IDX || p.out) dst[32 * i] = v;
-                        if (WITH_IDX) idst[32 * i] = valid ? lds_i32(ist_r + 128u * i) : -1;
-                    }
-                } else {
-                    unsigned sa = st_r, ia = ist_r;
-                    for (int sl = lane; sl < K; sl += 32, sa += 512u, ia += 128u, dst += 32) {
-                        const bool valid = sl < nvalid;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) v = lds_f4_v(sa);
-                        if (!WITH_IDX || p.out) *dst = v;
-                        if (WITH_IDX) { *idst = valid ? lds_i32(ia) : -1; idst += 32; }
+                for (int r = 0; r < 2; r++) {
+                    if (o[2 * h + r] < 0) continue;             // warp-uniform
+                    const unsigned q = r ? (ex[h] >> 16) : (ex[h] & 0xffffu);
+                    const unsigned st_r = stage_s + (r ? rowbytes : 0u), ist_r = istage_s + (r ? (unsigned)K * 4u : 0u);
+                    if (tot[r] <= (unsigned)K) {
+                        if (!wrap) emit_own_hits<WITH_IDX, false>(p, m[2 * h + r], st_r + q * 16u, ist_r + q * 4u, lane_cand, cand_s, candidx_s, px[r], py[r], pz[r]);
+                        else emit_own_hits<WITH_IDX, true>(p, m[2 * h + r], st_r + q * 16u, ist_r + q * 4u, lane_cand, cand_s, candidx_s, px[r], py[r], pz[r]);
+                    } else {
+                        emit_own_hits_over<WITH_IDX>((unsigned)K, make_float3(p.g.half[0], p.g.half[1], p.g.half[2]),
+                                                     make_float3(p.g.L[0], p.g.L[1], p.g.L[2]), m[2 * h + r], q, tot[r] - (unsigned)K,
+                                                     st_r, ist_r, lane_cand, cand_s, candidx_s, px[r], py[r], pz[r]);
                     }
                 }
-                if (total >= count_from && lane == 0) {
-                    if (need_count) p.count_out[row] = total;
-                    if (total >= K && p.overflow) atomicMax(p.overflow, total);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int orig = o[2 * h + r];
+                    if (orig < 0) continue;                      // warp-uniform
+                    const int total = (int)tot[r];
+                    const int nvalid = min(total, K);
+                    const unsigned row = (unsigned)(orig - p.row_lo);
+                    const unsigned st_r = st_lane + (r ? rowbytes : 0u), ist_r = ist_lane + (r ? (unsigned)K * 4u : 0u);
+                    if (KC && !WITH_IDX) {
+                        const unsigned long long dsta = out_lane_a + (unsigned long long)row * (unsigned long long)(KC * 16);
+#pragma unroll
+                        for (int i = 0; i < (KC ? KC / 32 : 1); i++)
+                            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x, y, z, w;\n\t"
+                                         "setp.lt.s32 p, %2, %3;\n\t"
+                                         "mov.f32 x, 0f00000000;\n\tmov.f32 y, 0f00000000;\n\tmov.f32 z, 0f00000000;\n\tmov.f32 w, 0f00000000;\n\t"
+                                         "@p ld.shared.v4.f32 {x, y, z, w}, [%1];\n\t"
+                                         "st.global.v4.f32 [%0], {x, y, z, w};\n\t}"
+                                         :: "l"(dsta + 512ull * i), "r"(st_r + 512u * i), "r"(lane + 32 * i), "r"(nvalid) : "memory");
+                    } else {
+                        float4 *dst = p.out + (size_t)row * (size_t)K + lane;
+                        int *idst = WITH_IDX ? p.idx_out + (size_t)row * (size_t)K + lane : nullptr;
+                        unsigned sa = st_r, ia = ist_r;
+                        for (int sl = lane; sl < K; sl += 32, sa += 512u, ia += 128u, dst += 32) {
+                            const bool valid = sl < nvalid;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (valid) v = lds_f4_v(sa);
+                            if (!WITH_IDX || p.out) *dst = v;
+                            if (WITH_IDX) { *idst = valid ? lds_i32(ia) : -1; idst += 32; }
+                        }
+                    }
+                    if (total >= count_from && lane == 0) {
+                        if (need_count) p.count_out[row] = total;
+                        if (total >= K && p.overflow) atomicMax(p.overflow, total);
+                    }
                 }
             }
         }
