@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--step-length", type=float, default=0.0087,
                     help="displacement per step in the --skin workload (LJ liquid at T*=1, dt=0.005: 0.005*sqrt(3))")
+    ap.add_argument("--counts", action="store_true",
+                    help="the builder writes per-row neighbor counts and the pair pass reads only the valid slots "
+                         "(27 %% less DRAM traffic, no faster: see DESIGN.md)")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from the host instead of replaying the three CUDA graphs "
                          "(binning | build | forces) the step is captured into")
@@ -411,6 +414,11 @@ def measure(args, env, scaling, full):
         d_L = torch.tensor([hi[a] - lo[a] for a in range(3)] + [1.0], dtype=torch.float32, device=dev)
         skin_state = {"t": 0, "rebuilds": 0}
 
+    # the builder's neighbors-per-row ride along to the pair pass, which then reads only each row's valid slots
+    cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if (args.counts and not skin) else None
+    if eds_model is not None:
+        eds_model.row_counts = cnt
+
     def phase_exchange():
         if halo:
             xch.exchange()                                            # the path's one exchange step (2 faces)
@@ -434,7 +442,7 @@ def measure(args, env, scaling, full):
             skin_state["t"] += 1
             ctx.skin_nlist(d_pos_all, out=nl)
         else:
-            ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False)
+            ctx.build_nlist(d_pos_all, row_lo, row_hi, out=nl, rebin=False, count_out=cnt)
 
     def phase_force():
         if train is not None:
@@ -452,14 +460,14 @@ def measure(args, env, scaling, full):
             ctx.mlp_forces(nl, packed, r_cut, out=fe)
         elif bins is not None:
             bins.zero_()
-            ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)
+            ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100, counts=cnt)
             if world > 1:
                 if p2p:
                     ctx.comm_allreduce(bins)                          # mailboxes in peer memory, graph-capturable
                 else:
                     dist.all_reduce(bins)
         else:
-            ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir)
+            ctx.lj_forces(nl, virial=True, virial_components=6, out=fe, virial_out=vir, counts=cnt)
 
     def step(marks=None):
         if marks is not None:

@@ -66,6 +66,8 @@ struct htf_ctx {
     float4 *d_skin_ref;           // positions at the last rebuild
     int64_t skin_rows_cap, skin_n_cap;
     int64_t skin_row_lo, skin_row_hi, skin_n;   // what the current lists cover (-1: none)
+    int *d_row_count;         // lazily sized [rows]: neighbors per row of the last fused build (the pair pass behind it
+    int64_t row_count_cap;    //   skips the padded slots of every row instead of reading their zeros)
     float *d_nlist_scratch;   // lazily sized [rows][K][4] for htf_lj_step(d_nlist_out = NULL)
     int64_t nlist_scratch_elems;
     // RDF threshold table (device) and the key it was built for
@@ -117,7 +119,7 @@ struct HtfSlab {
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                           int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
                           int type_i, int type_j, unsigned long long *bins, cudaStream_t st,
-                          const HtfSlab *slab = nullptr);
+                          const HtfSlab *slab = nullptr, const int32_t *row_count = nullptr);
 
 cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const float *row_type,
                            long long row_type_stride, const float *thr, int nb, int type_i, int type_j,
@@ -157,7 +159,8 @@ cudaError_t htf_launch_select(htf_ctx *ctx, const float4 *pos, int64_t n, int ax
 
 cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                              int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
-                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab = nullptr);
+                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab = nullptr,
+                             const int32_t *row_count = nullptr);
 
 int htf_mlp_packed_bytes_host();
 int htf_mlp_raw_count_host();

@@ -33,6 +33,8 @@ struct PairParams {
     const float4 *nlist;
     long long rows;
     int K;
+    const int *row_count;      // nullable [rows]: neighbors of the row (may exceed K); slots >= min(count, K) are the
+                               // builder's zero padding and are not read
     float4 *fe;
     float *virial;
     int vcomp;                 // 0, 6 or 9
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
             row = o - p.map_row_lo;
         }
         const float4 *rp = p.nlist + (active ? row : 0) * K;
+        int kv = K;                                 // valid slots of this lane's row
+        if (p.row_count) kv = active ? min(__ldg(p.row_count + row), K) : 0;
         float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
         float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
         float cn = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
@@ -102,53 +106,68 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
             row_in_rdf = active;
             if (active && p.type_i >= 0) row_in_rdf = (__ldg(p.row_type + row * p.row_type_stride) == (float)p.type_i);
         }
-        for (int s0 = sub; s0 < K; s0 += LPR * LJ_UNROLL) {
+        // slots at or past kmax are padding in every row of this warp: whole iterations are skipped (K = 96 at
+        // liquid density: one of three)
+        const int kmax = p.row_count ? __reduce_max_sync(HTF_FULL, kv) : K;
+        for (int s0 = sub; s0 - sub < kmax; s0 += LPR * LJ_UNROLL) {
             float4 d[LJ_UNROLL];
 #pragma unroll
             for (int u = 0; u < LJ_UNROLL; u++) {
                 const int s = s0 + u * LPR;
-                d[u] = (active && s < K) ? ld_stream(rp + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[u] = (active && s < kv) ? ld_stream(rp + s) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            // scheduling fence: in one basic block ptxas sinks each load next to its use in the (branch-free) body and
+            // the lane has one 16-byte request in flight instead of four (measured: 0.28 ms instead of 0.2 ms)
+            if (p.vcomp < 0) continue;                      // never true: a basic-block boundary between loads and math
 #pragma unroll
             for (int u = 0; u < LJ_UNROLL; u++) {
                 const float dx = d[u].x, dy = d[u].y, dz = d[u].z;
                 float r_guess = 0.f;                     // RDF: any r within a fraction of a bin of the exact one
                 if (FORCES) {
+                    // Branch-free: a padded slot (d = 0, rt = 1.7e-7) runs the same instructions with s = 0.
+                    // sqrt and the reciprocal are MUFU seeds + one Newton step each (<= 1 ulp, no slow-path calls):
+                    // the error of 1/(rt + 3e-6) (nlist_rinv) is amplified 13x by s^13, so the seed alone (1 ulp)
+                    // would already spend 1.5e-6 of the 1e-5 contract; the 1/rt of the gradient enters linearly and
+                    // keeps the 2-ulp MUFU.RSQ.
                     const float ax = dx + 1e-7f, ay = dy + 1e-7f, az = dz + 1e-7f;
-                    const float rt2 = ax * ax + ay * ay + az * az;
-                    const float rt = sqrtf(rt2);
+                    const float rt2 = fmaxf(ax * ax + ay * ay + az * az, 1e-30f);
+                    float irt;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(irt) : "f"(rt2));
+                    float rt = rt2 * irt;
+                    rt = fmaf(fmaf(-rt, rt, rt2), 0.5f * irt, rt);
                     r_guess = rt;
-                    if (rt > 3e-6f) {
-                        // 1/(rt + 3e-6) (nlist_rinv) is IEEE-rounded: its error is amplified 13x by s^13;
-                        // the 1/rt of the gradient enters linearly, the 2-ulp MUFU.RSQ is enough there
-                        const float si = 1.0f / (rt + 3e-6f);
-                        const float irt = rsqrtf(rt2);
-                        const float s2 = si * si, s6 = s2 * s2 * s2;
-                        en += 2.0f * (s6 * s6 - s6);
-                        const float coef = (24.0f * s6 * si - 48.0f * s6 * s6 * si) * irt;
-                        const float px = coef * ax, py = coef * ay, pz = coef * az;
-                        fx += px; fy += py; fz += pz;
-                        if (VIRIAL) {
-                            // |F_pair| / (2 |d|) = |coef| |a| / (2 |d|); |a| and |d| differ by the 1e-7 offset of
-                            // safe_norm only (< 2.2e-7 relative for r >= 0.8), far inside the 1e-5 contract
-                            const float w = 0.5f * fabsf(coef);
-                            const float wx = w * dx, wy = w * dy, wz = w * dz;
-                            vxx += wx * dx; vxy += wx * dy; vxz += wx * dz;
-                            vyy += wy * dy; vyz += wy * dz; vzz += wz * dz;
-                        }
-                        if (CV) {
-                            // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a
-                            const float x = rt * p.cv_inv_r0, x2 = x * x, x6 = x2 * x2 * x2;
-                            const float sw = __fdividef(1.0f, 1.0f + x6);      // 1-ulp reciprocal: 1e-7 relative on s
-                            cn += sw;
-                            const float cg = -6.0f * x6 * sw * sw * irt * irt;
-                            gx += cg * ax; gy += cg * ay; gz += cg * az;
-                        }
+                    const bool pair = rt > 3e-6f;
+                    const float a = rt + 3e-6f;
+                    float si;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(si) : "f"(a));
+                    si = fmaf(si, fmaf(-a, si, 1.0f), si);
+                    si = pair ? si : 0.0f;
+                    const float s2 = si * si, s6 = s2 * s2 * s2;
+                    en += 2.0f * (s6 * s6 - s6);
+                    const float coef = (24.0f * s6 * si - 48.0f * s6 * s6 * si) * irt;
+                    const float px = coef * ax, py = coef * ay, pz = coef * az;
+                    fx += px; fy += py; fz += pz;
+                    if (VIRIAL) {
+                        // |F_pair| / (2 |d|) = |coef| |a| / (2 |d|); |a| and |d| differ by the 1e-7 offset of
+                        // safe_norm only (< 2.2e-7 relative for r >= 0.8), far inside the 1e-5 contract
+                        const float w = 0.5f * fabsf(coef);
+                        const float wx = w * dx, wy = w * dy, wz = w * dz;
+                        vxx += wx * dx; vxy += wx * dy; vxz += wx * dz;
+                        vyy += wy * dy; vyz += wy * dz; vzz += wz * dz;
+                    }
+                    if (CV) {
+                        // s = 1/(1 + x^6), x = rt/r0;  ds/dd = -6 x^6 s^2 / rt^2 * a
+                        const float x = rt * p.cv_inv_r0, x2 = x * x, x6 = x2 * x2 * x2;
+                        float sw = __fdividef(1.0f, 1.0f + x6);      // 1-ulp reciprocal: 1e-7 relative on s
+                        sw = pair ? sw : 0.0f;
+                        cn += sw;
+                        const float cg = -6.0f * x6 * sw * sw * irt * irt;
+                        gx += cg * ax; gy += cg * ay; gz += cg * az;
                     }
                 }
                 if (RDF) {
                     const int s = s0 + u * LPR;
-                    if (row_in_rdf && s < K) {
+                    if (row_in_rdf && s < kv) {
                         float m = 1.0f;
                         if (p.type_j >= 0) m = (d[u].w == (float)p.type_j) ? 1.0f : 0.0f;
                         const float x = __fmul_rn(dx, m), y = __fmul_rn(dy, m), z = __fmul_rn(dz, m);
@@ -168,6 +187,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                 }
             }
         }
+        if (RDF && row_in_rdf && sub == 0) bin0 += (unsigned)(K - kv);      // the skipped padding: q = 0, bin 0
         if (FORCES) {
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) {
@@ -250,6 +270,8 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
     long long grid = blocks_needed;
     const long long persistent = (long long)ctx->sm_count * 8;     // 8 x 256 threads = full occupancy
     if ((RDF || CV) && grid > persistent) grid = persistent;       // fewer histogram / CV flushes
+    // (a one-wave persistent grid for the plain LJ pass, which amortises the ~60 set-up instructions of a warp, was
+    // measured: 0.198 ms either way at 1 M x 64, slower without the virial -- not adopted)
     if (p.row_map && p.blocks_per_sm > 0 && grid > (long long)ctx->sm_count * p.blocks_per_sm)
         grid = (long long)ctx->sm_count * p.blocks_per_sm;         // slab pass next to a running build: a slice of every SM
     if (grid < 1) grid = 1;
@@ -268,6 +290,7 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 static void set_slab(PairParams &p, const HtfSlab *slab)
 {
     p.row_map = nullptr; p.slot_lo = p.slot_hi = nullptr; p.map_row_lo = p.map_row_hi = 0; p.blocks_per_sm = 0;
+    p.row_count = nullptr;
     if (!slab) return;
     p.blocks_per_sm = slab->blocks_per_sm;
     p.row_map = slab->sorted_idx; p.slot_lo = slab->slot_lo; p.slot_hi = slab->slot_hi;
@@ -276,11 +299,13 @@ static void set_slab(PairParams &p, const HtfSlab *slab)
 
 cudaError_t htf_launch_lj(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                           int vcomp, const float *rdf_thr, int nb, const float *row_type, long long row_type_stride,
-                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st, const HtfSlab *slab)
+                          int type_i, int type_j, unsigned long long *bins, cudaStream_t st, const HtfSlab *slab,
+                          const int32_t *row_count)
 {
     if (rows <= 0) return cudaSuccess;
     PairParams p;
     set_slab(p, slab);
+    p.row_count = row_count;
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;
@@ -312,11 +337,12 @@ cudaError_t htf_launch_rdf(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
 // LJ forces + virial + smooth coordination CV (+ RDF) in one pass: the EDS-biased model of BASELINE config 5
 cudaError_t htf_launch_lj_cv(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, float4 *fe, float *virial,
                              int vcomp, float r0, float4 *cv_row, double *cv_sum, const float *rdf_thr, int nb,
-                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab)
+                             unsigned long long *bins, cudaStream_t st, const HtfSlab *slab, const int32_t *row_count)
 {
     if (rows <= 0) return cudaSuccess;
     PairParams p;
     set_slab(p, slab);
+    p.row_count = row_count;
     p.nlist = nlist; p.rows = rows; p.K = K; p.fe = fe; p.virial = virial; p.vcomp = virial ? vcomp : 0;
     p.thr = rdf_thr; p.nb = nb; p.r_lo = ctx->rdf_lo;
     p.inv_step = (nb > 0 && ctx->rdf_hi > ctx->rdf_lo) ? (float)nb / (ctx->rdf_hi - ctx->rdf_lo) : 0.f;

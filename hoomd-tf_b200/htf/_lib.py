@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HTF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhtf_b200.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESKEW, EARCH = 0, -1, -2, -3, -4, -5, -6
 FLAG_DETERMINISTIC = 1
@@ -38,9 +38,9 @@ SYMBOLS = {
     "htf_set_cutoff": (_i32, [_vp, _f32, _i32]),
     "htf_bin_particles": (_i32, [_vp, _vp, _i64, _vp]),
     "htf_build_nlist": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "htf_lj_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp]),
-    "htf_lj_forces_rdf": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _vp]),
-    "htf_lj_cv_forces": (_i32, [_vp, _vp, _i64, _i32, _f32, _vp, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _i32, _vp]),
+    "htf_lj_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "htf_lj_forces_rdf": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _vp]),
+    "htf_lj_cv_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _i32, _vp]),
     "htf_mlp_param_sizes": (_i32, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "htf_mlp_pack": (_i32, [_vp, _vp, _vp, _vp]),
     "htf_mlp_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp]),

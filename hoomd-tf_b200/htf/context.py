@@ -24,6 +24,14 @@ def _check_dev_f32(t, name, last=None):
         raise ValueError("%s must have last dimension %d" % (name, last))
 
 
+def _check_counts(c, rows):
+    if c is None:
+        return
+    if not isinstance(c, torch.Tensor) or not c.is_cuda or c.dtype != torch.int32 or not c.is_contiguous() \
+            or c.numel() != rows:
+        raise ValueError("counts must be a contiguous int32 CUDA tensor with one entry per row")
+
+
 class HtfContext:
     def __init__(self, n_max, nneighbor_cutoff, r_cut, device=None, deterministic=True):
         if not torch.cuda.is_available():
@@ -127,7 +135,7 @@ class HtfContext:
         self._ck(self.lib.htf_skin_rebuild(self._h, _ptr(pos), n, int(row_lo), n if row_hi is None else int(row_hi),
                                            self._stream()))
 
-    def skin_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False):
+    def skin_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False, count_out=None):
         """The per-step pass: neighbor tensor of the rows from the candidate lists of the last ``skin_rebuild``."""
         _check_dev_f32(pos, "positions", 4)
         n = pos.shape[0]
@@ -137,6 +145,9 @@ class HtfContext:
             out = torch.empty((rows, self.K, 4), dtype=torch.float32, device=self.device)
         idx = torch.empty((rows, self.K), dtype=torch.int32, device=self.device) if want_idx else None
         cnt = torch.empty((rows,), dtype=torch.int32, device=self.device) if want_count else None
+        if count_out is not None:                       # caller-owned counts (not returned)
+            _check_counts(count_out, rows)
+            cnt = count_out
         self._ck(self.lib.htf_skin_nlist(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(out), _ptr(idx), _ptr(cnt),
                                          _ptr(self._overflow), self._stream()))
         if want_idx or want_count:
@@ -166,7 +177,8 @@ class HtfContext:
         _check_dev_f32(pos, "positions", 4)
         self._ck(self.lib.htf_bin_particles(self._h, _ptr(pos), pos.shape[0], self._stream()))
 
-    def build_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False, rebin=True):
+    def build_nlist(self, pos, row_lo=0, row_hi=None, out=None, want_idx=False, want_count=False, rebin=True,
+                    count_out=None):
         """positions [N,4] -> nlist [rows,K,4] (and optionally idx [rows,K], count [rows])."""
         _check_dev_f32(pos, "positions", 4)
         n = pos.shape[0]
@@ -180,6 +192,9 @@ class HtfContext:
             _check_dev_f32(out, "nlist out", 4)
         idx = torch.empty((rows, self.K), dtype=torch.int32, device=self.device) if want_idx else None
         cnt = torch.empty((rows,), dtype=torch.int32, device=self.device) if want_count else None
+        if count_out is not None:                       # caller-owned counts (not returned)
+            _check_counts(count_out, rows)
+            cnt = count_out
         self._ck(self.lib.htf_build_nlist(self._h, _ptr(pos), n, int(row_lo), row_hi, _ptr(out), _ptr(idx),
                                           _ptr(cnt), _ptr(self._overflow), self._stream()))
         res = (out,)
@@ -197,8 +212,11 @@ class HtfContext:
             self._overflow.zero_()
         return v
 
-    def lj_forces(self, nlist, virial=False, virial_components=6, out=None, virial_out=None):
+    def lj_forces(self, nlist, virial=False, virial_components=6, out=None, virial_out=None, counts=None):
+        """LJ forces + energy (+ virial) of a neighbor tensor.  ``counts`` int32[rows] (``build_nlist(want_count=True)``)
+        lets the pass skip every row's zero padding instead of reading it."""
         _check_dev_f32(nlist, "nlist", 4)
+        _check_counts(counts, nlist.shape[0])
         if nlist.dim() != 3:
             raise ValueError("nlist must be [rows, K, 4]")
         rows, k = nlist.shape[0], nlist.shape[1]
@@ -207,21 +225,22 @@ class HtfContext:
         if virial:
             vir = virial_out if virial_out is not None else \
                 torch.empty((rows, virial_components), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.htf_lj_forces(self._h, _ptr(nlist), rows, int(k), _ptr(fe), _ptr(vir),
+        self._ck(self.lib.htf_lj_forces(self._h, _ptr(nlist), rows, int(k), _ptr(counts), _ptr(fe), _ptr(vir),
                                         int(virial_components), self._stream()))
         return (fe, vir) if virial else fe
 
-    def lj_step_forces_only(self, nlist, force_out, virial_out, bins, r_range, nbins=100):
+    def lj_step_forces_only(self, nlist, force_out, virial_out, bins, r_range, nbins=100, counts=None):
         """LJ forces+virial with the compute_rdf histogram fused into the same pass over ``nlist``."""
         _check_dev_f32(nlist, "nlist", 4)
+        _check_counts(counts, nlist.shape[0])
         vc = virial_out.shape[1] if virial_out is not None else 6
         self._ck(self.lib.htf_lj_forces_rdf(self._h, _ptr(nlist), nlist.shape[0], int(nlist.shape[1]),
-                                            _ptr(force_out), _ptr(virial_out), int(vc), _ptr(bins),
+                                            _ptr(counts), _ptr(force_out), _ptr(virial_out), int(vc), _ptr(bins),
                                             float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out
 
     def lj_cv_forces(self, nlist, r0, cv_row, cv_sum, force_out=None, virial_out=None, bins=None,
-                     r_range=(0.0, 1.0), nbins=100):
+                     r_range=(0.0, 1.0), nbins=100, counts=None):
         """LJ forces(+virial) + smooth coordination CV (+ RDF) in one pass (BASELINE config 5 model).
         ``cv_row`` float32[rows,4] = (dCV-sum/dd x,y,z, cn_i); ``cv_sum`` float64[1] is incremented."""
         _check_dev_f32(nlist, "nlist", 4)
@@ -232,7 +251,8 @@ class HtfContext:
         if force_out is None:
             force_out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
         vc = virial_out.shape[1] if virial_out is not None else 6
-        self._ck(self.lib.htf_lj_cv_forces(self._h, _ptr(nlist), rows, int(k), float(r0), _ptr(force_out),
+        _check_counts(counts, rows)
+        self._ck(self.lib.htf_lj_cv_forces(self._h, _ptr(nlist), rows, int(k), _ptr(counts), float(r0), _ptr(force_out),
                                            _ptr(virial_out), int(vc), _ptr(cv_row), _ptr(cv_sum), _ptr(bins),
                                            float(r_range[0]), float(r_range[1]), int(nbins), self._stream()))
         return force_out

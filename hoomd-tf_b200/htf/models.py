@@ -251,7 +251,9 @@ class EDSCoordinationModel(SimModel):
     fused_whole_shard_only = True      # the CV is a global quantity: row batches cannot be biased one by one
 
     def compute(self, nlist, positions, box):
-        fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins)
+        # row_counts: optional int32[rows] from the builder of THIS nlist (set by the caller that built it)
+        fe, _, cv_row, cv_sum, bins = ops.lj_cv_forces(nlist, self.r0, rdf_range=self.rdf_range, nbins=self.nbins,
+                                                       counts=getattr(self, "row_counts", None))
         return self._finish(nlist.shape[0], fe, cv_row, cv_sum, bins)
 
     def fused_rows(self, tfc, n, off, hi):

@@ -32,7 +32,7 @@ def _as_nlist(nlist):
     return nl
 
 
-def lj_forces(nlist, virial=False):
+def lj_forces(nlist, virial=False, counts=None):
     """LJ (epsilon = sigma = 1) forces+energy [N,4] (and the virial [N,3,3]) of the built-in LJ model.
 
     Same numbers as ``compute_nlist_forces(nlist, sum_j 2 (rinv^12 - rinv^6), virial)`` with
@@ -42,8 +42,8 @@ def lj_forces(nlist, virial=False):
     nl = _as_nlist(nlist)
     ctx = default_context(nl.device)
     if not virial:
-        return ctx.lj_forces(nl)
-    fe, v9 = ctx.lj_forces(nl, virial=True, virial_components=9)
+        return ctx.lj_forces(nl, counts=counts)
+    fe, v9 = ctx.lj_forces(nl, virial=True, virial_components=9, counts=counts)
     return fe, v9.view(-1, 3, 3)
 
 
@@ -62,11 +62,12 @@ def rdf_hist(nlist, r_range, nbins=100, type_tensor=None, type_i=None, type_j=No
                         type_j=type_j if type_tensor is not None else None, bins=bins)
 
 
-def lj_cv_forces(nlist, r0, virial=False, rdf_range=None, nbins=100, bins=None, cv_sum=None):
+def lj_cv_forces(nlist, r0, virial=False, rdf_range=None, nbins=100, bins=None, cv_sum=None, counts=None):
     """One pass: LJ forces (+virial [N,6]) + the smooth coordination CV of BASELINE config 5 (+ RDF histogram).
 
     Returns ``(forces[N,4], virial6 or None, cv_row[N,4], cv_sum float64[1], bins or None)`` where
     ``cv_row = (sum_j ds/dd_ij (x,y,z), cn_i)`` and ``cv_sum = sum_i cn_i`` (see include/htf_b200.h).
+    ``counts`` int32[N] (the builder's neighbors per row) lets the pass skip the zero padding.
     """
     nl = _as_nlist(nlist)
     ctx = default_context(nl.device)
@@ -78,7 +79,7 @@ def lj_cv_forces(nlist, r0, virial=False, rdf_range=None, nbins=100, bins=None, 
     if rdf_range is not None and bins is None:
         bins = torch.zeros(nbins + 2, dtype=torch.int64, device=nl.device)
     fe = ctx.lj_cv_forces(nl, r0, cv_row, cv_sum, virial_out=vir, bins=bins,
-                          r_range=rdf_range if rdf_range is not None else (0.0, 1.0), nbins=nbins)
+                          r_range=rdf_range if rdf_range is not None else (0.0, 1.0), nbins=nbins, counts=counts)
     return fe, vir, cv_row, cv_sum, bins
 
 

@@ -56,7 +56,7 @@ extern "C" {
 typedef struct htf_ctx htf_ctx;
 
 /* ABI version of this header; htf_abi_version() of the loaded library must match. */
-#define HTF_ABI_VERSION 17
+#define HTF_ABI_VERSION 18
 int htf_abi_version(void);
 
 /*
@@ -191,22 +191,28 @@ int htf_build_nlist(htf_ctx *ctx, const float *d_pos_all, int64_t n_all, int64_t
  * 3x3 -> 6 virial scatter (htf/tf2hoomd_op/tf2hoomd.cc:48-59, htf/TensorflowCompute.cc:285-301,
  * htf/TensorflowCompute.cu:41-71).
  *   k               second dimension of d_nlist
+ *   d_row_count     nullable int32[rows]: htf_build_nlist's d_count_out for these rows.  With it the pass reads only
+ *                   the first min(count, k) slots of a row -- the rest is the builder's zero padding, which adds
+ *                   nothing to any sum (and lands in bin 0 of the histogram) -- about 27 % less DRAM traffic at
+ *                   liquid density, bit-identical results.  NULL: every slot is read.  (Measured on B200: the pass
+ *                   is then bound by instruction issue and no faster, so the fused steps htf_lj_step / htf_lj_rows /
+ *                   htf_lj_cv_step only do this when HTF_ROW_COUNTS=1.)
  *   d_force_energy  float[rows][4] = (Fx, Fy, Fz, e_i)
  *   d_virial        nullable; virial_components = 6: float[rows][6] (xx,xy,xz,yy,yz,zz);
  *                   = 9: float[rows][9] row-major 3x3 (what get_virial_array returns,
  *                   htf/tensorflowcompute.py:388-392)
  */
-int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
-                  float *d_virial, int virial_components, void *stream);
+int htf_lj_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const int32_t *d_row_count,
+                  float *d_force_energy, float *d_virial, int virial_components, void *stream);
 
 /*
  * htf_lj_forces with the compute_rdf histogram (below) fused into the same read of the neighbor
  * tensor: the LJ + RDF model of BASELINE config 2 (htf/test-py/build_examples.py:297-314) in one
  * pass.  No type filter; d_bins as in htf_rdf_hist.
  */
-int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float *d_force_energy,
-                      float *d_virial, int virial_components, int64_t *d_bins, float r_lo, float r_hi,
-                      int nbins, void *stream);
+int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const int32_t *d_row_count,
+                      float *d_force_energy, float *d_virial, int virial_components, int64_t *d_bins, float r_lo,
+                      float r_hi, int nbins, void *stream);
 
 /*
  * EDS-biased model of BASELINE config 5 in one pass over the neighbor tensor: htf_lj_forces (+ optional
@@ -219,9 +225,9 @@ int htf_lj_forces_rdf(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, f
  *   d_cv_sum  double[1], atomically += sum_i cn_i (caller zeroes; all-reduce it across row shards)
  * EDSLayer (htf/layers.py:101-195) turns the CV into alpha on the host side of the ABI.
  */
-int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, float r0, float *d_force_energy,
-                     float *d_virial, int virial_components, float *d_cv_row, double *d_cv_sum, int64_t *d_bins,
-                     float r_lo, float r_hi, int nbins, void *stream);
+int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const int32_t *d_row_count, float r0,
+                     float *d_force_energy, float *d_virial, int virial_components, float *d_cv_row, double *d_cv_sum,
+                     int64_t *d_bins, float r_lo, float r_hi, int nbins, void *stream);
 
 /*
  * Pairwise-MLP neural force field over the neighbor tensor (BASELINE config 3): the per-pair analogue of the

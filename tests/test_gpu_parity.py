@@ -287,6 +287,48 @@ def test_virial_components_small_K(oracle_mod, K):
     assert torch.equal(v6c, v6)
 
 
+@pytest.mark.parametrize("K", [4, 24, 64])
+def test_row_counts_skip_padding_is_bit_identical(K):
+    """The pair passes given the builder's per-row counts read only the valid slots of each row; forces, virial,
+    CV sums and every RDF bin (the skipped padding is bin 0) must be bit-identical to the full read -- including
+    rows that overflow K (count > K: all K slots are valid)."""
+    from htf import synthetic
+    pos, lo, hi = synthetic.lattice_fluid((12, 12, 12), 0.7, seed=3 + K)
+    r_cut = 2.5
+    ctx = _ctx(pos.shape[0], K, r_cut, lo, hi)
+    n = pos.shape[0]
+    nl, cnt = ctx.build_nlist(torch.from_numpy(pos).cuda(), want_count=True)
+    if K < 64:
+        assert int(cnt.max()) > K            # the overflow case is part of the test
+    for vc in (6, 9):
+        fe_a, v_a = ctx.lj_forces(nl, virial=True, virial_components=vc)
+        fe_b, v_b = ctx.lj_forces(nl, virial=True, virial_components=vc, counts=cnt)
+        assert torch.equal(fe_a, fe_b) and torch.equal(v_a, v_b)
+    bins_a = torch.zeros(102, dtype=torch.int64, device="cuda"); bins_b = torch.zeros_like(bins_a)
+    fe = torch.empty((n, 4), device="cuda"); vir = torch.empty((n, 6), device="cuda")
+    ctx.lj_step_forces_only(nl, fe, vir, bins_a, (0.0, r_cut), 100)
+    fe2 = torch.empty_like(fe); vir2 = torch.empty_like(vir)
+    ctx.lj_step_forces_only(nl, fe2, vir2, bins_b, (0.0, r_cut), 100, counts=cnt)
+    assert torch.equal(bins_a, bins_b) and int(bins_a.sum()) == n * K and torch.equal(fe, fe2) and torch.equal(vir, vir2)
+    # a histogram range that does not start at zero: the padding still lands in bin 0
+    bins_c = torch.zeros(52, dtype=torch.int64, device="cuda"); bins_d = torch.zeros_like(bins_c)
+    ctx.lj_step_forces_only(nl, fe, vir, bins_c, (1.0, 2.0), 50)
+    ctx.lj_step_forces_only(nl, fe2, vir2, bins_d, (1.0, 2.0), 50, counts=cnt)
+    assert torch.equal(bins_c, bins_d)
+    cv_a = torch.empty((n, 4), device="cuda"); cv_b = torch.empty_like(cv_a)
+    s_a = torch.zeros(1, dtype=torch.float64, device="cuda"); s_b = torch.zeros_like(s_a)
+    bins_a.zero_(); bins_b.zero_()
+    fa = ctx.lj_cv_forces(nl, 1.3, cv_a, s_a, bins=bins_a, r_range=(0.0, r_cut), nbins=100)
+    fb = ctx.lj_cv_forces(nl, 1.3, cv_b, s_b, bins=bins_b, r_range=(0.0, r_cut), nbins=100, counts=cnt)
+    torch.cuda.synchronize()
+    assert torch.equal(fa, fb) and torch.equal(cv_a, cv_b) and torch.equal(bins_a, bins_b)
+    assert abs(float(s_a) - float(s_b)) <= 1e-9 * abs(float(s_a))          # float64 atomics: order only
+    # the fused step: same numbers as build + full-read pass
+    fe3 = ctx.lj_step(torch.from_numpy(pos).cuda(), virial_out=vir2)
+    torch.cuda.synchronize()
+    assert torch.equal(fe3, fe_a) and torch.equal(vir2, ctx.lj_forces(nl, virial=True)[1])
+
+
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_pipelined_step_is_bit_identical(oracle_mod, shuffle):
     """htf_lj_step / htf_lj_cv_step cut the cell layers into slabs and run each slab's pair pass on a second stream

@@ -26,8 +26,11 @@ nl = torch.empty((n, K, 4), device="cuda"); fe = torch.empty((n, 4), device="cud
 bins = torch.zeros(102, dtype=torch.int64, device="cuda")
 ctx.bin_particles(dpos)
 t_bin = timeit(lambda: ctx.bin_particles(dpos))
-t_build = timeit(lambda: ctx.build_nlist(dpos, out=nl, rebin=False))
-t_lj = timeit(lambda: ctx.lj_forces(nl, virial=True, out=fe, virial_out=vir))
+cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
+t_build_nc = timeit(lambda: ctx.build_nlist(dpos, out=nl, rebin=False))
+t_build = timeit(lambda: ctx.build_nlist(dpos, out=nl, rebin=False, count_out=cnt))
+t_lj_full = timeit(lambda: ctx.lj_forces(nl, virial=True, out=fe, virial_out=vir))
+t_lj = timeit(lambda: ctx.lj_forces(nl, virial=True, out=fe, virial_out=vir, counts=cnt))
 t_ljnv = timeit(lambda: ctx.lj_forces(nl, virial=False, out=fe))
 t_rdf = timeit(lambda: ctx.rdf_hist(nl, (0, r_cut), 100, bins=bins))
 t_step = timeit(lambda: ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial_out=vir))
@@ -35,8 +38,10 @@ t_step_rdf = timeit(lambda: ctx.lj_step(dpos, nlist_out=nl, force_out=fe, virial
 print("overflow", ctx.overflow())
 gb = lambda b, ms: b / ms / 1e6
 print("bin      med %.3f ms min %.3f" % t_bin)
-print("build    med %.3f ms min %.3f  -> %.0f GB/s" % (t_build + (gb(n * (16 * K + 16), t_build[0]),)))
-print("lj+vir   med %.3f ms min %.3f  -> %.0f GB/s" % (t_lj + (gb(n * (16 * K + 40), t_lj[0]),)))
+print("build    med %.3f ms min %.3f  -> %.0f GB/s" % (t_build_nc + (gb(n * (16 * K + 16), t_build_nc[0]),)))
+print("build+cnt med %.3f ms min %.3f" % t_build)
+print("lj+vir(all slots) med %.3f ms min %.3f  -> %.0f GB/s" % (t_lj_full + (gb(n * (16 * K + 40), t_lj_full[0]),)))
+print("lj+vir   med %.3f ms min %.3f  -> %.0f GB/s (algorithmic bytes)" % (t_lj + (gb(n * (16 * K + 40), t_lj[0]),)))
 print("lj       med %.3f ms min %.3f" % t_ljnv)
 print("rdf      med %.3f ms min %.3f" % t_rdf)
 print("step     med %.3f ms min %.3f  -> %.0f GB/s, %.3e particle-steps/s" % (t_step + (gb(n * (32 * K + 56), t_step[0]), n / t_step[0] * 1e3)))
