@@ -928,13 +928,9 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
 constexpr int NP2 = 64;          // piece table capacity of the second form: (TILE + 2) * 9 <= NP2
 constexpr int TILE2_HDR = (2 * NP2 + 32) * 4;
 static_assert((TILE + 2) * 9 <= NP2, "tile size");
-#ifndef HTF_T2_MINB
-#define HTF_T2_MINB 10
-#endif
-#ifndef HTF_T2_NPB
-#define HTF_T2_NPB 1
-#endif
-constexpr int NPB = HTF_T2_NPB;   // row pairs tested per candidate load (1 or 2)
+// NPB = row pairs tested per candidate load.  2 halves the shared-memory traffic and the loop overhead of the test
+// phase per row but needs 63 registers (8 blocks per SM instead of 10): measured 1.90 vs 2.14 ms at 4 M x 96 (windows
+// of 16 chunks), 0.373 vs 0.377 ms at 1 M x 64 (10 chunks).
 
 __device__ __forceinline__ float4 lds_f4_v(unsigned addr)
 {
@@ -1095,8 +1091,8 @@ __device__ __forceinline__ void emit_own_hits_over(const unsigned K, const float
     }
 }
 
-template <bool WITH_IDX, bool MAPPED, int KC>
-__global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(const NlistParams p)
+template <bool WITH_IDX, bool MAPPED, int KC, int NPB>
+__global__ void __launch_bounds__(TILE * 32, NPB == 2 ? 8 : 10) nlist_tile2_kernel(const NlistParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1411,28 +1407,31 @@ __global__ void __launch_bounds__(TILE * 32, HTF_T2_MINB) nlist_tile2_kernel(con
     }
 }
 
-template <bool WITH_IDX, bool MAPPED, int KC>
+template <bool WITH_IDX, bool MAPPED, int KC, int NPB>
 cudaError_t launch_tile2_kc(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // the attribute is per device
     size_t &configured = configured_dev[htf_current_device_slot()];
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(nlist_tile2_kernel<WITH_IDX, MAPPED, KC>,
+        cudaError_t e = cudaFuncSetAttribute(nlist_tile2_kernel<WITH_IDX, MAPPED, KC, NPB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    nlist_tile2_kernel<WITH_IDX, MAPPED, KC><<<grid, TILE * 32, smem, st>>>(p);
+    nlist_tile2_kernel<WITH_IDX, MAPPED, KC, NPB><<<grid, TILE * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-// the slot phase is unrolled for the two cutoffs of the benchmark configurations (K = 64, 96)
+// the slot phase is unrolled for the two cutoffs of the benchmark configurations (K = 64, 96); four rows per
+// candidate load where cells hold enough rows for it (pairs2)
 template <bool WITH_IDX, bool MAPPED>
-cudaError_t launch_tile2_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
+cudaError_t launch_tile2_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st, bool pairs2)
 {
-    if (!WITH_IDX && p.K == 64) return launch_tile2_kc<WITH_IDX, MAPPED, 64>(p, grid, smem, st);
-    if (!WITH_IDX && p.K == 96) return launch_tile2_kc<WITH_IDX, MAPPED, 96>(p, grid, smem, st);
-    return launch_tile2_kc<WITH_IDX, MAPPED, 0>(p, grid, smem, st);
+    if (!WITH_IDX && p.K == 64) return pairs2 ? launch_tile2_kc<WITH_IDX, MAPPED, 64, 2>(p, grid, smem, st)
+                                              : launch_tile2_kc<WITH_IDX, MAPPED, 64, 1>(p, grid, smem, st);
+    if (!WITH_IDX && p.K == 96) return pairs2 ? launch_tile2_kc<WITH_IDX, MAPPED, 96, 2>(p, grid, smem, st)
+                                              : launch_tile2_kc<WITH_IDX, MAPPED, 96, 1>(p, grid, smem, st);
+    return launch_tile2_kc<WITH_IDX, MAPPED, 0, 1>(p, grid, smem, st);
 }
 
 size_t tile2_block_bytes(int capB, int K, bool with_idx)
@@ -1577,10 +1576,13 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             ctx->flag_parity[lane] ^= 1;
             ctx->launches += 1;
             const dim3 tg((unsigned)g.n[0], (unsigned)tiles_y, (unsigned)p.g.zcount);
-            e = with_idx ? (mapped ? launch_tile2_variant<true, true>(p, tg, bytes, st)
-                                   : launch_tile2_variant<true, false>(p, tg, bytes, st))
-                         : (mapped ? launch_tile2_variant<false, true>(p, tg, bytes, st)
-                                   : launch_tile2_variant<false, false>(p, tg, bytes, st));
+            // four rows per candidate load when the cells hold enough rows to fill the batches
+            static const int pairs_env = [] { const char *e2 = getenv("HTF_TILE_PAIRS"); return e2 ? atoi(e2) : 0; }();
+            const bool pairs2 = pairs_env ? pairs_env == 2 : cell_mean >= 6.0;
+            e = with_idx ? (mapped ? launch_tile2_variant<true, true>(p, tg, bytes, st, pairs2)
+                                   : launch_tile2_variant<true, false>(p, tg, bytes, st, pairs2))
+                         : (mapped ? launch_tile2_variant<false, true>(p, tg, bytes, st, pairs2)
+                                   : launch_tile2_variant<false, false>(p, tg, bytes, st, pairs2));
             if (e != cudaSuccess) return e;
             tiled = true;
         }
