@@ -32,6 +32,7 @@
 
 #include <math_constants.h>
 #include <cstdlib>
+#include <cstring>
 #ifdef HTF_DEBUG_FLAGS
 #include <cstdio>
 #include <vector>
@@ -57,6 +58,8 @@ struct NlistParams {
     int K;
     float rc2;
     unsigned long long one2;   // (1.0f, 1.0f): an OPAQUE packed one (see add2_exact)
+    unsigned long long inv_l2[3], neg_l2[3], magic2;   // packed (1/L, 1/L), (-L, -L) per axis (0 where n < 5), (1.5 * 2^23) x 2
+    int fast_wrap;             // every dimension has >= 5 cells: minimum image by rounding (see test_window_bits)
     int map_type_start;
     int cap;             // per-warp window capacity (candidates), multiple of 32, <= 4064
     int cap_tile;        // tile kernel: candidates staged per block
@@ -983,7 +986,21 @@ __device__ __forceinline__ void test_window_bits(const NlistParams &p, unsigned 
         for (int h = 0; h < NP; h++) {
             const f32x2 dx2 = sub2(cx, rp[h].x), dy2 = sub2(cy, rp[h].y), dz2 = sub2(cz, rp[h].z);
             float q[2];
-            if (WRAP) {
+            if (WRAP && p.fast_wrap) {
+                // With >= 5 cells per dimension a stencil candidate is either less than 2 cell edges away (no shift)
+                // or, reached through the periodic boundary, at least n - 2 >= 3 edges away (one shift) -- never near
+                // L/2 = n/2 edges.  Then d - L * rint(d / L) is bit-identical to HOOMD's compare-and-shift, and it
+                // runs on the packed pipe: k = (d/L + 1.5 * 2^23) - 1.5 * 2^23, d' = fma(k, -L, d) (k L is exact, so
+                // the fma rounds once, like the subtraction).
+                f32x2 dd[3] = {dx2, dy2, dz2};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    f32x2 k = add2_exact(mul2(dd[a], p.inv_l2[a]), p.magic2, one);
+                    k = sub2(k, p.magic2);
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd[a]) : "l"(k), "l"(p.neg_l2[a]));
+                }
+                unpack2(add2_exact(add2_exact(mul2(dd[0], dd[0]), mul2(dd[1], dd[1]), one), mul2(dd[2], dd[2]), one), q[0], q[1]);
+            } else if (WRAP) {
                 float dx[2], dy[2], dz[2];
                 unpack2(dx2, dx[0], dx[1]); unpack2(dy2, dy[0], dy[1]); unpack2(dz2, dz[0], dz[1]);
 #pragma unroll
@@ -1510,6 +1527,18 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     p.K = ctx->K;
     p.rc2 = ctx->r_cut * ctx->r_cut;
     p.one2 = 0x3f8000003f800000ull;
+    {
+        auto pack = [](float v) { unsigned u; memcpy(&u, &v, 4); return (unsigned long long)u | ((unsigned long long)u << 32); };
+        p.fast_wrap = 1;
+        for (int a = 0; a < 3; a++) {
+            if (ctx->grid.n[a] < 5) p.fast_wrap = 0;
+            p.inv_l2[a] = pack(1.0f / ctx->grid.L[a]);
+            p.neg_l2[a] = pack(-ctx->grid.L[a]);
+        }
+        p.magic2 = pack(12582912.0f);
+        static const bool exact_env = [] { const char *e2 = getenv("HTF_EXACT_WRAP"); return e2 && atoi(e2) != 0; }();
+        if (exact_env) p.fast_wrap = 0;
+    }
     p.map_type_start = ctx->map_type_start;
     p.out = out;
     p.idx_out = idx_out;
