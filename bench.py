@@ -610,7 +610,7 @@ def measure(args, env, scaling, full):
             "exchange": ({"transport": xch.transport, "note": xch.transport_note or None,
                           "what": "fused pack + send into the neighbours' peer-memory windows, flags, gather (htf_comm_exchange_halo)"
                                   if p2p else "pack kernels + NCCL send/recv"} if xch is not None else None),
-            "roofline": {"bound": "hbm", "kernel": "nlist_tile_kernel (+ per-cell fallback pass)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "nlist_tile2_kernel (+ per-cell fallback pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_build, "kernel_ms": build_ms,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,

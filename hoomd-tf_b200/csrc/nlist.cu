@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams
 //     (dx,dy,dz,type) to its slots of a per-warp row stage; the row then leaves as coalesced 16-byte
 //     stores, zero padding included.  No slot map, no gather with bank conflicts.
 // Slot order inside a row: lane-major, within a lane from the last chunk to the first.
-constexpr int NP2 = 64;          // piece table capacity of the second form: (TILE + 2) * 9 <= NP2
+constexpr int NP2 = ((TILE + 2) * 9 + 31) / 32 * 32;   // piece table capacity of the second form (64 for TILE = 4)
 constexpr int TILE2_HDR = (2 * NP2 + 32) * 4;
 static_assert((TILE + 2) * 9 <= NP2, "tile size");
 // NPB = row pairs tested per candidate load.  2 halves the shared-memory traffic and the loop overhead of the test
@@ -1109,7 +1109,7 @@ __device__ __forceinline__ void emit_own_hits_over(const unsigned K, const float
 }
 
 template <bool WITH_IDX, bool MAPPED, int KC, int NPB>
-__global__ void __launch_bounds__(TILE * 32, NPB == 2 ? 8 : 10) nlist_tile2_kernel(const NlistParams p)
+__global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_tile2_kernel(const NlistParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
