@@ -5,17 +5,15 @@
 // (htf/TensorflowCompute.cu:80-151: one thread per row, 16-byte stores strided by 16*K)
 // and the cudaMemset before it (.cu:180).
 //
-// Work decomposition: one warp per cell.
-//   stage : the positions of the 3x3x3 stencil (9 contiguous runs of the cell-sorted array
-//           when the x-neighbours do not wrap) are copied to shared memory with cp.async;
-//   test  : the rows of the cell are taken four at a time; every lane holds one candidate
-//           per 32-candidate chunk, tests it against the four rows and, on a hit, appends the
-//           candidate's 16-bit index to its own (lane-private) list of that row -- one
-//           predicated store and one predicated add, no ballot / popc / branch;
-//   emit  : per row, an exclusive scan of the lane counts gives every lane its slot range; the
-//           lanes publish "slot -> candidate" in a small shared map, then lane s re-derives d
-//           for slot s, s+32, ... and the row leaves the SM as contiguous coalesced 16-byte
-//           stores, zero padding included -- no memset pass, no partial-sector traffic.
+// Two kernels.  nlist_tile2_kernel (further down) does the work: a block takes TILE y-adjacent
+// cells, one warp each, stages their common neighbourhood once with TMA bulk copies, tests every
+// candidate chunk against two or four rows on the packed fp32 pipe (hits become bits of per-lane
+// masks in registers) and emits each row through a per-warp stage as contiguous 16-byte stores,
+// zero padding included -- no memset pass, no partial-sector traffic.  nlist_build_kernel is the
+// general form (one warp per cell with its own staging buffer, windows for cells of any density,
+// lane-private hit lists in shared memory): it runs as a second, persistent pass over the tiles
+// the tile kernel flagged as too dense for its buffers, and alone when the tile kernel does not
+// apply.
 //
 // Arithmetic is the oracle's, bit for bit: d = p_j - p_i, compare-and-shift minimum image
 // (HOOMD BoxDim::minImage CPU branch), rsq = (dx*dx + dy*dy) + dz*dz with round-to-nearest
@@ -24,7 +22,8 @@
 // half IEEE-rounded like the scalar op); the sums stay scalar because ptxas contracts a
 // packed mul feeding a packed add into FFMA2 even with .rn.
 //
-// Slot order inside a row is lane-major (lane 0's hits in candidate order, then lane 1's, ...):
+// Slot order inside a row is lane-major (lane 0's hits, then lane 1's, ...; within a lane in candidate
+// order in the per-cell kernel, from the last chunk to the first in the tile kernel):
 // deterministic, and as unspecified as the reference's HOOMD-internal order.  When a row has
 // more than K neighbors the slot index wraps modulo K and the last writer wins, exactly like
 // htf/TensorflowCompute.cc:370 (with this kernel's hit order).
@@ -67,18 +66,13 @@ struct NlistParams {
     int *flag_count;            // tiles flagged by this launch's tile kernel (nullptr: unknown, always scan)
     int *flag_count_next;       // the other parity's counter, zeroed by the per-cell kernel for the next launch
     int use_flags;       // per-cell kernel: process only cells of flagged tiles
-    int tile_axis;       // 0: flagged tiles run along x (first tile kernel), 1: along y (second form)
     float4 *out;
     int *idx_out;
     int *count_out;
     int *overflow;
 };
 
-#ifdef HTF_EXP_COLD_NOINLINE
-#define HTF_EMIT_INLINE __noinline__
-#else
 #define HTF_EMIT_INLINE __forceinline__
-#endif
 
 typedef unsigned long long f32x2;
 
@@ -92,11 +86,7 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 __device__ __forceinline__ f32x2 pack2_pinned(float lo, float hi)
 {
     f32x2 r;
-#ifdef HTF_EXP_NOPIN
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-#else
     asm volatile("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-#endif
     return r;
 }
 __device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
@@ -176,10 +166,6 @@ __device__ __forceinline__ float4 lds_f4_ro(unsigned addr)
     float4 v;
     asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
-}
-__device__ __forceinline__ void sts_u16_nb(unsigned addr, unsigned v)
-{
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
 }
 
 struct RowState {
@@ -332,56 +318,8 @@ __device__ HTF_EMIT_INLINE void emit_single_window(const NlistParams &p, unsigne
     __syncwarp();
 }
 
-// Slot phase of the emit: lane s derives (d, type) for slots s, s+32, ... of one row and stores them
-// coalesced.  KCH = K/32 when that is a compile-time-friendly value (fully unrolled, immediate offsets),
-// 0 = generic K.
-template <bool WITH_IDX, int KCH>
-__device__ __forceinline__ void emit_slots(const NlistParams &p, unsigned cand_ws, unsigned idx_base,
-                                           const int *candidx_w, unsigned slotmap_s, const float4 &pi, bool wrap,
-                                           int total, size_t row, int lane)
-{
-    const int K = KCH ? KCH * 32 : p.K;
-    float4 *dst = p.out + row * K + lane;
-    int *idst = WITH_IDX ? p.idx_out + row * K + lane : nullptr;
-    const unsigned sa = slotmap_s + 2u * lane;
-    if (KCH) {
-#pragma unroll
-        for (int i = 0; i < (KCH ? KCH : 1); i++) {
-            const int sl = lane + 32 * i;
-            const bool valid = sl < total;
-            const unsigned ci = valid ? lds_u16(sa + 64u * i) : 0u;      // byte offset; stale map entries are never dereferenced
-            const float4 cd = lds_f4(cand_ws + ci);
-            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
-            if (wrap) {
-                dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
-                dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
-                dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
-            }
-            if (!WITH_IDX || p.out) dst[32 * i] = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (WITH_IDX) idst[32 * i] = valid ? candidx_w[(ci - idx_base) >> 4] : -1;
-        }
-    } else {
-        unsigned sb = sa;
-        for (int sl = lane; sl < K; sl += 32, dst += 32, sb += 64u) {
-            const bool valid = sl < total;
-            const unsigned ci = valid ? lds_u16(sb) : 0u;
-            const float4 cd = lds_f4(cand_ws + ci);
-            float dx = __fsub_rn(cd.x, pi.x), dy = __fsub_rn(cd.y, pi.y), dz = __fsub_rn(cd.z, pi.z);
-            if (wrap) {
-                dz = wrap_axis(dz, -p.g.half[2], p.g.half[2], p.g.L[2]);
-                dy = wrap_axis(dy, -p.g.half[1], p.g.half[1], p.g.L[1]);
-                dx = wrap_axis(dx, -p.g.half[0], p.g.half[0], p.g.L[0]);
-            }
-            if (!WITH_IDX || p.out) *dst = valid ? make_float4(dx, dy, dz, cd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (WITH_IDX) { *idst = valid ? candidx_w[(ci - idx_base) >> 4] : -1; idst += 32; }
-        }
-    }
-}
-
 constexpr int TILE = HTF_TILE;    // cells per block along x in the tile kernel (= warps per block)
-constexpr int NPMAX = 128;        // piece table capacity: (TILE + 2) * 9 <= NPMAX  ->  TILE <= 12
-constexpr int TILE_HDR = (2 * NPMAX + 32) * 4;   // bytes: piece table end[NPMAX] + adj[NPMAX] + colstart[24] + warp totals[8]
-static_assert((TILE + 2) * 9 <= NPMAX && TILE * 32 >= (TILE + 2) * 9 && TILE + 3 <= 24, "tile size");
+static_assert(TILE * 32 >= (TILE + 2) * 9 && TILE + 3 <= 24, "tile size");
 
 // One warp builds all rows of one cell with its own staging buffer (any density: candidates are
 // re-staged in windows when they do not fit).
@@ -640,283 +578,25 @@ __global__ void __launch_bounds__(128) nlist_build_kernel(const NlistParams p)
         if (nflag == 0) return;
     }
     const int nx = p.g.n[0], ny = p.g.n[1];
-    const int tiles_t = ((p.tile_axis ? ny : nx) + TILE - 1) / TILE;
-    const int per_layer = tiles_t * (p.tile_axis ? nx : ny);
+    const int tiles_t = (ny + TILE - 1) / TILE;
+    const int per_layer = tiles_t * nx;
     const int ntiles_win = per_layer * p.g.zcount;                  // tiles of the z-window only
     for (int tw = blockIdx.x * wpb + warp; tw < ntiles_win; tw += gridDim.x * wpb) {
         const int lz = tw / per_layer;
         const int cz = (p.g.z0 + lz) % p.g.n[2];
         const int tile = cz * per_layer + (tw - lz * per_layer);
         if (!p.tile_flag[tile]) continue;
-        if (p.tile_axis) {
-            // tile = (cz * tiles_y + ty) * nx + cx: cells (cx, ty * TILE + c, cz)
-            const int cx = tile % nx, ty = (tile / nx) % tiles_t;
-            for (int c = 0; c < TILE && ty * TILE + c < ny; c++)
-                build_cell<WITH_IDX, MAPPED>(p, (cz * ny + ty * TILE + c) * nx + cx, smem_raw);
-        } else {
-            const int tx = tile % tiles_t, row = tile / tiles_t;        // row = cz * ny + cy
-            for (int c = 0; c < TILE && tx * TILE + c < nx; c++) build_cell<WITH_IDX, MAPPED>(p, row * nx + tx * TILE + c, smem_raw);
-        }
+        // tile = (cz * tiles_y + ty) * nx + cx: cells (cx, ty * TILE + c, cz)
+        const int cx = tile % nx, ty = (tile / nx) % tiles_t;
+        for (int c = 0; c < TILE && ty * TILE + c < ny; c++)
+            build_cell<WITH_IDX, MAPPED>(p, (cz * ny + ty * TILE + c) * nx + cx, smem_raw);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile kernel: one block = TILE x-adjacent cells (one warp each) of one (y,z) cell row.  The block
-// stages the (TILE+2) x 3 x 3 cell neighbourhood ONCE, column-major, so that each warp's 3x3x3
-// stencil is one contiguous window of the shared buffer: per-cell staging traffic drops from 3 to
-// (TILE+2)/TILE columns, the stencil / prefix set-up is paid once per block, and the smaller
-// shared-memory footprint per warp doubles the resident warps.  Tiles whose neighbourhood does
-// not fit (dense clusters) are flagged and left to the per-cell kernel above.
-template <bool WITH_IDX, bool MAPPED>
-__global__ void __launch_bounds__(TILE * 32) nlist_tile_kernel(const NlistParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.K, capB = p.cap_tile, capW = p.cap;
-    int *ptab_end = reinterpret_cast<int *>(smem_raw);          // [NPMAX] inclusive prefix of piece lengths
-    int *ptab_adj = ptab_end + NPMAX;                           // [NPMAX] source slot - staged index
-    int *colstart = ptab_adj + NPMAX;                           // [<= TILE+3] staged offset of each column
-    int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
-    float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE_HDR);
-    int *candidx = reinterpret_cast<int *>(cand + capB + 32);
-    unsigned char *wbase = WITH_IDX ? reinterpret_cast<unsigned char *>(candidx + capB + 32)
-                                    : reinterpret_cast<unsigned char *>(candidx);
-    const size_t per_warp = (size_t)RPP * capW * 2 + (((size_t)K * 2 + 15) & ~(size_t)15);
-    unsigned char *lists = wbase + per_warp * warp;
-    const unsigned lists_s = (unsigned)__cvta_generic_to_shared(lists);
-    const unsigned slotmap_s = lists_s + (unsigned)(RPP * capW * 2);
-    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
-    const unsigned candidx_s = (unsigned)__cvta_generic_to_shared(candidx);
-
-    const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
-    const int tiles_x = gridDim.x;                              // = ceil(nx / TILE)
-    const int tx = blockIdx.x, cy = blockIdx.y;
-    const int cz = (p.g.z0 + (int)blockIdx.z) % nz;            // grid.z = cell layers of the z-window
-    const int bid = (cz * ny + cy) * tiles_x + tx;
-    const int cx0 = tx * TILE;
-    const int nact = min(TILE, nx - cx0);                       // cells of this tile
-    const int nly = min(ny, 3), nlz = min(nz, 3), nyz = nly * nlz;
-    const bool xs = nx >= 3;                                    // x stencil = {c-1, c, c+1}; else every x cell
-    const int ncol = xs ? nact + 2 : nx;
-    const int npieces = ncol * nyz;                             // <= 6 * 9
-
-    // ---- piece table: piece (col, j) = one stencil cell; prefix sums give the staged layout ----
-    int pl = 0, pb = 0;
-    if (tid < npieces) {
-        const int col = tid / nyz, j = tid - col * nyz, jy = j % nly, jz = j / nly;
-        int sx = xs ? cx0 - 1 + col : col;
-        sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
-        int sy = ny <= 3 ? jy : cy + jy - 1;
-        sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
-        int sz = nz <= 3 ? jz : cz + jz - 1;
-        sz = sz < 0 ? sz + nz : (sz >= nz ? sz - nz : sz);
-        const int c0 = (sz * ny + sy) * nx + sx;
-        pb = __ldg(p.cell_start + c0);
-        pl = __ldg(p.cell_start + c0 + 1) - pb;
-    }
-    int incl = pl;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(HTF_FULL, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31 && warp < 4) wtot[warp] = incl;              // totals of pieces [32w, 32w+32)
-    const unsigned stage_bar = (unsigned)__cvta_generic_to_shared(wtot + 4);   // mbarrier of the bulk copies (8-byte aligned)
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stage_bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    for (int w = 0; w < warp && w < 4; w++) incl += wtot[w];
-    if (tid < NPMAX) {
-        ptab_end[tid] = incl;
-        ptab_adj[tid] = pb - (incl - pl);
-        if (tid < npieces && tid % nyz == 0) colstart[tid / nyz] = incl - pl;
-        if (tid == npieces - 1) colstart[ncol] = incl;
-    }
-    __syncthreads();
-    const int mblock = colstart[ncol];
-    bool fits = mblock <= capB;
-    for (int w = 0; w < nact; w++) {
-        const int wl = xs ? colstart[w + 3] - colstart[w] : mblock;
-        fits = fits && wl <= capW;
-    }
-    if (tid == 0) {
-        p.tile_flag[bid] = fits ? 0 : 1;
-        if (!fits && p.flag_count) atomicAdd(p.flag_count, 1);
-    }
-    if (!fits) return;                                          // block-uniform
-    const bool full = (p.row_lo == 0 && p.row_hi == p.n_all);
-    if (!full) {
-        // sharded build: skip the tile (before staging anything) when none of its cells holds a local row
-        bool any = false;
-        if (warp < nact) {
-            const int c = (cz * ny + cy) * nx + cx0 + warp;
-            const int cb_ = __ldg(p.cell_start + c), ce_ = __ldg(p.cell_start + c + 1);
-            for (int s = cb_ + lane; s < ce_; s += 32) {
-                const int o = __ldg(p.sorted_idx + s);
-                any |= (o >= p.row_lo && o < p.row_hi);
-            }
-        }
-        if (!__syncthreads_or(any)) return;
-    }
-
-    // ---- stage the whole neighbourhood once: one TMA bulk copy per piece (a piece = one stencil cell = one
-    //      contiguous run of the cell-sorted positions), issued by the thread that owns the piece's table entry;
-    //      completion is counted in bytes on one mbarrier ----
-    if (tid == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(stage_bar), "r"((unsigned)mblock * 16u) : "memory");
-    if (tid < npieces && pl > 0)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(cand_s + (unsigned)(incl - pl) * 16u), "l"(p.spos + pb), "r"((unsigned)pl * 16u), "r"(stage_bar) : "memory");
-    if (WITH_IDX) {
-        // original indices ride along as 4-byte cp.async (bulk copies need 16-byte granules): warp w takes pieces w, w+TILE, ...
-        for (int q = warp; q < npieces; q += TILE) {
-            const int qend = ptab_end[q], qadj = ptab_adj[q];
-            const int qbeg = q == 0 ? 0 : ptab_end[q - 1];
-            for (int t = qbeg + lane; t < qend; t += 32) cp_async4(candidx_s + (unsigned)t * 4u, p.sorted_idx + (t + qadj));
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-    // 32 sentinels behind the staged data: the last chunk of the last window may read past its end
-    if (warp == 0) cand[mblock + lane] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(stage_bar) : "memory");
-    __syncthreads();
-
-    // ---- one warp per cell of the tile ----
-    if (warp >= nact) return;
-    const int cx = cx0 + warp;
-    const int cell = (cz * ny + cy) * nx + cx;
-    const int b = __ldg(p.cell_start + cell), e = __ldg(p.cell_start + cell + 1);
-    if (e == b) return;
-    if (!full) {
-        bool any = false;
-        for (int s = b + lane; s < e; s += 32) {
-            const int o = __ldg(p.sorted_idx + s);
-            any |= (o >= p.row_lo && o < p.row_hi);
-        }
-        if (!__any_sync(HTF_FULL, any)) return;
-    }
-    const bool wrap = !((nx >= 5 && cx >= 1 && cx <= nx - 2) && (ny >= 5 && cy >= 1 && cy <= ny - 2) &&
-                        (nz >= 5 && cz >= 1 && cz <= nz - 2));
-    const int ws = xs ? colstart[warp] : 0;
-    const int mlen_true = (xs ? colstart[warp + 3] : mblock) - ws;
-    const int mround = (mlen_true + 31) & ~31;
-    // With >= TILE + 2 cells in x, whatever follows the window in the buffer is the x-column two cells away (or
-    // the sentinels): farther than r_cut in x by construction of the grid, so it can never pass the cutoff test
-    // and the "past the end of the window" mask is unnecessary.  With fewer cells in x the columns behind the
-    // window alias the periodic image of the warp's own stencil (nx = 4, 5: column w+4 / w+5 is column w-1 /
-    // the warp's own cell again), so those grids keep the mask.
-    // staged position of this cell's own particles: piece (own column, own (y,z))
-    const int ps = (xs ? warp + 1 : cx) * nyz + (nz <= 3 ? cz : 1) * nly + (ny <= 3 ? cy : 1);
-    const int self_base = (ps == 0 ? 0 : ptab_end[ps - 1]) - ws - b;
-    const float4 *cand_w = cand + ws;
-    const unsigned cand_ws = cand_s + (unsigned)ws * 16u;
-#ifdef HTF_EXP_NOUNROLL
-    const int kch = 0;
-#elif defined(HTF_EXP_UNROLL3)
-    const int kch = (K == 64) ? 2 : (K == 96 ? 3 : 0);
-#else
-    const int kch = (K == 64) ? 2 : 0;          // unrolled slot phase for K = 64; more copies cost more in I-cache
-#endif
-    const int *candidx_w = candidx + ws;
-
-    for (int s0 = b; s0 < e; s0 += RPP) {
-        RowState rs;
-        int orig[RPP];
-        bool anyrow = false;
-        {
-            float px[RPP], py[RPP], pz[RPP];
-#pragma unroll
-            for (int r = 0; r < RPP; r++) {
-                const int s = min(s0 + r, e - 1);
-                const int rel = self_base + s;                       // the row's own particle in the window
-                float4 pi = cand_w[rel];
-                const int o = __ldg(p.sorted_idx + s);               // needed for the row address anyway
-                const bool ok = (s0 + r < e) && o >= p.row_lo && o < p.row_hi;
-                orig[r] = ok ? o : -1;
-                if (!ok) pi = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);       // never hits
-                px[r] = pi.x; py[r] = pi.y; pz[r] = pi.z; rs.t[r] = pi.w;
-                rs.self_addr[r] = ok ? cand_ws + (unsigned)rel * 16u : 0xffffffffu;
-                rs.lp[r] = lists_s + (unsigned)(r * capW + lane) * 2u;
-                anyrow |= ok;
-            }
-            if (!anyrow) continue;
-#pragma unroll
-            for (int h = 0; h < RPP / 2; h++) {
-                rs.x[h] = pack2_pinned(px[2 * h], px[2 * h + 1]);
-                rs.y[h] = pack2_pinned(py[2 * h], py[2 * h + 1]);
-                rs.z[h] = pack2_pinned(pz[2 * h], pz[2 * h + 1]);
-            }
-        }
-#ifdef HTF_EXP_MASKALL
-        if (!wrap) test_window<false, MAPPED, true, true>(p, cand_ws, mround, mlen_true, rs, lane);
-        else test_window<true, MAPPED, true, true>(p, cand_ws, mround, mlen_true, rs, lane);
-#else
-        if (!wrap) test_window<false, MAPPED, false, true>(p, cand_ws, mround, mround, rs, lane);
-        else if (nx >= TILE + 2) test_window<true, MAPPED, false, true>(p, cand_ws, mround, mround, rs, lane);
-        else test_window<true, MAPPED, true, true>(p, cand_ws, mround, mlen_true, rs, lane);
-#endif
-        __syncwarp();
-
-        // ---- emit the batch.  Lane counts of two rows share one 32-bit scan (16 bits each). ----
-        int cl[RPP], excl[RPP], tot[RPP];
-#pragma unroll
-        for (int r = 0; r < RPP; r++) cl[r] = (int)((rs.lp[r] - (lists_s + (unsigned)(r * capW + lane) * 2u)) >> 6);
-#pragma unroll
-        for (int h = 0; h < RPP / 2; h++) {
-            const unsigned packed = (unsigned)cl[2 * h] | ((unsigned)cl[2 * h + 1] << 16);
-            unsigned inc = packed;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(HTF_FULL, inc, o);
-                if (lane >= o) inc += t;
-            }
-            const unsigned all = __shfl_sync(HTF_FULL, inc, 31);
-            const unsigned ex = inc - packed;
-            excl[2 * h] = (int)(ex & 0xffffu); excl[2 * h + 1] = (int)(ex >> 16);
-            tot[2 * h] = (int)(all & 0xffffu); tot[2 * h + 1] = (int)(all >> 16);
-        }
-#pragma unroll
-        for (int r = 0; r < RPP; r++) {
-            if (orig[r] < 0) continue;                                   // warp-uniform
-            const unsigned list_s = lists_s + (unsigned)(r * capW + lane) * 2u;
-            const int total = tot[r];
-            const size_t row = (size_t)(orig[r] - p.row_lo);
-            if (total > K) {
-                // overflowing row: modulo-K rule of htf/TensorflowCompute.cc:370 (cold path)
-                const float4 pi = cand_w[self_base + s0 + r];
-                emit_single_window<WITH_IDX>(p, 0u, cand_ws, candidx_w, slotmap_s, list_s, cl[r], wrap, pi, orig[r], lane);
-                continue;
-            }
-            // slot -> candidate map: slots [0,total) are exactly the hits, lane-major
-            const unsigned qa = slotmap_s + (unsigned)excl[r] * 2u;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (k < cl[r]) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
-            if (__any_sync(HTF_FULL, cl[r] > 4))
-                for (int k = 4; k < cl[r]; k++) sts_u16(qa + 2u * k, lds_u16(list_s + 64u * k));
-            __syncwarp();
-            const float4 pi = lds_f4(cand_ws + (unsigned)(self_base + s0 + r) * 16u);
-            if (kch == 2) emit_slots<WITH_IDX, 2>(p, 0u, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
-#ifdef HTF_EXP_UNROLL3
-            else if (kch == 3) emit_slots<WITH_IDX, 3>(p, 0u, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
-#endif
-            else emit_slots<WITH_IDX, 0>(p, 0u, cand_ws, candidx_w, slotmap_s, pi, wrap, total, row, lane);
-            if (lane == 0 && (p.count_out != nullptr || total == K)) {
-                if (p.count_out) p.count_out[row] = total;
-                if (total == K && p.overflow) atomicMax(p.overflow, total);
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Tile kernel, second form.  Same block shape (TILE cells, one warp each, the shared neighbourhood
-// staged once by TMA), with three changes that cut warp instructions per row:
+// Tile kernel (second form; the first one -- tiles along x, one bulk copy per stencil cell, hits appended to
+// lane-private lists in shared memory -- needed 339 warp instructions per row against 255).  One block = TILE
+// y-adjacent cells (one warp each) whose shared neighbourhood is staged once by TMA:
 //   * the tile runs along y, so that the three x cells of a stencil row are ONE contiguous run of the
 //     cell-sorted array: (TILE+2) x 3 bulk copies per block instead of (TILE+2) x 9;
 //   * hits are not appended to lists in shared memory: every lane keeps one 32-bit mask per row, bit k =
@@ -1119,7 +799,6 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
     int *colstart = ptab_adj + NP2;                           // [<= TILE+3] staged offset of each column
     int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
     float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE2_HDR);
-    int *candidx = reinterpret_cast<int *>(cand + capB + 32);
     const unsigned istage_bytes = WITH_IDX ? (unsigned)(((size_t)2 * (KC ? KC : p.K) * 4 + 15) & ~(size_t)15) : 0u;
     const unsigned per_warp = 2u * (unsigned)(KC ? KC : p.K) * 16u + istage_bytes;
     // one opaque base register: otherwise every shared address below is re-derived from SR_CgaCtaId where it is used
@@ -1460,29 +1139,6 @@ size_t tile2_block_bytes(int capB, int K, bool with_idx)
 }
 
 template <bool WITH_IDX, bool MAPPED>
-cudaError_t launch_tile_variant(const NlistParams &p, dim3 grid, size_t smem, cudaStream_t st)
-{
-    static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // the attribute is per device
-    size_t &configured = configured_dev[htf_current_device_slot()];
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(nlist_tile_kernel<WITH_IDX, MAPPED>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    nlist_tile_kernel<WITH_IDX, MAPPED><<<grid, TILE * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-size_t tile_block_bytes(int capB, int capW, int K, bool with_idx)
-{
-    size_t b = TILE_HDR + (size_t)(capB + 32) * 16;
-    if (with_idx) b += (size_t)(capB + 32) * 4;
-    b += (size_t)TILE * ((size_t)RPP * capW * 2 + (((size_t)K * 2 + 15) & ~(size_t)15));
-    return b;
-}
-
-template <bool WITH_IDX, bool MAPPED>
 cudaError_t launch_variant(const NlistParams &p, int grid, int wpb, size_t smem, cudaStream_t st)
 {
     static size_t configured_dev[HTF_MAX_DEVICES] = {0};   // per instantiation and device: largest dynamic smem opted in so far
@@ -1574,17 +1230,14 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     cudaError_t e;
 
     // ---- pass 1: the tile kernel ----
-    const int tiles_x = (g.n[0] + TILE - 1) / TILE;
-    const int ntiles = tiles_x * g.n[1] * g.n[2];
     p.use_flags = 0;
     p.tile_flag = nullptr;
     p.flag_count = nullptr;
     p.flag_count_next = nullptr;
-    p.tile_axis = 0;
     bool tiled = false;
-    static const int tile_form = [] { const char *e = getenv("HTF_TILE_KERNEL"); return e ? atoi(e) : 2; }();
-    if (tile_form == 2) {
-        // second form: tiles along y, hit masks in registers (see nlist_tile2_kernel)
+    static const bool tile_off = [] { const char *e = getenv("HTF_TILE_KERNEL"); return e && atoi(e) == 0; }();   // 0: per-cell kernel only
+    if (!tile_off) {
+        // tiles along y, hit masks in registers (see nlist_tile2_kernel)
         const int tiles_y = (g.n[1] + TILE - 1) / TILE;
         const int ncol = g.n[1] >= 3 ? min(TILE, g.n[1]) + 2 : g.n[1];
         const double bmean = (double)ncol * min(g.n[0], 3) * min(g.n[2], 3) * cell_mean;
@@ -1597,7 +1250,6 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             if ((e = htf_ensure_tile_flags(ctx, ntiles2)) != cudaSuccess) return e;
             p.cap = cap;
             p.cap_tile = capB;
-            p.tile_axis = 1;
             p.tile_flag = ctx->d_tile_flag;
             lane &= 1;
             p.flag_count = ctx->d_flag_count + 2 * lane + (ctx->flag_parity[lane] & 1);
@@ -1616,34 +1268,6 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
             tiled = true;
         }
     }
-    if (!tiled) {
-        const int ncol = g.n[0] >= 3 ? min(TILE, g.n[0]) + 2 : g.n[0];
-        const double bmean = (double)ncol * min(g.n[1], 3) * min(g.n[2], 3) * cell_mean;
-        int capB = (int)(bmean + 5.0 * sqrt(bmean > 1.0 ? bmean : 1.0)) + 32;
-        capB = (capB + 31) / 32 * 32;
-        const size_t bytes = tile_block_bytes(capB, cap, p.K, with_idx);
-        // list entries are 16-bit shared-memory addresses: the whole block must stay below 64 KB (else per-cell only)
-        if (capB <= 4064 && bytes <= 64 * 1024 && g.n[1] <= 65535 && g.n[2] <= 65535) {
-            if ((e = htf_ensure_tile_flags(ctx, ntiles)) != cudaSuccess) return e;
-            p.cap = cap;
-            p.cap_tile = capB;
-            p.tile_flag = ctx->d_tile_flag;
-            // two counters in turn: this launch counts into one, its per-cell pass zeroes the other for the next launch
-            lane &= 1;
-            p.flag_count = ctx->d_flag_count + 2 * lane + (ctx->flag_parity[lane] & 1);
-            p.flag_count_next = ctx->d_flag_count + 2 * lane + ((ctx->flag_parity[lane] + 1) & 1);
-            ctx->flag_parity[lane] ^= 1;
-            ctx->launches += 1;
-            const dim3 tg((unsigned)tiles_x, (unsigned)g.n[1], (unsigned)p.g.zcount);
-            e = with_idx ? (mapped ? launch_tile_variant<true, true>(p, tg, bytes, st)
-                                   : launch_tile_variant<true, false>(p, tg, bytes, st))
-                         : (mapped ? launch_tile_variant<false, true>(p, tg, bytes, st)
-                                   : launch_tile_variant<false, false>(p, tg, bytes, st));
-            if (e != cudaSuccess) return e;
-            tiled = true;
-        }
-    }
-
     // ---- pass 2: per-cell kernel; after the tile kernel it only walks the tiles that were flagged ----
     p.use_flags = tiled ? 1 : 0;
     int wpb = 4;
@@ -1659,7 +1283,7 @@ cudaError_t htf_launch_nlist(htf_ctx *ctx, int64_t row_lo, int64_t row_hi, float
     const size_t smem = per_warp_bytes(cap, p.K, with_idx) * wpb;
     int grid = (g.n[0] * g.n[1] * p.g.zcount + wpb - 1) / wpb;
     if (tiled) {                                                                                 // persistent flag scan
-        const int ntw = (p.tile_axis ? (g.n[1] + TILE - 1) / TILE * g.n[0] : tiles_x * g.n[1]) * p.g.zcount;
+        const int ntw = (g.n[1] + TILE - 1) / TILE * g.n[0] * p.g.zcount;
         grid = min((ntw + wpb - 1) / wpb, 2 * ctx->sm_count);
     }
     ctx->launches += 1;

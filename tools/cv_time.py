@@ -9,7 +9,8 @@ pos, lo, hi, r_cut, K = synthetic.config(name)
 n = pos.shape[0]
 ctx = htf.HtfContext(n, K, r_cut); ctx.set_box(lo, hi)
 d = torch.from_numpy(pos).cuda()
-nl = ctx.build_nlist(d)
+nl, cnt = ctx.build_nlist(d, want_count=True)
+print('mean count %.1f of K=%d' % (float(cnt.float().mean()), K))
 fe = torch.empty((n, 4), device="cuda"); vir = torch.empty((n, 6), device="cuda")
 cv_row = torch.empty((n, 4), device="cuda"); cv_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
 bins = torch.zeros(102, dtype=torch.int64, device="cuda")
@@ -25,6 +26,10 @@ for label, fn in (("lj", lambda: ctx.lj_forces(nl, out=fe)),
                   ("lj+cv", lambda: ctx.lj_cv_forces(nl, 1.3, cv_row, cv_sum)),
                   ("lj+cv+rdf", lambda: ctx.lj_cv_forces(nl, 1.3, cv_row, cv_sum, bins=bins, r_range=(0.0, r_cut), nbins=100)),
                   ("lj+rdf", lambda: ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100)),
-                  ("rdf only", lambda: ctx.rdf_hist(nl, (0.0, r_cut), 100, bins=bins))):
+                  ("rdf only", lambda: ctx.rdf_hist(nl, (0.0, r_cut), 100, bins=bins)),
+                  ("lj+vir      [counts]", lambda: ctx.lj_forces(nl, virial=True, out=fe, virial_out=vir, counts=cnt)),
+                  ("lj+cv       [counts]", lambda: ctx.lj_cv_forces(nl, 1.3, cv_row, cv_sum, counts=cnt)),
+                  ("lj+cv+rdf   [counts]", lambda: ctx.lj_cv_forces(nl, 1.3, cv_row, cv_sum, bins=bins, r_range=(0.0, r_cut), nbins=100, counts=cnt)),
+                  ("lj+rdf      [counts]", lambda: ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100, counts=cnt))):
     ms = timeit(fn)
-    print("%-10s %.3f ms  %.0f GB/s" % (label, ms, gb / ms))
+    print("%-22s %.3f ms  %.0f GB/s" % (label, ms, gb / ms))

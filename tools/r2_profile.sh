@@ -13,7 +13,10 @@ timeout 300 $F -k regex:mlp_train_kernel -s 1 -c 1 -f -o gpurun_out/r2_train pyt
 timeout 300 $F -k regex:mlp_force_kernel -s 1 -c 1 -f -o gpurun_out/r2_mlp python bench.py --model mlp --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-graph > /dev/null 2>&1
 timeout 300 $F -k regex:pair_pass_kernel -s 1 -c 1 -f -o gpurun_out/r2_pair python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-graph > /dev/null 2>&1
 timeout 300 $F -k regex:pair_pass_kernel -s 1 -c 1 -f -o gpurun_out/r2_pair_cv python bench.py --workload cfg5 --model eds --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-graph > /dev/null 2>&1
-for n in r2_train r2_mlp r2_pair r2_pair_cv; do
+timeout 300 $F -k regex:nlist_tile2 -s 1 -c 1 -f -o gpurun_out/r2_tile python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-graph > /dev/null 2>&1
+timeout 300 $F -k regex:nlist_tile2 -s 1 -c 1 -f -o gpurun_out/r2_tile_cfg5 python bench.py --workload cfg5 --model eds --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-graph > /dev/null 2>&1
+ncu -i gpurun_out/r2_tile.ncu-rep --page source --csv > gpurun_out/r2_tile_src.csv 2>/dev/null
+for n in r2_train r2_mlp r2_pair r2_pair_cv r2_tile r2_tile_cfg5; do
   ncu -i gpurun_out/$n.ncu-rep --page raw --csv > gpurun_out/${n}_raw.csv 2>/dev/null
 done
 ls -la gpurun_out/*.ncu-rep gpurun_out/r2_launches*.csv
