@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
     }
     const long long groups = (nrows + RPW - 1) / RPW;       // one warp-iteration = RPW rows
     for (long long gi = (long long)blockIdx.x * WARPS + warp; gi < groups; gi += (long long)gridDim.x * WARPS) {
-        long long row = gi * RPW + lane / LPR;
+        // plain mode walks the rows from the last to the first: with spatially coherent particle order the rows the
+        // builder wrote last are still in the 126 MB L2 (measured: 188.7 -> 186.3 us at 1 M x 64)
+        long long row = (p.row_map ? gi : groups - 1 - gi) * RPW + lane / LPR;
         bool active = row < nrows;
         if (p.row_map) {
             const long long o = active ? (long long)__ldg(p.row_map + slot0 + row) : -1;

@@ -799,16 +799,19 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
     int *colstart = ptab_adj + NP2;                           // [<= TILE+3] staged offset of each column
     int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
     float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE2_HDR);
-    const unsigned istage_bytes = WITH_IDX ? (unsigned)(((size_t)2 * (KC ? KC : p.K) * 4 + 15) & ~(size_t)15) : 0u;
-    const unsigned per_warp = 2u * (unsigned)(KC ? KC : p.K) * 16u + istage_bytes;
+    // rows in the per-warp stage: two for K = 64 (both rows of a pair are emitted between one pair of warp barriers);
+    // one otherwise -- at K = 96 the two-row stage (3 KB per warp) held the kernel at 6 blocks per SM
+    constexpr unsigned RS = (KC == 64) ? 2u : 1u;
+    const unsigned istage_bytes = WITH_IDX ? (unsigned)(((size_t)RS * (KC ? KC : p.K) * 4 + 15) & ~(size_t)15) : 0u;
+    const unsigned per_warp = RS * (unsigned)(KC ? KC : p.K) * 16u + istage_bytes;
     // one opaque base register: otherwise every shared address below is re-derived from SR_CgaCtaId where it is used
     unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
     asm volatile("mov.u32 %0, %0;" : "+r"(smem_s));
     const unsigned cand_s = smem_s + (unsigned)TILE2_HDR;
     const unsigned candidx_s = cand_s + (unsigned)(capB + 32) * 16u;
-    unsigned stage_s = (WITH_IDX ? candidx_s + (unsigned)(capB + 32) * 4u : candidx_s) + per_warp * (unsigned)warp;   // [2][K] float4
+    unsigned stage_s = (WITH_IDX ? candidx_s + (unsigned)(capB + 32) * 4u : candidx_s) + per_warp * (unsigned)warp;   // [RS][K] float4
     asm volatile("mov.u32 %0, %0;" : "+r"(stage_s));
-    const unsigned istage_s = stage_s + 2u * (unsigned)(KC ? KC : p.K) * 16u;                                      // [2][K] int
+    const unsigned istage_s = stage_s + RS * (unsigned)(KC ? KC : p.K) * 16u;                                      // [RS][K] int
 
     const int nx = p.g.n[0], ny = p.g.n[1], nz = p.g.n[2];
     const int tiles_y = gridDim.y;                              // = ceil(ny / TILE)
@@ -1047,12 +1050,15 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
                 float px[2], py[2], pz[2];                      // the register halves of the packed rows: no moves
                 unpack2(rp[h].x, px[0], px[1]); unpack2(rp[h].y, py[0], py[1]); unpack2(rp[h].z, pz[0], pz[1]);
                 const unsigned tot[2] = {all[h] & 0xffffu, all[h] >> 16};
-                __syncwarp();                                   // the previous pair's slot phase has left the row stage
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
+                for (int g = 0; g < 2 / (int)RS; g++) {         // RS = 2: both rows at once; RS = 1: row by row
+                __syncwarp();                                   // the previous slot phase has left the row stage
+#pragma unroll
+                for (int rr = 0; rr < (int)RS; rr++) {
+                    const int r = g * (int)RS + rr;
                     if (o[2 * h + r] < 0) continue;             // warp-uniform
                     const unsigned q = r ? (ex[h] >> 16) : (ex[h] & 0xffffu);
-                    const unsigned st_r = stage_s + (r ? rowbytes : 0u), ist_r = istage_s + (r ? (unsigned)K * 4u : 0u);
+                    const unsigned st_r = stage_s + (rr ? rowbytes : 0u), ist_r = istage_s + (rr ? (unsigned)K * 4u : 0u);
                     if (tot[r] <= (unsigned)K) {
                         if (!wrap) emit_own_hits<WITH_IDX, false>(p, m[2 * h + r], st_r + q * 16u, ist_r + q * 4u, lane_cand, cand_s, candidx_s, px[r], py[r], pz[r]);
                         else emit_own_hits<WITH_IDX, true>(p, m[2 * h + r], st_r + q * 16u, ist_r + q * 4u, lane_cand, cand_s, candidx_s, px[r], py[r], pz[r]);
@@ -1064,13 +1070,14 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
                 }
                 __syncwarp();
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
+                for (int rr = 0; rr < (int)RS; rr++) {
+                    const int r = g * (int)RS + rr;
                     const int orig = o[2 * h + r];
                     if (orig < 0) continue;                      // warp-uniform
                     const int total = (int)tot[r];
                     const int nvalid = min(total, K);
                     const unsigned row = (unsigned)(orig - p.row_lo);
-                    const unsigned st_r = st_lane + (r ? rowbytes : 0u), ist_r = ist_lane + (r ? (unsigned)K * 4u : 0u);
+                    const unsigned st_r = st_lane + (rr ? rowbytes : 0u), ist_r = ist_lane + (rr ? (unsigned)K * 4u : 0u);
                     if (KC && !WITH_IDX) {
                         const unsigned long long dsta = out_lane_a + (unsigned long long)row * (unsigned long long)(KC * 16);
 #pragma unroll
@@ -1097,6 +1104,7 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
                         if (need_count) p.count_out[row] = total;
                         if (total >= K && p.overflow) atomicMax(p.overflow, total);
                     }
+                }
                 }
             }
         }
@@ -1134,7 +1142,8 @@ size_t tile2_block_bytes(int capB, int K, bool with_idx)
 {
     size_t b = TILE2_HDR + (size_t)(capB + 32) * 16;
     if (with_idx) b += (size_t)(capB + 32) * 4;
-    b += (size_t)TILE * ((size_t)2 * K * 16 + (with_idx ? (((size_t)2 * K * 4 + 15) & ~(size_t)15) : 0));
+    const size_t rs = (K == 64 && !with_idx) ? 2 : 1;          // rows in the per-warp stage (see the kernel)
+    b += (size_t)TILE * (rs * K * 16 + (with_idx ? ((rs * K * 4 + 15) & ~(size_t)15) : 0));
     return b;
 }
 
