@@ -799,9 +799,9 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_
     int *colstart = ptab_adj + NP2;                           // [<= TILE+3] staged offset of each column
     int *wtot = colstart + 24;                                  // [4] piece-length totals of warps 0..3
     float4 *cand = reinterpret_cast<float4 *>(smem_raw + TILE2_HDR);
-    // rows in the per-warp stage: two for K = 64 (both rows of a pair are emitted between one pair of warp barriers);
-    // one otherwise -- at K = 96 the two-row stage (3 KB per warp) held the kernel at 6 blocks per SM
-    constexpr unsigned RS = (KC == 64) ? 2u : 1u;
+    // rows in the per-warp stage.  One: a two-row stage (both rows of a pair emitted between one pair of warp barriers)
+    // is no faster at K = 64 (0.363 vs 0.361 ms) and at K = 96 (3 KB per warp) it held the kernel at 6 blocks per SM
+    constexpr unsigned RS = 1u;
     const unsigned istage_bytes = WITH_IDX ? (unsigned)(((size_t)RS * (KC ? KC : p.K) * 4 + 15) & ~(size_t)15) : 0u;
     const unsigned per_warp = RS * (unsigned)(KC ? KC : p.K) * 16u + istage_bytes;
     // one opaque base register: otherwise every shared address below is re-derived from SR_CgaCtaId where it is used
@@ -1142,7 +1142,7 @@ size_t tile2_block_bytes(int capB, int K, bool with_idx)
 {
     size_t b = TILE2_HDR + (size_t)(capB + 32) * 16;
     if (with_idx) b += (size_t)(capB + 32) * 4;
-    const size_t rs = (K == 64 && !with_idx) ? 2 : 1;          // rows in the per-warp stage (see the kernel)
+    const size_t rs = 1;                                        // rows in the per-warp stage (see the kernel)
     b += (size_t)TILE * (rs * K * 16 + (with_idx ? ((rs * K * 4 + 15) & ~(size_t)15) : 0));
     return b;
 }
