@@ -42,6 +42,9 @@ namespace {
 #ifndef HTF_RPP
 #define HTF_RPP 2
 #endif
+#ifndef HTF_T2_WARPS2
+#define HTF_T2_WARPS2 32      // resident warps per SM the two-pair form of the tile kernel is compiled for (63 registers)
+#endif
 #ifndef HTF_TILE
 #define HTF_TILE 4
 #endif
@@ -789,7 +792,7 @@ __device__ __forceinline__ void emit_own_hits_over(const unsigned K, const float
 }
 
 template <bool WITH_IDX, bool MAPPED, int KC, int NPB>
-__global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? 32 : 40) / TILE) nlist_tile2_kernel(const NlistParams p)
+__global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? HTF_T2_WARPS2 : 40) / TILE) nlist_tile2_kernel(const NlistParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
