@@ -415,7 +415,8 @@ def measure(args, env, scaling, full):
         skin_state = {"t": 0, "rebuilds": 0}
 
     # the builder's neighbors-per-row ride along to the pair pass, which then reads only each row's valid slots
-    cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if (args.counts and not skin) else None
+    # (--model mlp always takes them: its compaction pre-pass then reads 4 bytes per row instead of the tensor twice)
+    cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if ((args.counts or args.model == "mlp") and not skin) else None
     if eds_model is not None:
         eds_model.row_counts = cnt
 
@@ -457,7 +458,7 @@ def measure(args, env, scaling, full):
         elif eds_model is not None:
             eds_model.compute(nl, None, None)                         # fused LJ + CV + RDF pass, all-reduces, EDS update, bias
         elif packed is not None:
-            ctx.mlp_forces(nl, packed, r_cut, out=fe)
+            ctx.mlp_forces(nl, packed, r_cut, out=fe, counts=cnt)
         elif bins is not None:
             bins.zero_()
             ctx.lj_step_forces_only(nl, fe, vir, bins, (0.0, r_cut), 100, counts=cnt)

@@ -750,8 +750,8 @@ int htf_mlp_pack(htf_ctx *ctx, const float *d_raw, void *d_packed, void *stream)
     return HTF_OK;
 }
 
-int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const void *d_packed, float rbf_high,
-                   float *d_force_energy, void *stream)
+int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const int32_t *d_row_count, const void *d_packed,
+                   float rbf_high, float *d_force_energy, void *stream)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
@@ -762,7 +762,7 @@ int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, cons
     DeviceGuard guard(ctx->device);
     HTF_CUDA(ctx, htf_launch_mlp(ctx, reinterpret_cast<const float4 *>(d_nlist), rows, k,
                                  reinterpret_cast<const unsigned char *>(d_packed), rbf_high,
-                                 reinterpret_cast<float4 *>(d_force_energy), (cudaStream_t)stream));
+                                 reinterpret_cast<float4 *>(d_force_energy), (cudaStream_t)stream, d_row_count));
     return HTF_OK;
 }
 

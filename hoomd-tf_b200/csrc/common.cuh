@@ -166,7 +166,7 @@ int htf_mlp_packed_bytes_host();
 int htf_mlp_raw_count_host();
 cudaError_t htf_launch_mlp_pack(htf_ctx *ctx, const float *raw, unsigned char *packed, cudaStream_t st);
 cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const unsigned char *packed,
-                           float rbf_high, float4 *fe, cudaStream_t st);
+                           float rbf_high, float4 *fe, cudaStream_t st, const int32_t *row_count = nullptr);
 
 // pairwise-MLP training step (mlp_train.cu)
 int htf_mlp_train_partial_floats(int sm_count);

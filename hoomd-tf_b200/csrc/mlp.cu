@@ -583,6 +583,60 @@ __global__ void __launch_bounds__(256) mlp_scatter_kernel(const float4 *__restri
     }
 }
 
+// ---- the same compaction from the builder's per-row neighbor counts: the valid slots of a row are its first
+//      min(count, K), so neither pass reads the padding (the pre-pass drops from two reads + one write of the
+//      tensor to 4 bytes per row + one read and one write of the valid slots) ----
+constexpr int CR_ROWS = 64;             // rows per block of the row-wise kernels (8 warps x 8 rows)
+
+__global__ void __launch_bounds__(256) mlp_rowsum_kernel(const int *__restrict__ row_count, long long rows, int K,
+                                                         int *__restrict__ blk_cnt)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per block of CR_ROWS rows
+    const long long r0 = b * CR_ROWS;
+    if (r0 >= rows) return;
+    int t = 0;
+    for (int i = 0; i < CR_ROWS && r0 + i < rows; i++) t += min(__ldg(row_count + r0 + i), K);
+    blk_cnt[b] = t;
+}
+
+__global__ void __launch_bounds__(256) mlp_rowscatter_kernel(const float4 *__restrict__ nlist, const int *__restrict__ row_count,
+                                                             long long rows, int K, const int *__restrict__ blk_off,
+                                                             float4 *__restrict__ out)
+{
+    __shared__ int s_off[CR_ROWS + 1];
+    const long long r0 = (long long)blockIdx.x * CR_ROWS;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (w < 2) {                                            // offsets of the block's rows: two 32-lane scans
+        const long long r = r0 + threadIdx.x;
+        const int c = r < rows ? min(__ldg(row_count + r), K) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HTF_FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        s_off[1 + threadIdx.x] = incl;                      // inclusive within the half; the second half is shifted below
+    }
+    if (threadIdx.x == 0) s_off[0] = 0;
+    __syncthreads();
+    const int half = s_off[32];
+    __syncthreads();
+    if (w == 1) s_off[1 + threadIdx.x] += half;
+    __syncthreads();
+    const int base = blk_off[blockIdx.x];
+    for (int i = w; i < CR_ROWS; i += 8) {                  // a warp copies a row's valid slots, 32 at a time
+        const long long r = r0 + i;
+        if (r >= rows) break;
+        const int o = s_off[i], c = s_off[i + 1] - o;
+        const float4 *src = nlist + r * K;
+        for (int j = lane; j < c; j += 32) {
+            float4 v = __ldg(src + j);
+            v.w = __int_as_float((int)r);
+            out[base + o + j] = v;
+        }
+    }
+}
+
 }  // namespace
 
 int htf_mlp_packed_bytes_host() { return MLP_PACKED_BYTES; }
@@ -596,7 +650,7 @@ cudaError_t htf_launch_mlp_pack(htf_ctx *ctx, const float *raw, unsigned char *p
 }
 
 cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int K, const unsigned char *packed,
-                           float rbf_high, float4 *fe, cudaStream_t st)
+                           float rbf_high, float4 *fe, cudaStream_t st, const int32_t *row_count)
 {
     if (rows <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(fe, 0, sizeof(float4) * (size_t)rows, st);
@@ -605,7 +659,8 @@ cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
     const long long slots = (long long)rows * K;
     bool compact = slots >= (1ll << 20) && slots < (1ll << 31);
     if (const char *env = getenv("HTF_MLP_COMPACT")) compact = atoi(env) != 0 && slots < (1ll << 31);
-    const int nb = (int)((slots + CP_BLOCK - 1) / CP_BLOCK);
+    const bool by_rows = compact && row_count != nullptr;
+    const int nb = by_rows ? (int)((rows + CR_ROWS - 1) / CR_ROWS) : (int)((slots + CP_BLOCK - 1) / CP_BLOCK);
     if (compact) {
         if (slots + MLP_TM > ctx->mlp_pairs_cap) {
             if (ctx->d_mlp_pairs) cudaFree(ctx->d_mlp_pairs);
@@ -620,9 +675,11 @@ cudaError_t htf_launch_mlp(htf_ctx *ctx, const float4 *nlist, int64_t rows, int 
             ctx->mlp_blk_cap = nb + 2;
         }
         long long *total = reinterpret_cast<long long *>(ctx->d_mlp_blk + ((nb + 2 + 1) / 2) * 2);   // 8-byte aligned tail
-        mlp_count_kernel<<<nb, 256, 0, st>>>(nlist, slots, ctx->d_mlp_blk);
+        if (by_rows) mlp_rowsum_kernel<<<(nb + 255) / 256, 256, 0, st>>>(row_count, rows, K, ctx->d_mlp_blk);
+        else mlp_count_kernel<<<nb, 256, 0, st>>>(nlist, slots, ctx->d_mlp_blk);
         mlp_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_mlp_blk, nb, total);
-        mlp_scatter_kernel<<<nb, 256, 0, st>>>(nlist, slots, K, ctx->d_mlp_blk, ctx->d_mlp_pairs);
+        if (by_rows) mlp_rowscatter_kernel<<<nb, 256, 0, st>>>(nlist, row_count, rows, K, ctx->d_mlp_blk, ctx->d_mlp_pairs);
+        else mlp_scatter_kernel<<<nb, 256, 0, st>>>(nlist, slots, K, ctx->d_mlp_blk, ctx->d_mlp_pairs);
         ctx->launches += 3;
     }
     static bool configured_dev[HTF_MAX_DEVICES] = {false};  // the attribute is per device

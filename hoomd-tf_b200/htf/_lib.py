@@ -43,7 +43,7 @@ SYMBOLS = {
     "htf_lj_cv_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _i32, _vp]),
     "htf_mlp_param_sizes": (_i32, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "htf_mlp_pack": (_i32, [_vp, _vp, _vp, _vp]),
-    "htf_mlp_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _f32, _vp, _vp]),
+    "htf_mlp_forces": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
     "htf_rdf_hist": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _f32, _f32, _i32, _i32, _i32, _vp, _vp]),
     "htf_lj_step": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i32, _vp]),
     "htf_unstuff4": (_i32, [_vp, _vp, _vp, _i64, _vp]),

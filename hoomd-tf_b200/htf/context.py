@@ -273,14 +273,16 @@ class HtfContext:
         self._ck(self.lib.htf_mlp_pack(self._h, _ptr(raw), _ptr(packed), self._stream()))
         return packed
 
-    def mlp_forces(self, nlist, packed, rbf_high, out=None):
-        """Pairwise-MLP forces+energy [rows,4] on the tensor cores (tcgen05)."""
+    def mlp_forces(self, nlist, packed, rbf_high, out=None, counts=None):
+        """Pairwise-MLP forces+energy [rows,4] on the tensor cores (tcgen05).  ``counts`` int32[rows] (the builder's
+        neighbors per row) makes the compaction pre-pass of large tensors read only the valid slots."""
         _check_dev_f32(nlist, "nlist", 4)
         rows, k = nlist.shape[0], nlist.shape[1]
+        _check_counts(counts, rows)
         if out is None:
             out = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.htf_mlp_forces(self._h, _ptr(nlist), rows, int(k), _ptr(packed), float(rbf_high), _ptr(out),
-                                         self._stream()))
+        self._ck(self.lib.htf_mlp_forces(self._h, _ptr(nlist), rows, int(k), _ptr(counts), _ptr(packed), float(rbf_high),
+                                         _ptr(out), self._stream()))
         return out
 
     def mlp_train_grads(self, nlist, raw, rbf_high, labels, n_total=None, grads=None, pred=None, loss=None):

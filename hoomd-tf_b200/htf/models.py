@@ -294,9 +294,10 @@ class EDSCoordinationModel(SimModel):
         cv = (cv_sum / n).to(torch.float32)[0]
         self.cv_avg.update_state(cv)
         alpha = self.eds_bias(cv)
-        scale = (alpha / n.to(torch.float32))[0]
-        # one contiguous pass: (F, e) += (2 s, 2 s, 2 s, s) * (grad sums, cn)
-        forces = torch.addcmul(fe, cv_row, torch.stack([2.0 * scale, 2.0 * scale, 2.0 * scale, scale]), out=out)
+        if getattr(self, "_coef4", None) is None or self._coef4.device != fe.device:
+            self._coef4 = torch.tensor([2.0, 2.0, 2.0, 1.0], dtype=torch.float32, device=fe.device)
+        # one contiguous pass: (F, e) += (2 s, 2 s, 2 s, s) * (grad sums, cn),  s = alpha / N
+        forces = torch.addcmul(fe, cv_row, self._coef4 * (alpha / n.to(torch.float32))[0], out=out)
         if bins is not None:
             self.last_bins = bins
             rdf, _ = rdf_from_hist(bins, self.rdf_range, self.nbins)

@@ -259,10 +259,16 @@ def compute_rdf(nlist, r_range, type_tensor=None, nbins=100, type_i=None, type_j
     return rdf_from_hist(hist, r_range, nbins)
 
 
+_RDF_SHELLS = {}
+
+
 def rdf_from_hist(hist, r_range, nbins=100):
-    lo = torch.tensor(float(r_range[0]), dtype=torch.float32, device=hist.device)
-    hi = torch.tensor(float(r_range[1]), dtype=torch.float32, device=hist.device)
-    shell_rs = torch.linspace(float(lo), float(hi), nbins + 1, dtype=torch.float32, device=hist.device)
-    vis_rs = (shell_rs[1:] + shell_rs[:-1]) * 0.5
-    vols = shell_rs[1:] ** 3 - shell_rs[:-1] ** 3
+    key = (float(r_range[0]), float(r_range[1]), int(nbins), hist.device)
+    cached = _RDF_SHELLS.get(key)
+    if cached is None:                      # shell volumes / bin centres of a range are made once per device
+        shell_rs = torch.linspace(key[0], key[1], nbins + 1, dtype=torch.float32, device=hist.device)
+        vis_rs = (shell_rs[1:] + shell_rs[:-1]) * 0.5
+        vols = shell_rs[1:] ** 3 - shell_rs[:-1] ** 3
+        cached = _RDF_SHELLS[key] = (vols, vis_rs)
+    vols, vis_rs = cached
     return hist[1:-1].to(torch.float32) / vols, vis_rs

@@ -239,12 +239,14 @@ int htf_lj_cv_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, co
  *   htf_mlp_param_sizes  number of fp32 values of the raw parameter blob / bytes of the packed blob
  *   htf_mlp_pack         raw blob, torch.nn.Linear layout  W1[64][32] b1[64] W2[64][64] b2[64] W3[64][64] b3[64]
  *                        w4[64] b4[1]  ->  packed bf16 operand layouts (call again whenever the weights change)
- *   htf_mlp_forces       d_force_energy float[rows][4] = (Fx, Fy, Fz, e_i), overwritten
+ *   htf_mlp_forces       d_force_energy float[rows][4] = (Fx, Fy, Fz, e_i), overwritten.  d_row_count: nullable
+ *                        int32[rows], htf_build_nlist's d_count_out: the compaction of the valid pairs that precedes
+ *                        the kernel on large tensors then reads 4 bytes per row instead of the whole tensor twice
  */
 int htf_mlp_param_sizes(int *raw_count, int *packed_bytes);
 int htf_mlp_pack(htf_ctx *ctx, const float *d_raw, void *d_packed, void *stream);
-int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const void *d_packed, float rbf_high,
-                   float *d_force_energy, void *stream);
+int htf_mlp_forces(htf_ctx *ctx, const float *d_nlist, int64_t rows, int k, const int32_t *d_row_count, const void *d_packed,
+                   float rbf_high, float *d_force_energy, void *stream);
 
 /*
  * Replaces compute_rdf's histogram (htf/simmodel.py:638-669: masked_nlist :672-693, tf.norm,

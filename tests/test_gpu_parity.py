@@ -674,9 +674,16 @@ def test_pairwise_mlp_full_size_slice():
     pos, lo, hi, r_cut, K = synthetic.config("cfg3")
     n = pos.shape[0]
     ctx = _ctx(n, K, r_cut, lo, hi)
-    nl = ctx.build_nlist(torch.from_numpy(pos).cuda())
+    nl, cnt = ctx.build_nlist(torch.from_numpy(pos).cuda(), want_count=True)
     model = htf.models.PairwiseMLPModel(K, r_cut=r_cut, seed=3).cuda()
     fused = model([nl, None], False)[0]
+    # the compaction pre-pass fed by the builder's per-row counts lists the same pairs in the same order
+    packed = ctx.mlp_pack(model.raw_parameters())
+    f_a = ctx.mlp_forces(nl, packed, r_cut)
+    f_b = ctx.mlp_forces(nl, packed, r_cut, counts=cnt)
+    torch.cuda.synchronize()
+    # (rows cut by a 128-pair tile boundary are combined with fp32 atomics: equal up to the order of two additions)
+    assert float((f_a - f_b).abs().max()) <= 1e-5 * float(f_a.abs().max())
     a0 = n // 2
     ref = model([nl[a0:a0 + 4096].contiguous(), None], True)[0].detach()
     torch.cuda.synchronize()
