@@ -57,9 +57,9 @@ def parse():
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--step-length", type=float, default=0.0087,
                     help="displacement per step in the --skin workload (LJ liquid at T*=1, dt=0.005: 0.005*sqrt(3))")
-    ap.add_argument("--counts", action="store_true",
-                    help="the builder writes per-row neighbor counts and the pair pass reads only the valid slots "
-                         "(27 %% less DRAM traffic, no faster: see DESIGN.md)")
+    ap.add_argument("--no-counts", action="store_true",
+                    help="the pair pass reads all K slots of every row (default: the builder hands it per-row neighbor "
+                         "counts and it reads only the valid slots)")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from the host instead of replaying the three CUDA graphs "
                          "(binning | build | forces) the step is captured into")
@@ -415,8 +415,8 @@ def measure(args, env, scaling, full):
         skin_state = {"t": 0, "rebuilds": 0}
 
     # the builder's neighbors-per-row ride along to the pair pass, which then reads only each row's valid slots
-    # (--model mlp always takes them: its compaction pre-pass then reads 4 bytes per row instead of the tensor twice)
-    cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if ((args.counts or args.model == "mlp") and not skin) else None
+    # (--model mlp: its compaction pre-pass then reads 4 bytes per row instead of the tensor twice)
+    cnt = None if (skin or args.no_counts) else torch.empty((rows,), dtype=torch.int32, device=dev)
     if eds_model is not None:
         eds_model.row_counts = cnt
 
