@@ -974,11 +974,9 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? HTF_T2_WARPS2 : 40) / T
     const unsigned rowbytes = (unsigned)K * 16u;
     const bool need_count = p.count_out != nullptr;
     unsigned long long out_lane_a = (unsigned long long)__cvta_generic_to_global(p.out + lane);
-    int count_from = need_count ? 0 : K;                         // rows with at least this many hits report (count / overflow)
     // opaque copies: under the register cap ptxas otherwise re-derives these from tid / the parameters at every use
     asm volatile("mov.u32 %0, %0;" : "+r"(st_lane));
     asm volatile("mov.u64 %0, %0;" : "+l"(out_lane_a));
-    asm volatile("mov.u32 %0, %0;" : "+r"(count_from));
 
     for (int sb = b; sb < e; sb += 32) {
         if (sb != b) {                                          // cells with more than 32 rows (rare): next 32 indices
@@ -989,6 +987,7 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? HTF_T2_WARPS2 : 40) / T
             }
         }
         const int nrow = min(32, e - sb);
+        int my_cnt = 0;                                         // neighbor count of row sb + lane
         unsigned pa = cand_ws + (unsigned)(self_base + sb) * 16u;        // shared address of row sb's own particle
         for (int r0 = 0; r0 < nrow; r0 += 2 * NPB, pa += 32u * NPB) {
             int o[2 * NPB];
@@ -1103,14 +1102,14 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? HTF_T2_WARPS2 : 40) / T
                             if (WITH_IDX) { *idst = valid ? lds_i32(ia) : -1; idst += 32; }
                         }
                     }
-                    if (total >= count_from && lane == 0) {
-                        if (need_count) p.count_out[row] = total;
-                        if (total >= K && p.overflow) atomicMax(p.overflow, total);
-                    }
+                    if (need_count && lane == r0 + 2 * h + r) my_cnt = total;      // stored once per 32 rows of the cell
+                    if (total >= K && lane == 0 && p.overflow) atomicMax(p.overflow, total);
                 }
                 }
             }
         }
+        // the counts of up to 32 rows of the cell in one store instruction
+        if (need_count && my_o >= 0) p.count_out[my_o - p.row_lo] = my_cnt;
     }
 }
 
