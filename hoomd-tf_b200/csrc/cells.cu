@@ -381,7 +381,10 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_scattered);
     const int layer = g.n[0] * g.n[1];
     const int ncell_win = layer * g.zcount;                     // only the cell layers the region of interest touches
-    constexpr int LPC = 8;
+#ifndef HTF_LPC
+#define HTF_LPC 8
+#endif
+    constexpr int LPC = HTF_LPC;
     const int cb = (int)(((long long)ncell_win * LPC + 255) / 256);
     if (ctx->flags & 1 /* HTF_FLAG_DETERMINISTIC */)
         cell_order_gather_kernel<true, LPC><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
