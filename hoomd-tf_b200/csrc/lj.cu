@@ -23,6 +23,10 @@ constexpr int LJ_THREADS = 256;
 #endif
 constexpr int LJ_UNROLL = HTF_LJ_UNROLL;          // independent 16-byte loads in flight per lane
 constexpr int RDF_MAX_BINS = 1024;    // nbins + 2 <= RDF_MAX_BINS (shared-memory histogram)
+#ifndef HTF_HSPLIT
+#define HTF_HSPLIT 2
+#endif
+constexpr int HSPLIT_MAX = HTF_HSPLIT;    // private histograms per warp (power of two), fewer when nbins is large
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
@@ -60,6 +64,7 @@ struct PairParams {
     const int *slot_lo, *slot_hi;
     long long map_row_lo, map_row_hi;
     int blocks_per_sm;         // host only: grid cap of a slab pass
+    int hsplit;                // private histograms per warp (set by the launcher)
 };
 
 template <int LPR, bool FORCES, bool VIRIAL, bool RDF, bool CV>
@@ -78,9 +83,10 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
     unsigned bin0 = 0;                          // lane-private count of bin 0 (padded slots land here)
     double cv_acc = 0.0;                        // CV: coordination numbers of the rows this lane reported
     if (RDF) {
-        my_hist = s_hist + warp * p.nb;
-        s_thr = reinterpret_cast<float *>(s_hist + WARPS * p.nb);
-        for (int q = threadIdx.x; q < WARPS * p.nb; q += LJ_THREADS) s_hist[q] = 0;
+        // HSPLIT private histograms per warp (lane mod HSPLIT): fewer lanes of one atomic instruction on the same bin
+        my_hist = s_hist + (warp * p.hsplit + (lane & (p.hsplit - 1))) * p.nb;
+        s_thr = reinterpret_cast<float *>(s_hist + WARPS * p.hsplit * p.nb);
+        for (int q = threadIdx.x; q < WARPS * p.hsplit * p.nb; q += LJ_THREADS) s_hist[q] = 0;
         for (int q = threadIdx.x; q <= p.nb; q += LJ_THREADS) s_thr[q] = p.thr[q];
         __syncthreads();
     }
@@ -174,9 +180,14 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                 if (RDF) {
                     const int s = s0 + u * LPR;
                     if (row_in_rdf && s < kv) {
-                        float m = 1.0f;
-                        if (p.type_j >= 0) m = (d[u].w == (float)p.type_j) ? 1.0f : 0.0f;
-                        const float x = __fmul_rn(dx, m), y = __fmul_rn(dy, m), z = __fmul_rn(dz, m);
+                        // type filter (masked_nlist): a slot of another type counts with d = 0.  The untyped histogram
+                        // (warp-uniform test) skips the three mask multiplications
+                        const bool typed = p.type_j >= 0;
+                        float m = 1.0f, x = dx, y = dy, z = dz;
+                        if (typed) {
+                            m = (d[u].w == (float)p.type_j) ? 1.0f : 0.0f;
+                            x = __fmul_rn(dx, m); y = __fmul_rn(dy, m); z = __fmul_rn(dz, m);
+                        }
                         const float q = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
                         // first guess from an approximate r (off by far less than a bin), then the exact threshold
                         // table decides: thr[g] <= q < thr[g+1], thr[0] = 0, thr[nb] = +inf, so one step each way is
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
                         if (!FORCES) r_guess = q * rsqrtf(fmaxf(q, 1e-30f));
                         int g = (int)((r_guess - p.r_lo) * p.inv_step);
                         g = max(0, min(p.nb - 1, g));
-                        if (p.type_j >= 0 && m == 0.0f) g = 0;              // masked entry: q = 0 whatever r was
+                        if (typed && m == 0.0f) g = 0;                      // masked entry: q = 0 whatever r was
                         g += (q >= s_thr[g + 1]) ? 1 : 0;
                         g -= (q < s_thr[g]) ? 1 : 0;
                         if (g == 0) bin0++;
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(LJ_THREADS) pair_pass_kernel(const PairParams 
         for (int b = threadIdx.x; b < p.nb; b += LJ_THREADS) {
             unsigned long long t = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; w++) t += (unsigned)s_hist[w * p.nb + b];
+            for (int w = 0; w < WARPS * p.hsplit; w++) t += (unsigned)s_hist[w * p.nb + b];
             if (t) atomicAdd(p.bins + b, t);
         }
     }
@@ -268,7 +279,11 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
 {
     // lanes per row: 8 keeps every warp request on whole 128-byte lines; small K uses fewer
     const int K = p.K;
-    const size_t smem = RDF ? sizeof(int) * ((size_t)(LJ_THREADS / 32) * p.nb + p.nb + 1) : 0;
+    int hs = HSPLIT_MAX;
+    while (hs > 1 && sizeof(int) * ((size_t)(LJ_THREADS / 32) * hs * p.nb + p.nb + 1) > 40 * 1024) hs /= 2;
+    PairParams pp = p;
+    pp.hsplit = hs;
+    const size_t smem = RDF ? sizeof(int) * ((size_t)(LJ_THREADS / 32) * hs * p.nb + p.nb + 1) : 0;
     // 4 lanes per row: a warp request covers 8 rows x 64 B (whole sectors), and the per-warp set-up and the shuffle
     // reductions are shared by 8 rows instead of 4 (measured at 1 M x 64: 0.180 vs 0.197 ms, with the builder's row
     // counts 0.149 vs 0.191 ms; 8 lanes per row can be asked for with HTF_LJ_LPR=8)
@@ -288,10 +303,10 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
         grid = (long long)ctx->sm_count * p.blocks_per_sm;         // slab pass next to a running build: a slice of every SM
     if (grid < 1) grid = 1;
     switch (lpr) {
-    case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    case 4: pair_pass_kernel<4, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    case 2: pair_pass_kernel<2, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
-    default: pair_pass_kernel<1, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(p); break;
+    case 8: pair_pass_kernel<8, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(pp); break;
+    case 4: pair_pass_kernel<4, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(pp); break;
+    case 2: pair_pass_kernel<2, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(pp); break;
+    default: pair_pass_kernel<1, FORCES, VIRIAL, RDF, CV><<<(unsigned)grid, LJ_THREADS, smem, st>>>(pp); break;
     }
     ctx->launches += 1;
     return cudaGetLastError();
