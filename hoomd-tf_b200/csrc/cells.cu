@@ -374,10 +374,17 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     }
     const int pb = (n + 255) / 256;
     cell_count_kernel<<<pb, 256, 0, st>>>(pos, n, g, ctx->d_cell_of, ctx->d_cell_cnt);
-    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums);
-    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
-    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
+    int scan_launches = 3;
+    if (ncell <= 1024 * SCAN1_ITEMS) {
+        // small grids (launch-bound systems): one block scans all the counts
+        scan_one_block_kernel<<<1, 1024, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_cell_start, ctx->d_cell_start + ncell);
+        scan_launches = 1;
+    } else {
+        const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+        scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums);
+        scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(ctx->d_block_sums, ntiles, ctx->d_cell_start + ncell);
+        scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(ctx->d_cell_cnt, ncell, ctx->d_block_sums, ctx->d_cell_start);
+    }
     cell_scatter_kernel<<<pb, 256, 0, st>>>(ctx->d_cell_of, n, ctx->d_cell_start, ctx->d_cell_cnt, ctx->d_scattered);
     const int layer = g.n[0] * g.n[1];
     const int ncell_win = layer * g.zcount;                     // only the cell layers the region of interest touches
@@ -392,7 +399,7 @@ cudaError_t htf_launch_binning(htf_ctx *ctx, const float4 *pos, int64_t n64, cud
     else
         cell_order_gather_kernel<false, LPC><<<cb, 256, 0, st>>>(pos, ctx->d_cell_start, ncell_win, layer, g.z0, g.n[2],
                                                                  ctx->d_scattered, ctx->d_sorted_idx, ctx->d_spos);
-    ctx->launches += 6;
+    ctx->launches += 3 + scan_launches;
     return cudaGetLastError();
 }
 
