@@ -17,7 +17,10 @@
 
 namespace {
 
-constexpr int LJ_THREADS = 256;
+#ifndef HTF_LJ_THREADS
+#define HTF_LJ_THREADS 128      // A/B at 1 M x 64 (4 lanes per row, counts): 64 -> 0.145, 128 -> 0.146, 256 -> 0.150, 512 -> 0.174 ms; 64 loses on the histogram
+#endif
+constexpr int LJ_THREADS = HTF_LJ_THREADS;
 #ifndef HTF_LJ_UNROLL
 #define HTF_LJ_UNROLL 4
 #endif
@@ -295,7 +298,7 @@ cudaError_t launch_pair(htf_ctx *ctx, const PairParams &p, cudaStream_t st)
     const long long groups = (p.rows + rpw - 1) / rpw;
     const long long blocks_needed = (groups + LJ_THREADS / 32 - 1) / (LJ_THREADS / 32);
     long long grid = blocks_needed;
-    const long long persistent = (long long)ctx->sm_count * 8;     // 8 x 256 threads = full occupancy
+    const long long persistent = (long long)ctx->sm_count * (2048 / LJ_THREADS);     // a full complement of threads per SM
     if ((RDF || CV) && grid > persistent) grid = persistent;       // fewer histogram / CV flushes
     // (a one-wave persistent grid for the plain LJ pass, which amortises the ~60 set-up instructions of a warp, was
     // measured: 0.198 ms either way at 1 M x 64, slower without the virial -- not adopted)
