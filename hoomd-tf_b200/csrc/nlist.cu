@@ -45,6 +45,9 @@ namespace {
 #ifndef HTF_T2_WARPS2
 #define HTF_T2_WARPS2 32      // resident warps per SM the two-pair form of the tile kernel is compiled for (63 registers)
 #endif
+#ifndef HTF_T2_STQ
+#define HTF_T2_STQ ".cs"       // cache operator of the tensor stores: streaming (A/B in the step at 1 M x 64: "" 0.5296, ".cs" 0.5266, ".cg" 0.5302, ".wt" 0.5305 ms)
+#endif
 #ifndef HTF_TILE
 #define HTF_TILE 4
 #endif
@@ -1088,7 +1091,7 @@ __global__ void __launch_bounds__(TILE * 32, (NPB == 2 ? HTF_T2_WARPS2 : 40) / T
                                          "setp.lt.s32 p, %2, %3;\n\t"
                                          "mov.f32 x, 0f00000000;\n\tmov.f32 y, 0f00000000;\n\tmov.f32 z, 0f00000000;\n\tmov.f32 w, 0f00000000;\n\t"
                                          "@p ld.shared.v4.f32 {x, y, z, w}, [%1];\n\t"
-                                         "st.global.v4.f32 [%0], {x, y, z, w};\n\t}"
+                                         "st.global" HTF_T2_STQ ".v4.f32 [%0], {x, y, z, w};\n\t}"
                                          :: "l"(dsta + 512ull * i), "r"(st_r + 512u * i), "r"(lane + 32 * i), "r"(nvalid) : "memory");
                     } else {
                         float4 *dst = p.out + (size_t)row * (size_t)K + lane;
