@@ -117,6 +117,17 @@ def ncu_traffic(args, rows, K):
     return None
 
 
+def ncu_force_traffic(args, rows, K, counts):
+    """Same for the LJ forces+virial pass (profiles/pair_pass_traffic.json: taken with the per-row counts)."""
+    path = os.path.join(ROOT, "profiles", "pair_pass_traffic.json")
+    if os.path.exists(path) and args.model == "lj" and not args.rdf:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t.get("rows", -1)) == int(rows) and int(t.get("K", -1)) == int(K) and bool(t.get("counts")) == bool(counts):
+            return t
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 20 ms while the benchmark runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -603,6 +614,7 @@ def measure(args, env, scaling, full):
         achieved = alg_build / (build_ms * 1e-3) / 1e9
         traffic = ncu_traffic(args, rows, K) if (full and not skin) else None
         step_ms = ms / args.steps
+        ftraffic = ncu_force_traffic(args, rows, K, cnt is not None) if (full and not skin) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True,
@@ -623,9 +635,14 @@ def measure(args, env, scaling, full):
                          "path_frac_single_write": (rows * (16 * K + 56)) / (step_ms * 1e-3) / 1e9 / peak,
                          "binning_ms": bin_ms, "force_kernel_ms": force_ms,
                          "force_kernel_frac": rows * (16 * K + 40) / (force_ms * 1e-3) / 1e9 / peak,
+                         "force_kernel_traffic": ftraffic["dram_bytes_per_launch"] if ftraffic else None,
+                         "force_kernel_frac_dram": (ftraffic["dram_bytes_per_launch"] / (force_ms * 1e-3) / 1e9 / peak
+                                                    if ftraffic else None),
                          "force_kernel_note": ("algorithmic bytes (16K+40 per row) over the measured time; the pass gets the "
                                                "builder's per-row counts and reads only the valid slots of each row, so its "
-                                               "DRAM traffic is below the algorithmic figure and the fraction can exceed 1"
+                                               "DRAM traffic is below the algorithmic figure and force_kernel_frac can exceed 1; "
+                                               "force_kernel_frac_dram is the committed ncu capture's DRAM bytes over the "
+                                               "measured time (profiles/pair_pass_traffic.json)"
                                                if cnt is not None else "reads all K slots of every row")},
             "exchange_ms": exchange_ms if world > 1 else 0.0,
             "clocks": clocks, "gpu_launches": launches,

@@ -354,6 +354,8 @@ int htf_create(htf_ctx **out, int device, int64_t n_max, int k, float r_cut, int
     if (!rc) rc = dev_realloc(ctx, &ctx->d_stats, 16);         // [0..2] cell statistics, [6..7] skin status, [8..11] flagged-tile counters
     if (!rc && cudaMemset(ctx->d_stats, 0, 16 * sizeof(int)) != cudaSuccess) rc = HTF_ECUDA;
     if (!rc) ctx->d_flag_count = ctx->d_stats + 8;
+    if (!rc) rc = dev_realloc(ctx, &ctx->d_sel_slots, (size_t)HTF_SEL_MAX_BLOCKS + 2);
+    if (!rc && cudaMemset(ctx->d_sel_slots, 0, (HTF_SEL_MAX_BLOCKS + 2) * sizeof(unsigned long long)) != cudaSuccess) rc = HTF_ECUDA;
     if (rc) { memcpy(g_create_err, ctx->err, sizeof(g_create_err)); htf_destroy(ctx); return rc; }
     *out = ctx;
     return HTF_OK;
@@ -366,7 +368,7 @@ void htf_destroy(htf_ctx *ctx)
     if (ctx->skin_ctx) { htf_destroy(ctx->skin_ctx); ctx->skin_ctx = nullptr; }
     void *ptrs[] = {ctx->d_skin_cand, ctx->d_skin_count, ctx->d_skin_ref, ctx->d_cell_cnt, ctx->d_cell_start, ctx->d_block_sums, ctx->d_cell_of, ctx->d_sorted_idx, ctx->d_scattered,
                     ctx->d_spos, ctx->d_nlist_scratch, ctx->d_row_count, ctx->d_rdf_thr, ctx->d_tile_flag, ctx->d_stats,
-                    ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums, ctx->d_train_packed, ctx->d_train_pred,
+                    ctx->d_sel_cnt, ctx->d_sel_off, ctx->d_sel_sums, ctx->d_sel_slots, ctx->d_train_packed, ctx->d_train_pred,
                     ctx->d_train_partial, ctx->d_train_loss_partial, ctx->d_mlp_pairs, ctx->d_mlp_blk};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
         if (!ptrs[i]) continue;

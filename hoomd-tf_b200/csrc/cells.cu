@@ -353,6 +353,124 @@ __global__ void __launch_bounds__(256) select_scatter2_kernel(const float4 *__re
     }
 }
 
+// ---- the same compaction of both faces as ONE launch (instead of count + scan + scatter) ----
+// A grid of 2 blocks per SM, all co-resident.  Warp w of block b owns the contiguous particles
+// [(8 b + w) * items * 32, +items * 32) and keeps them IN REGISTERS (items <= IMAX, all loads of a thread in flight at
+// once; a first version that re-read the selected particles iteration by iteration took 17 us because the blocks at
+// the two ends of a spatially sorted slab hold nothing but face particles).  A block publishes its two counts as ONE
+// 64-bit word tagged with the launch epoch (so the slots never have to be cleared), one warp reads the words of all
+// blocks (spinning on the tag: every block of the grid is resident and publishes before it waits), and the block
+// stores its selected particles at the prefix.  Order = index order, exactly as the three-kernel form.
+template <int IMAX>
+__global__ void __launch_bounds__(256, 2) select_fused2_kernel(const float4 *__restrict__ pos, int n, int axis, float thr_lo,
+                                                               float thr_hi, int items, unsigned long long *slots,
+                                                               unsigned *ctl /* [0] epoch, [1] blocks done */,
+                                                               float4 *__restrict__ out_lo, float4 *__restrict__ out_hi, int cap,
+                                                               int *__restrict__ counts, int *__restrict__ overflow,
+                                                               const HtfHaloDst *dst)
+{
+    __shared__ int wsum[16];
+    __shared__ int red[4];
+    __shared__ int red4[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned e = *reinterpret_cast<volatile unsigned *>(&ctl[0]);
+    const unsigned tag = e + 1u;
+    if (dst) {
+        const int par = (int)(*reinterpret_cast<const volatile unsigned long long *>(&dst->epoch) & 1ull);
+        out_lo = dst->lo[par];
+        out_hi = dst->hi[par];
+    }
+    const long long base = ((long long)blockIdx.x * 8 + w) * items * 32 + lane;
+    float4 p[IMAX];
+#pragma unroll
+    for (int it = 0; it < IMAX; it++) {
+        const long long i = base + it * 32;
+        // a particle that is in neither face (coordinate 0 lies between the thresholds only by luck: use a flag value)
+        p[it] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00001));
+        if (it < items && i < n) p[it] = __ldg(pos + i);
+    }
+    int cl = 0, ch = 0;
+#pragma unroll
+    for (int it = 0; it < IMAX; it++) {
+        const bool valid = __float_as_int(p[it].w) != 0x7fc00001;
+        const float v = axis == 0 ? p[it].x : (axis == 1 ? p[it].y : p[it].z);
+        cl += __popc(__ballot_sync(HTF_FULL, valid && v < thr_lo));
+        ch += __popc(__ballot_sync(HTF_FULL, valid && v > thr_hi));
+    }
+    if (lane == 0) { wsum[w] = cl; wsum[8 + w] = ch; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int bl = 0, bh = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { bl += wsum[q]; bh += wsum[8 + q]; }
+        *reinterpret_cast<volatile unsigned long long *>(&slots[blockIdx.x]) =
+            ((unsigned long long)tag << 32) | ((unsigned long long)(unsigned)bh << 16) | (unsigned long long)(unsigned)bl;
+    }
+    // counts of every block: prefix over the lower blocks and the grand totals.  Every thread polls at most
+    // ceil(grid / 256) slots, so the block pays one or two L2 round trips (one warp walking all slots: ten)
+    {
+        int pl = 0, ph = 0, tl = 0, th = 0;
+        for (int t = threadIdx.x; t < (int)gridDim.x; t += 256) {
+            unsigned long long v;
+            do {
+                v = *reinterpret_cast<volatile unsigned long long *>(&slots[t]);
+            } while ((unsigned)(v >> 32) != tag);
+            const int a = (int)(v & 0xffffull), b = (int)((v >> 16) & 0xffffull);
+            tl += a; th += b;
+            if (t < (int)blockIdx.x) { pl += a; ph += b; }
+        }
+        pl = __reduce_add_sync(HTF_FULL, pl); ph = __reduce_add_sync(HTF_FULL, ph);
+        tl = __reduce_add_sync(HTF_FULL, tl); th = __reduce_add_sync(HTF_FULL, th);
+        if (lane == 0) { red4[4 * w] = pl; red4[4 * w + 1] = ph; red4[4 * w + 2] = tl; red4[4 * w + 3] = th; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int t = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += red4[4 * q + threadIdx.x];
+        red[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int tl = red[2], th = red[3];
+    int ol = red[0], oh = red[1];
+    if (threadIdx.x == 0) {
+        // every block reads the epoch before it gets here: the last one advances it for the next launch
+        __threadfence();
+        if (atomicAdd(&ctl[1], 1u) == gridDim.x - 1u) {
+            ctl[1] = 0u;
+            __threadfence();
+            ctl[0] = tag;
+        }
+        if (blockIdx.x == 0 && counts) { counts[0] = tl; counts[1] = th; }
+    }
+    for (int q = 0; q < w; q++) { ol += wsum[q]; oh += wsum[8 + q]; }
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < IMAX; it++) {
+        const bool valid = __float_as_int(p[it].w) != 0x7fc00001;
+        const float v = axis == 0 ? p[it].x : (axis == 1 ? p[it].y : p[it].z);
+        const bool sl = valid && v < thr_lo, sh = valid && v > thr_hi;
+        const unsigned ml = __ballot_sync(HTF_FULL, sl), mh = __ballot_sync(HTF_FULL, sh);
+        if (sl) {
+            const int k = ol + __popc(ml & below);
+            if (k < cap) out_lo[k] = p[it];
+            else if (overflow) atomicMax(overflow, k + 1);
+        }
+        if (sh) {
+            const int k = oh + __popc(mh & below);
+            if (k < cap) out_hi[k] = p[it];
+            else if (overflow) atomicMax(overflow, k + 1);
+        }
+        ol += __popc(ml);
+        oh += __popc(mh);
+    }
+    // sentinel padding behind the two faces
+    const float4 far = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+    const int gt = blockIdx.x * 256 + threadIdx.x, gs = gridDim.x * 256;
+    for (int i = tl + gt; i < cap; i += gs) out_lo[i] = far;
+    for (int i = th + gt; i < cap; i += gs) out_hi[i] = far;
+}
+
 __global__ void __launch_bounds__(256) fill_sentinel_kernel(float4 *__restrict__ out, int cap)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -432,6 +550,29 @@ cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64,
 {
     const int n = (int)n64;
     const int nb = (n + 255) / 256;
+    {
+        // HTF_SELECT_FUSED=1: one launch instead of three (14.1 vs 18.5 us at 1 M rows).  Not the default: its blocks
+        // wait for each other, which is only safe while all 2 x SM-count blocks are resident together (not under an
+        // MPS / green-context SM limit), and 4 us per step do not pay for that condition.
+        const char *fe = getenv("HTF_SELECT_FUSED");
+        const bool fused_on = fe && fe[0] == '1';
+        const int g = max(1, min(min(2 * ctx->sm_count, HTF_SEL_MAX_BLOCKS), nb));
+        const int items = (int)((n64 + (int64_t)g * 256 - 1) / ((int64_t)g * 256));
+        if (fused_on && ctx->d_sel_slots && items <= 24) {
+            unsigned *ctl = reinterpret_cast<unsigned *>(ctx->d_sel_slots + HTF_SEL_MAX_BLOCKS);
+            if (items <= 8)
+                select_fused2_kernel<8><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
+                                                           out_hi, cap, d_counts, d_overflow, dst);
+            else if (items <= 16)
+                select_fused2_kernel<16><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
+                                                            out_hi, cap, d_counts, d_overflow, dst);
+            else
+                select_fused2_kernel<24><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
+                                                            out_hi, cap, d_counts, d_overflow, dst);
+            ctx->launches += 1;
+            return cudaGetLastError();
+        }
+    }
     int *cnt = ctx->d_sel_cnt, *off = ctx->d_sel_off, *sums = ctx->d_sel_sums;
     if (nb > 0) select_count2_kernel<<<nb, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, nb, cnt);
     const int m = 2 * nb + 1;                                   // one extra (zero) entry so that off[2 nb] exists

@@ -26,6 +26,8 @@ struct CellGrid {
 
 struct HtfComm;
 
+constexpr int HTF_SEL_MAX_BLOCKS = 1024;     // grid limit of the one-launch halo selection (select_fused2_kernel)
+
 struct htf_ctx {
     int device;
     int sm_count;
@@ -54,6 +56,7 @@ struct htf_ctx {
     double calib_cell_mean;       // particles per occupied cell
     int *d_sel_cnt, *d_sel_off, *d_sel_sums;   // halo selection scratch (per 256-particle block)
     int64_t sel_cap;
+    unsigned long long *d_sel_slots;   // [HTF_SEL_MAX_BLOCKS] tagged per-block counts of the one-launch selection + [1] epoch / done counter
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
     int tile_flag_cap;
     int *d_flag_count;            // per build lane two counters (inside d_stats) of tiles the tile kernel flagged, used in turn

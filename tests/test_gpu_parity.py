@@ -552,6 +552,38 @@ def test_slab_halo_exchange_emulated(oracle_mod):
         assert np.array_equal(canon(nl.cpu().numpy()).view(np.uint32), canon(full[a:b]).view(np.uint32)), r
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("n", [1, 31, 257, 70001, 1048576, 2400000])
+def test_pack_halo_pair_sizes_and_replays(n, fused, monkeypatch):
+    """the two-face packer -- the three-kernel form and the opt-in one-launch form (HTF_SELECT_FUSED=1,
+    select_fused2_kernel; above 24 particles per thread it falls back) -- against a boolean-mask selection in index
+    order, called repeatedly (the epoch-tagged block counts of the one-launch form are never cleared) and with
+    capacities below and above the face sizes."""
+    import htf
+    monkeypatch.setenv("HTF_SELECT_FUSED", fused)
+    g = torch.Generator(device="cpu").manual_seed(n)
+    pos = (torch.rand((n, 4), generator=g) * 10.0 - 5.0).cuda()
+    ctx = htf.HtfContext(max(n, 1), 8, 1.0)
+    ctx.set_box((-5.0, -5.0, -5.0), (5.0, 5.0, 5.0))
+    for rep, (axis, t_lo, t_hi) in enumerate([(2, -4.0, 4.2), (0, -4.9, 4.99), (1, -5.5, 5.5), (2, -4.0, 4.2)]):
+        want_lo, want_hi = pos[pos[:, axis] < t_lo], pos[pos[:, axis] > t_hi]
+        cap = max(int(max(len(want_lo), len(want_hi))) + 5 + 300 * (rep & 1), 1)
+        out_lo, out_hi = torch.zeros((cap, 4), device="cuda"), torch.zeros((cap, 4), device="cuda")
+        counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+        ctx.pack_halo_pair(pos, axis, t_lo, t_hi, out_lo, out_hi, counts)
+        assert ctx.overflow() == 0
+        assert counts.tolist() == [len(want_lo), len(want_hi)]
+        assert torch.equal(out_lo[:len(want_lo)], want_lo) and torch.equal(out_hi[:len(want_hi)], want_hi)
+        assert bool((out_lo[len(want_lo):, :3] > 1e29).all()) and bool((out_hi[len(want_hi):, :3] > 1e29).all())
+    # a capacity below the face size raises the overflow flag and keeps the first `cap` selected particles
+    want_lo = pos[pos[:, 2] < 0.0]
+    if len(want_lo) > 4:
+        cap = len(want_lo) // 2
+        out_lo, out_hi = torch.zeros((cap, 4), device="cuda"), torch.zeros((cap, 4), device="cuda")
+        ctx.pack_halo_pair(pos, 2, 0.0, 6.0, out_lo, out_hi)
+        assert torch.equal(out_lo, want_lo[:cap]) and ctx.overflow() >= len(want_lo)
+
+
 def test_coordination_cv_fused_pass(oracle_mod):
     """fused LJ + coordination CV (+RDF) pass vs the oracle and vs torch autograd of the same CV (config 5 model)."""
     from htf import synthetic
