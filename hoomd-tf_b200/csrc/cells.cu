@@ -358,9 +358,10 @@ __global__ void __launch_bounds__(256) select_scatter2_kernel(const float4 *__re
 // [(8 b + w) * items * 32, +items * 32) and keeps them IN REGISTERS (items <= IMAX, all loads of a thread in flight at
 // once; a first version that re-read the selected particles iteration by iteration took 17 us because the blocks at
 // the two ends of a spatially sorted slab hold nothing but face particles).  A block publishes its two counts as ONE
-// 64-bit word tagged with the launch epoch (so the slots never have to be cleared), one warp reads the words of all
-// blocks (spinning on the tag: every block of the grid is resident and publishes before it waits), and the block
-// stores its selected particles at the prefix.  Order = index order, exactly as the three-kernel form.
+// 64-bit word tagged with the launch epoch (so the slots never have to be cleared), its threads read the words of all
+// blocks (spinning on the tag: the launch is COOPERATIVE, so every block of the grid is resident, and a block publishes
+// before it waits), and the block stores its selected particles at the prefix.  Order = index order, exactly as the
+// three-kernel form.
 template <int IMAX>
 __global__ void __launch_bounds__(256, 2) select_fused2_kernel(const float4 *__restrict__ pos, int n, int axis, float thr_lo,
                                                                float thr_hi, int items, unsigned long long *slots,
@@ -551,26 +552,42 @@ cudaError_t htf_launch_select_pair(htf_ctx *ctx, const float4 *pos, int64_t n64,
     const int n = (int)n64;
     const int nb = (n + 255) / 256;
     {
-        // HTF_SELECT_FUSED=1: one launch instead of three (14.1 vs 18.5 us at 1 M rows).  Not the default: its blocks
-        // wait for each other, which is only safe while all 2 x SM-count blocks are resident together (not under an
-        // MPS / green-context SM limit), and 4 us per step do not pay for that condition.
+        // One launch instead of three (exchange 45.5 -> 35.0 us per step at 2 x 1 M rows).  Its blocks wait for each other,
+        // so it goes out as a COOPERATIVE launch: the driver either places all blocks together or refuses, and a refusal
+        // (SM-limited context, another resident kernel) falls back to the three-kernel form for good.
+        // HTF_SELECT_FUSED=0 selects the three-kernel form.
         const char *fe = getenv("HTF_SELECT_FUSED");
-        const bool fused_on = fe && fe[0] == '1';
+        const bool fused_on = !(fe && fe[0] == '0') && !ctx->sel_fused_refused;
         const int g = max(1, min(min(2 * ctx->sm_count, HTF_SEL_MAX_BLOCKS), nb));
         const int items = (int)((n64 + (int64_t)g * 256 - 1) / ((int64_t)g * 256));
         if (fused_on && ctx->d_sel_slots && items <= 24) {
             unsigned *ctl = reinterpret_cast<unsigned *>(ctx->d_sel_slots + HTF_SEL_MAX_BLOCKS);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            unsigned long long *slots = ctx->d_sel_slots;
+            cudaError_t e;
             if (items <= 8)
-                select_fused2_kernel<8><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
-                                                           out_hi, cap, d_counts, d_overflow, dst);
+                e = cudaLaunchKernelEx(&cfg, select_fused2_kernel<8>, pos, n, axis, thr_lo, thr_hi, items, slots, ctl, out_lo,
+                                       out_hi, cap, d_counts, d_overflow, dst);
             else if (items <= 16)
-                select_fused2_kernel<16><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
-                                                            out_hi, cap, d_counts, d_overflow, dst);
+                e = cudaLaunchKernelEx(&cfg, select_fused2_kernel<16>, pos, n, axis, thr_lo, thr_hi, items, slots, ctl, out_lo,
+                                       out_hi, cap, d_counts, d_overflow, dst);
             else
-                select_fused2_kernel<24><<<g, 256, 0, st>>>(pos, n, axis, thr_lo, thr_hi, items, ctx->d_sel_slots, ctl, out_lo,
-                                                            out_hi, cap, d_counts, d_overflow, dst);
-            ctx->launches += 1;
-            return cudaGetLastError();
+                e = cudaLaunchKernelEx(&cfg, select_fused2_kernel<24>, pos, n, axis, thr_lo, thr_hi, items, slots, ctl, out_lo,
+                                       out_hi, cap, d_counts, d_overflow, dst);
+            if (e == cudaSuccess) {
+                ctx->launches += 1;
+                return cudaSuccess;
+            }
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            if (cs != cudaStreamCaptureStatusNone) return e;          // a failed launch has already broken the capture
+            (void)cudaGetLastError();
+            ctx->sel_fused_refused = true;
         }
     }
     int *cnt = ctx->d_sel_cnt, *off = ctx->d_sel_off, *sums = ctx->d_sel_sums;

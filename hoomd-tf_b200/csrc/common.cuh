@@ -56,6 +56,7 @@ struct htf_ctx {
     double calib_cell_mean;       // particles per occupied cell
     int *d_sel_cnt, *d_sel_off, *d_sel_sums;   // halo selection scratch (per 256-particle block)
     int64_t sel_cap;
+    bool sel_fused_refused;            // the driver refused the cooperative launch of select_fused2_kernel once: three-kernel form from then on
     unsigned long long *d_sel_slots;   // [HTF_SEL_MAX_BLOCKS] tagged per-block counts of the one-launch selection + [1] epoch / done counter
     unsigned char *d_tile_flag;   // [tiles] written by the tile kernel, read by the per-cell kernel
     int tile_flag_cap;

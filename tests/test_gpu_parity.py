@@ -555,8 +555,8 @@ def test_slab_halo_exchange_emulated(oracle_mod):
 @pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("n", [1, 31, 257, 70001, 1048576, 2400000])
 def test_pack_halo_pair_sizes_and_replays(n, fused, monkeypatch):
-    """the two-face packer -- the three-kernel form and the opt-in one-launch form (HTF_SELECT_FUSED=1,
-    select_fused2_kernel; above 24 particles per thread it falls back) -- against a boolean-mask selection in index
+    """the two-face packer -- the one-launch form (select_fused2_kernel, cooperative launch; above 24 particles per
+    thread it falls back) and the three-kernel form (HTF_SELECT_FUSED=0) -- against a boolean-mask selection in index
     order, called repeatedly (the epoch-tagged block counts of the one-launch form are never cleared) and with
     capacities below and above the face sizes."""
     import htf
