@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from the host instead of replaying the three CUDA graphs "
                          "(binning | build | forces) the step is captured into")
+    ap.add_argument("--phase-every", type=int, default=10,
+                    help="every n-th step of the timed region runs phase by phase (one graph per phase, CUDA events between: "
+                         "the per-kernel times of the roofline block); the other steps are one graph replay. 1 = every step")
     ap.add_argument("--rdf", action="store_true", help="fuse the 100-bin compute_rdf histogram into the force pass")
     ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
                     help="N>1: slab halo exchange (send/recv of the two faces) or all-gather of every position")
@@ -330,7 +333,7 @@ def run_b200(args):
     if world > 1 and args.scaling in ("both", "strong") and args.skin <= 0.0:
         st = measure(args, env, "strong", full=False)      # the named size itself, split over the GPUs
         if rank == 0:
-            line["strong"] = {k: st[k] for k in ("value", "ms_per_step", "exchange_ms", "exchange", "parity", "config") if k in st}
+            line["strong"] = {k: st[k] for k in ("value", "ms_per_step", "exchange_ms", "per_rank", "exchange", "parity", "config") if k in st}
             line["strong"]["efficiency_inputs"] = {
                 "particles": st["config"]["particles"], "n_gpus": world, "ms_per_step": st["ms_per_step"],
                 "note": "strong-scaling efficiency = value(N) / (N x value(1)) with value(1) from the --gpus 1 line"}
@@ -511,6 +514,7 @@ def measure(args, env, scaling, full):
     # ---- the step's phases captured into CUDA graphs (same kernels, same stream order; the events between the
     #      phases stay live).  Binning alone is six dependent launches of a few microseconds.  NCCL stays eager. ----
     graphs = None
+    step_graph = None
     launches_per_step = None
     eager_force = eds_model is not None or (bins is not None and world > 1 and not p2p) or \
         (train is not None and world > 1 and not p2p)              # host-side collectives / metric updates
@@ -535,8 +539,20 @@ def measure(args, env, scaling, full):
                 fn()
             graphs.append(g_)
         launches_per_step = ctx.launches - l0
+        # ... and the whole step as ONE graph (same kernels, same order) when nothing in it needs the host: the five
+        # event records and the graph boundaries of the phase-by-phase form cost 14 + 4 us per step (tools/graph_gap_time.py),
+        # so only every --phase-every-th step of the timed region runs phase by phase with the events between
+        if not eager_force and (not halo or p2p) and args.phase_every != 1:
+            step_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(step_graph, stream=side):
+                if halo:
+                    xch.pack()
+                phase_bin(); phase_build(); phase_force()
 
         def step(marks=None):                                   # noqa: F811 -- the graph replay of the same step
+            if marks is None and step_graph is not None:
+                step_graph.replay()
+                return
             if marks is not None:
                 marks[0].record()
             if pack_graph is not None:
@@ -571,7 +587,8 @@ def measure(args, env, scaling, full):
     assert ctx.overflow() == 0, "neighbor list overflowed K: the run is void"
 
     # ---- timed region: exactly --steps steps, device timed, clocks sampled meanwhile ----
-    marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
+    every = max(1, args.phase_every) if step_graph is not None else 1
+    marks = [[ev() for _ in range(5)] if i % every == 0 else None for i in range(args.steps)]
     skin_t0 = skin_state["t"] if skin else 0
     line0 = sampler.lines() if sampler else 0
     launches0 = ctx.launches
@@ -592,8 +609,18 @@ def measure(args, env, scaling, full):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    phase = lambda a, b: float(np.mean([m[a].elapsed_time(m[b]) for m in marks]))
+    phase = lambda a, b: float(np.mean([m[a].elapsed_time(m[b]) for m in marks if m is not None]))
     exchange_ms, bin_ms, build_ms, force_ms = phase(0, 1), phase(1, 2), phase(2, 3), phase(3, 4)
+    per_rank = None
+    if world > 1:
+        # every rank's own phase times: a rank waits for both neighbours inside its exchange phase, so the rank with the
+        # longest compute phases shows the shortest exchange and sets the pace of all
+        mine = {"exchange_ms": round(exchange_ms, 5), "compute_ms": round(bin_ms + build_ms + force_ms, 5)}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        per_rank = {"exchange_ms": [r_["exchange_ms"] for r_ in allr], "compute_ms": [r_["compute_ms"] for r_ in allr],
+                    "what": "per rank: exchange phase (pack + signal + wait for both neighbours + gather) and "
+                            "binning + build + forces, CUDA events, mean over the timed steps"}
     value = n * args.steps / (ms * 1e-3)
 
     # ---- parity leg (outside the timed region; the oracle is the checker, never the thing measured) ----
@@ -645,8 +672,13 @@ def measure(args, env, scaling, full):
                                                "measured time (profiles/pair_pass_traffic.json)"
                                                if cnt is not None else "reads all K slots of every row")},
             "exchange_ms": exchange_ms if world > 1 else 0.0,
+            "per_rank": per_rank,
             "clocks": clocks, "gpu_launches": launches,
-            "launch": ("%d CUDA graphs per step (%sbinning | build%s), %d kernels"
+            "launch": (("1 CUDA graph per step (%sbinning, build, forces: %d kernels); every %d-th step of the timed region "
+                        "runs as %d graphs with CUDA event records between the phases (the phase times of this record)"
+                        % ("halo exchange, " if halo else "", launches_per_step, every, len(graphs) + (1 if halo else 0)))
+                       if step_graph is not None else
+                       "%d CUDA graphs per step (%sbinning | build%s), %d kernels"
                        % (len(graphs) + (1 if halo else 0), "halo packing | " if halo else "",
                           "" if eager_force else " | forces", launches_per_step)
                        if graphs is not None else "stream launches from the host"),
