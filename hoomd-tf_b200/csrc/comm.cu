@@ -5,11 +5,12 @@
 // Here one process drives one GPU; every rank owns a "window" (one cudaMalloc, exported with cudaIpcGetMemHandle)
 // that its peers map with cudaIpcOpenMemHandle.  The per-step traffic never touches the host and needs no NCCL:
 //
-//   halo exchange   the stable compaction of the two slab faces (select_scatter2_kernel, cells.cu) writes the faces
+//   halo exchange   the stable compaction of the two slab faces (select_fused2_kernel, cells.cu) writes the faces
 //                   STRAIGHT INTO the neighbours' windows (fused pack + send); the gather kernel then publishes the
 //                   epoch to the neighbours' flags (release, system scope), waits for both own flags (acquire) and
 //                   copies the received faces behind the rank's own rows, where the binning expects them.
-//                   Four launches in all: count, one-block scan, scatter-to-peer, signal + wait + gather.
+//                   Two launches in all: the one-launch compaction (select_fused2_kernel, cooperative; count + one-block
+//                   scan + scatter-to-peer when it cannot be used) and signal + wait + gather.
 //   all-reduce      every rank stores its (small) vector into every peer's window, publishes the epoch, waits for all
 //                   contributions and sums them in rank order -- the same bits on every rank, int64 or fp64.
 //
